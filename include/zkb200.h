@@ -1,0 +1,145 @@
+/* zkb200.h -- C ABI of libzkb200.so: the B200 (sm_100a) back end for zksnake's proving hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one call the reference makes from its pyo3 extension
+ * module `zksnake._algebra` into arkworks (reference paths are relative to /root/reference):
+ *
+ *   zkb_ntt / zkb_ntt_dev            src/bn254/polynomial.rs:536-545 fft, :548-559 coset_fft, :562-571 ifft,
+ *                                    :574-585 coset_ifft            (src/bls12_381/polynomial.rs: same lines)
+ *   zkb_vec_op / zkb_vec_op_dev      src/bn254/polynomial.rs:588-607 add_over_evaluation_domain,
+ *                                    :610-634 mul_over_evaluation_domain
+ *   zkb_fr_reduce                    the `Fr::from(BigUint)` loops, e.g. src/bn254/polynomial.rs:537-540
+ *   zkb_msm / zkb_msm_dev            src/bn254/curve.rs:356-373 multiscalar_mul_g1, :375-392 multiscalar_mul_g2
+ *                                    (src/bls12_381/curve.rs:367-384, :386-403)
+ *   zkb_batch_mul_dev                src/bn254/curve.rs:326-354 batch_multi_scalar_g1/g2 (setup side)
+ *   zkb_groth16_h / _h_dev           python/zksnake/groth16/qap.py:42-71 QAP.evaluate_witness (after the A.w/B.w/C.w dots)
+ *   zkb_groth16_pk_* / _prove        python/zksnake/groth16/protocol.py:115-165 Groth16.prove
+ *
+ * Conventions
+ *   - curve: ZKB_BN254 (0) or ZKB_BLS12_381 (1); group: 1 = G1, 2 = G2.
+ *   - Fr elements on the wire: 4 x uint64 little-endian limbs, canonical (non-Montgomery).  Values >= r are accepted
+ *     wherever the reference accepts arbitrary non-negative ints and are reduced mod r (Fr::from(BigUint)).
+ *   - Fq elements: 4 x uint64 (BN254) / 6 x uint64 (BLS12-381), canonical.  G1 affine = (x, y); G2 affine =
+ *     (x.c0, x.c1, y.c0, y.c1).  The point at infinity is the all-zero coordinate tuple (0,0 is on neither curve).
+ *   - "_dev" entry points take device pointers (from zkb_dev_alloc or any CUDA allocation of the same process) and
+ *     are asynchronous on the library stream unless they return host data.  Device point vectors are kept in
+ *     Montgomery form (zkb_points_upload / zkb_points_download convert); device Fr vectors are canonical.
+ *   - Return value: 0 on success, a negative ZKB_ERR_* code otherwise; zkb_last_error() gives the text.  The host
+ *     binding maps codes to the reference's exception types.
+ *   - No exceptions and no allocator ownership cross this boundary: callers allocate outputs.
+ *   - There is NO CPU fallback: every compute entry point fails with ZKB_ERR_NOINIT / ZKB_ERR_CUDA without a B200.
+ */
+#ifndef ZKB200_H
+#define ZKB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKB_BN254 0
+#define ZKB_BLS12_381 1
+
+#define ZKB_OK 0
+#define ZKB_ERR_CUDA (-1)          /* CUDA failure or no usable device            -> RuntimeError */
+#define ZKB_ERR_ARG (-2)           /* bad argument                                -> ValueError   */
+#define ZKB_ERR_MISMATCH (-3)      /* "Number of points and scalars mismatch"     -> ValueError   (curve.rs:369-371) */
+#define ZKB_ERR_DOMAIN (-4)        /* "Domain size is too large"                  -> ValueError   (polynomial.rs:638-639) */
+#define ZKB_ERR_NOT_DIVISIBLE (-5) /* "(U * V - W) did not divided by Z to zero"  -> ValueError   (qap.py:68-69) */
+#define ZKB_ERR_NOINIT (-6)        /* zkb_init not called                         -> RuntimeError */
+
+#define ZKB_VEC_MUL 0
+#define ZKB_VEC_ADD 1
+#define ZKB_VEC_SUB 2
+
+/* ---- context ---------------------------------------------------------------------------------------------- */
+int zkb_device_count(void);
+int zkb_init(int device);                 /* binds this process to one GPU (one process per GPU) */
+void zkb_shutdown(void);
+const char* zkb_last_error(void);
+void* zkb_stream(void);                   /* the cudaStream_t all work is issued on */
+int zkb_sync(void);
+unsigned long long zkb_launch_count(void); /* kernels launched by this library so far */
+int zkb_timer_start(void);                /* CUDA events on the library stream */
+int zkb_timer_stop(float* ms);
+
+/* ---- raw memory ------------------------------------------------------------------------------------------- */
+int zkb_dev_alloc(size_t bytes, void** out);
+int zkb_dev_free(void* p);
+int zkb_host_alloc(size_t bytes, void** out);   /* pinned */
+int zkb_host_free(void* p);
+int zkb_h2d(void* dst, const void* src, size_t bytes);
+int zkb_d2h(void* dst, const void* src, size_t bytes);
+int zkb_d2d(void* dst, const void* src, size_t bytes);
+int zkb_memset(void* dst, int value, size_t bytes);
+
+/* ---- Fr vectors ------------------------------------------------------------------------------------------- */
+/* N = 2^log_n.  in_len <= any; inputs are zero-padded or truncated to N.  coset: 0 = plain, 1 = the reference's
+ * coset (offset = generator of the size-N domain).  out holds N elements. */
+int zkb_ntt(int curve, int inverse, int coset, uint32_t log_n, const uint64_t* in, size_t in_len, uint64_t* out);
+int zkb_ntt_dev(int curve, int inverse, int coset, uint32_t log_n, const void* d_in, size_t in_len, void* d_out);
+/* out[i] = a[i] op b[i] for i < n; a / b shorter than n are zero-extended (mul_over_evaluation_domain semantics). */
+int zkb_vec_op(int curve, int op, size_t n, const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* out);
+int zkb_vec_op_dev(int curve, int op, size_t n, const void* d_a, size_t na, const void* d_b, size_t nb, void* d_out);
+int zkb_fr_reduce(int curve, size_t n, uint64_t* inout);            /* arbitrary 256-bit values -> mod r */
+int zkb_fr_reduce_dev(int curve, size_t n, void* d_inout);
+int zkb_fr_powers_dev(int curve, const uint64_t base[4], const uint64_t scale[4], size_t n, void* d_out); /* scale*base^i */
+
+/* ---- points and MSM --------------------------------------------------------------------------------------- */
+size_t zkb_affine_bytes(int curve, int group);
+int zkb_points_upload(int curve, int group, const uint64_t* pts, size_t n, void* d_out);    /* canonical -> device Montgomery */
+int zkb_points_download(int curve, int group, const void* d_pts, size_t n, uint64_t* out);  /* device Montgomery -> canonical */
+/* sum_i scalars[i] * pts[i].  n_points must equal n_scalars (else ZKB_ERR_MISMATCH).  out_xy: one affine point. */
+int zkb_msm(int curve, int group, const uint64_t* pts, size_t n_points, const uint64_t* scalars, size_t n_scalars,
+            uint64_t* out_xy, int* out_inf);
+int zkb_msm_dev(int curve, int group, const void* d_pts, const void* d_scalars, size_t n, uint64_t* out_xy, int* out_inf);
+/* d_out[i] = scalars[i] * bases[single_base ? 0 : i]  (device Montgomery points in and out) */
+int zkb_batch_mul_dev(int curve, int group, const void* d_bases, int single_base, const void* d_scalars, size_t n,
+                      void* d_out);
+void zkb_msm_set_tuning(int window_bits, int segment, int reduce_chunk);  /* 0 = heuristic */
+
+/* ---- Groth16 ---------------------------------------------------------------------------------------------- */
+/* a, b, c: the vectors A.w, B.w, C.w (n = 2^log_n each).  u, v, w, h receive n coefficients each (h[n-1] = 0).
+ * Returns ZKB_ERR_NOT_DIVISIBLE when a[i]*b[i] != c[i] somewhere (the reference's non-zero remainder). */
+int zkb_groth16_h(int curve, uint32_t log_n, const uint64_t* a, const uint64_t* b, const uint64_t* c, uint64_t* u,
+                  uint64_t* v, uint64_t* w, uint64_t* h);
+int zkb_groth16_h_dev(int curve, uint32_t log_n, const void* d_a, const void* d_b, const void* d_c, void* d_u, void* d_v,
+                      void* d_w, void* d_h, int check);
+
+/* Device-resident proving key (ProvingKey of python/zksnake/groth16/serialization.py:45-66).  The four point vectors are
+ * device Montgomery buffers the key takes a reference to (the caller keeps ownership and must keep them alive);
+ * the five single points are canonical host coordinates. */
+typedef struct zkb_groth16_pk zkb_groth16_pk;
+int zkb_groth16_pk_create(int curve, uint32_t log_n, const void* d_tau1, const void* d_tau2, const void* d_target1,
+                          const void* d_kdelta1, size_t n_kdelta, const uint64_t* alpha1, const uint64_t* beta1,
+                          const uint64_t* beta2, const uint64_t* delta1, const uint64_t* delta2, zkb_groth16_pk** out);
+void zkb_groth16_pk_free(zkb_groth16_pk* pk);
+/* Groth16.prove from host buffers: a, b, c = A.w, B.w, C.w (n each), priv = private witness (n_kdelta scalars), r, s = the
+ * prover's randomness.  Outputs canonical affine A (G1), B (G2), C (G1) and their infinity flags.  The timed e2e region of
+ * bench.py is exactly one call of this function. */
+int zkb_groth16_prove(zkb_groth16_pk* pk, const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t* priv,
+                      const uint64_t r[4], const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c,
+                      int out_inf[3]);
+/* same with the four input vectors already resident on the device */
+int zkb_groth16_prove_dev(zkb_groth16_pk* pk, const void* d_a, const void* d_b, const void* d_c, const void* d_priv,
+                          const uint64_t r[4], const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c,
+                          int out_inf[3]);
+/* intermediate results of the last prove on this key, for parity tests: which = 0 U, 1 V, 2 H (n coefficients each) */
+int zkb_groth16_last_poly(zkb_groth16_pk* pk, int which, uint64_t* out);
+/* the five raw MSM results of the last prove (A, B1, B2, HZ, KW) as affine canonical points + infinity flags */
+int zkb_groth16_last_msm(zkb_groth16_pk* pk, int which, uint64_t* out_xy, int* out_inf);
+
+/* ---- self test hooks (used by tests/ to compare host and device arithmetic paths) ------------------------- */
+/* field: 0 FrBN254, 1 FqBN254, 2 FrBLS381, 3 FqBLS381.  op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 neg(a).  Canonical in/out. */
+int zkb_test_field_op_host(int field, int op, size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out);
+int zkb_test_field_op_dev(int field, int op, size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out);
+
+/* sum_i k_i P_i computed by the host-side group code (has_scalar[i] == 0: k_i = 1); needs no GPU */
+int zkb_test_lincomb_host(int curve, int group, int n_terms, const uint64_t* points, const int* infs,
+                          const uint64_t* scalars, const int* has_scalar, uint64_t* out_xy, int* out_inf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKB200_H */

@@ -1,0 +1,18 @@
+"""CPU oracle for the zksnake proving hot path -- TEST INFRASTRUCTURE ONLY.
+
+Pure-Python big-int restatement of what the reference computes through arkworks
+(ark-poly 0.4.2 / ark-ec 0.4.2 / ark-ff 0.4.2 / ark-bn254 0.4.0 / ark-bls12-381 0.4.0 /
+ark-serialize 0.4.2, pinned in /root/reference/Cargo.lock:18-140; none of them vendored).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this package.  The product (zksnake_b200/) never does.
+
+PARITY STATUS: "parity unpinned" at the numeric level -- the reference ships no golden vector
+for NTT output, MSM results, point encodings or proof bytes and cannot be
+built here (no Rust toolchain).  What *is* pinned (tests/test_oracle_pins.py):
+  * the polynomial KATs of /root/reference/tests/test_algebra.py:6-26,
+  * the published constants (roots of unity, Montgomery constants, curve generators and the
+    standard Zcash/IETF compressed encodings of the BLS12-381 generators),
+  * algebraic identities (NTT by definition, H*Z == U*V-W, MSM == discrete-log closed form,
+    Groth16 verification equation through an independent pairing implementation).
+"""

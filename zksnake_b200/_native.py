@@ -1,0 +1,183 @@
+"""ctypes binding of libzkb200.so (the C ABI in include/zkb200.h).
+
+There is no CPU fallback: importing works anywhere (so that host-only logic can be tested), but every compute
+entry point raises unless a B200 is present and `ensure_init()` succeeded.  The library is looked up in-tree
+(zksnake_b200/libzkb200.so, built by `__graft_entry__.build()` / `make -C zksnake_b200/csrc`).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+BN254, BLS12_381 = 0, 1
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzkb200.so")
+
+ERR_CUDA, ERR_ARG, ERR_MISMATCH, ERR_DOMAIN, ERR_NOT_DIVISIBLE, ERR_NOINIT = -1, -2, -3, -4, -5, -6
+
+
+class ZkbError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(zksnake_b200 has no CPU fallback)"
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    c_sz, c_vp, c_int, c_u32 = ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32
+    sig = {
+        "zkb_device_count": (c_int, []),
+        "zkb_init": (c_int, [c_int]),
+        "zkb_shutdown": (None, []),
+        "zkb_last_error": (ctypes.c_char_p, []),
+        "zkb_stream": (c_vp, []),
+        "zkb_sync": (c_int, []),
+        "zkb_launch_count": (ctypes.c_ulonglong, []),
+        "zkb_timer_start": (c_int, []),
+        "zkb_timer_stop": (c_int, [ctypes.POINTER(ctypes.c_float)]),
+        "zkb_dev_alloc": (c_int, [c_sz, ctypes.POINTER(c_vp)]),
+        "zkb_dev_free": (c_int, [c_vp]),
+        "zkb_host_alloc": (c_int, [c_sz, ctypes.POINTER(c_vp)]),
+        "zkb_host_free": (c_int, [c_vp]),
+        "zkb_h2d": (c_int, [c_vp, c_vp, c_sz]),
+        "zkb_d2h": (c_int, [c_vp, c_vp, c_sz]),
+        "zkb_d2d": (c_int, [c_vp, c_vp, c_sz]),
+        "zkb_memset": (c_int, [c_vp, c_int, c_sz]),
+        "zkb_ntt": (c_int, [c_int, c_int, c_int, c_u32, c_vp, c_sz, c_vp]),
+        "zkb_ntt_dev": (c_int, [c_int, c_int, c_int, c_u32, c_vp, c_sz, c_vp]),
+        "zkb_vec_op": (c_int, [c_int, c_int, c_sz, c_vp, c_sz, c_vp, c_sz, c_vp]),
+        "zkb_vec_op_dev": (c_int, [c_int, c_int, c_sz, c_vp, c_sz, c_vp, c_sz, c_vp]),
+        "zkb_fr_reduce": (c_int, [c_int, c_sz, c_vp]),
+        "zkb_fr_reduce_dev": (c_int, [c_int, c_sz, c_vp]),
+        "zkb_fr_powers_dev": (c_int, [c_int, c_vp, c_vp, c_sz, c_vp]),
+        "zkb_affine_bytes": (c_sz, [c_int, c_int]),
+        "zkb_points_upload": (c_int, [c_int, c_int, c_vp, c_sz, c_vp]),
+        "zkb_points_download": (c_int, [c_int, c_int, c_vp, c_sz, c_vp]),
+        "zkb_msm": (c_int, [c_int, c_int, c_vp, c_sz, c_vp, c_sz, c_vp, ctypes.POINTER(c_int)]),
+        "zkb_msm_dev": (c_int, [c_int, c_int, c_vp, c_vp, c_sz, c_vp, ctypes.POINTER(c_int)]),
+        "zkb_batch_mul_dev": (c_int, [c_int, c_int, c_vp, c_int, c_vp, c_sz, c_vp]),
+        "zkb_msm_set_tuning": (None, [c_int, c_int, c_int]),
+        "zkb_groth16_h": (c_int, [c_int, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+        "zkb_groth16_h_dev": (c_int, [c_int, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int]),
+        "zkb_groth16_pk_create": (c_int, [c_int, c_u32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                          ctypes.POINTER(c_vp)]),
+        "zkb_groth16_pk_free": (None, [c_vp]),
+        "zkb_groth16_prove": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+        "zkb_groth16_prove_dev": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+        "zkb_groth16_last_poly": (c_int, [c_vp, c_int, c_vp]),
+        "zkb_groth16_last_msm": (c_int, [c_vp, c_int, c_vp, ctypes.POINTER(c_int)]),
+        "zkb_test_field_op_host": (c_int, [c_int, c_int, c_sz, c_vp, c_vp, c_vp]),
+        "zkb_test_field_op_dev": (c_int, [c_int, c_int, c_sz, c_vp, c_vp, c_vp]),
+        "zkb_test_lincomb_host": (c_int, [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_int)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError here = header and library out of sync
+        fn.restype = res
+        fn.argtypes = args
+    return lib, sorted(sig)
+
+
+lib, EXPORTED = _load()
+_initialised = False
+
+
+def last_error():
+    return (lib.zkb_last_error() or b"").decode()
+
+
+def check(rc):
+    """Map C-ABI codes to the exception types the reference raises."""
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc in (ERR_ARG, ERR_MISMATCH, ERR_DOMAIN, ERR_NOT_DIVISIBLE):
+        raise ValueError(msg)
+    raise ZkbError(msg or f"libzkb200 error {rc}")
+
+
+def ensure_init(device=None):
+    """Bind this process to one GPU (LOCAL_RANK by default).  Raises when no B200 is visible."""
+    global _initialised
+    if _initialised and device is None:
+        return
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+        n = lib.zkb_device_count()
+        if n > 0:
+            device %= n
+    check(lib.zkb_init(device))
+    _initialised = True
+
+
+def gpu_available():
+    return lib.zkb_device_count() > 0
+
+
+# ---- numpy <-> Python int helpers (little-endian limbs) --------------------------------------------------------
+def ints_to_limbs(values, nbytes=32):
+    """list[int] -> uint64 array of shape (len, nbytes/8).  Values must be in [0, 2^(8 nbytes))."""
+    buf = b"".join(int(v).to_bytes(nbytes, "little") for v in values)
+    return np.frombuffer(buf, dtype=np.uint64).reshape(len(values), nbytes // 8).copy()
+
+
+def limbs_to_ints(arr, nbytes=32):
+    raw = np.ascontiguousarray(arr).tobytes()
+    return [int.from_bytes(raw[i:i + nbytes], "little") for i in range(0, len(raw), nbytes)]
+
+
+def ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class DeviceBuffer:
+    """Owning handle of a raw device allocation."""
+
+    def __init__(self, nbytes):
+        ensure_init()
+        self.nbytes = int(nbytes)
+        p = ctypes.c_void_p()
+        check(lib.zkb_dev_alloc(self.nbytes, ctypes.byref(p)))
+        self.ptr = p
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        check(lib.zkb_h2d(self.ptr, ptr(arr), arr.nbytes))
+        return self
+
+    def download(self, dtype=np.uint64, count=None):
+        nbytes = self.nbytes if count is None else count
+        out = np.empty(nbytes // np.dtype(dtype).itemsize, dtype=dtype)
+        check(lib.zkb_d2h(ptr(out), self.ptr, out.nbytes))
+        return out
+
+    def at(self, byte_offset):
+        return ctypes.c_void_p(self.ptr.value + byte_offset)
+
+    def free(self):
+        if self.ptr is not None and self.ptr.value:
+            lib.zkb_dev_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Timer:
+    """CUDA-event timer on the library stream."""
+
+    def __enter__(self):
+        check(lib.zkb_timer_start())
+        return self
+
+    def __exit__(self, *exc):
+        ms = ctypes.c_float()
+        check(lib.zkb_timer_stop(ctypes.byref(ms)))
+        self.ms = ms.value
+        return False

@@ -1,0 +1,462 @@
+// api.cu -- extern "C" entry points of libzkb200.so declared in include/zkb200.h (host-buffer wrappers, Groth16
+// prover object, self-test hooks).  Reference call sites are cited in the header.
+#include <cuda_runtime.h>
+#include <string.h>
+#include <vector>
+#include "../../include/zkb200.h"
+#include "ec.cuh"
+#include "zkb_internal.h"
+
+using namespace zkb;
+
+static inline cudaStream_t S() { return (cudaStream_t)ctx_stream(); }
+#define NEED_INIT() \
+  if (!ctx_ready()) return set_error(ZKB_ERR_NOINIT, "zkb_init has not been called (no CUDA context; no CPU fallback)")
+#define CHECK_CURVE(c) \
+  if ((c) != ZKB_BN254 && (c) != ZKB_BLS12_381) return set_error(ZKB_ERR_ARG, "unknown curve id")
+#define CHECK_GROUP(g) \
+  if ((g) != 1 && (g) != 2) return set_error(ZKB_ERR_ARG, "group must be 1 (G1) or 2 (G2)")
+
+// grow-only staging buffers for the host-pointer entry points (separate from the kernel scratch arena)
+namespace {
+struct Stage {
+  char* p = nullptr;
+  size_t cap = 0;
+};
+Stage g_stage[6];
+int stage(int slot, size_t bytes, void** out) {
+  Stage& s = g_stage[slot];
+  if (bytes > s.cap) {
+    ZKB_CUDA(cudaStreamSynchronize(S()));
+    if (s.p) ZKB_CUDA(cudaFree(s.p));
+    s.p = nullptr;
+    s.cap = 0;
+    size_t cap = bytes + (bytes >> 2) + 4096;
+    ZKB_CUDA(cudaMalloc((void**)&s.p, cap));
+    s.cap = cap;
+  }
+  *out = s.p;
+  return ZKB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------------- Fr vectors
+int zkb_ntt_dev(int curve, int inverse, int coset, uint32_t log_n, const void* d_in, size_t in_len, void* d_out) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  return ntt_dev(curve, inverse, coset, log_n, d_in, in_len, d_out);
+}
+
+int zkb_ntt(int curve, int inverse, int coset, uint32_t log_n, const uint64_t* in, size_t in_len, uint64_t* out) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  if (log_n > 30) return set_error(ZKB_ERR_DOMAIN, "Domain size is too large");
+  size_t n = (size_t)1 << log_n;
+  if (in_len > n) in_len = n;
+  void *d_in, *d_out;
+  int rc;
+  if ((rc = stage(0, (in_len ? in_len : 1) * 32, &d_in))) return rc;
+  if ((rc = stage(1, n * 32, &d_out))) return rc;
+  if (in_len) ZKB_CUDA(cudaMemcpyAsync(d_in, in, in_len * 32, cudaMemcpyHostToDevice, S()));
+  if ((rc = fr_reduce_dev(curve, in_len, d_in))) return rc;
+  if ((rc = ntt_dev(curve, inverse, coset, log_n, d_in, in_len, d_out))) return rc;
+  ZKB_CUDA(cudaMemcpyAsync(out, d_out, n * 32, cudaMemcpyDeviceToHost, S()));
+  ZKB_CUDA(cudaStreamSynchronize(S()));
+  return ZKB_OK;
+}
+
+int zkb_vec_op_dev(int curve, int op, size_t n, const void* d_a, size_t na, const void* d_b, size_t nb, void* d_out) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  if (op < 0 || op > 2) return set_error(ZKB_ERR_ARG, "unknown vector op");
+  return vec_op_dev(curve, op, n, d_a, na, d_b, nb, nullptr, d_out);
+}
+
+int zkb_vec_op(int curve, int op, size_t n, const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* out) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  if (op < 0 || op > 2) return set_error(ZKB_ERR_ARG, "unknown vector op");
+  if (n == 0) return ZKB_OK;
+  if (na > n) na = n;
+  if (nb > n) nb = n;
+  void *d_a, *d_b, *d_o;
+  int rc;
+  if ((rc = stage(0, (na ? na : 1) * 32, &d_a))) return rc;
+  if ((rc = stage(1, (nb ? nb : 1) * 32, &d_b))) return rc;
+  if ((rc = stage(2, n * 32, &d_o))) return rc;
+  if (na) ZKB_CUDA(cudaMemcpyAsync(d_a, a, na * 32, cudaMemcpyHostToDevice, S()));
+  if (nb) ZKB_CUDA(cudaMemcpyAsync(d_b, b, nb * 32, cudaMemcpyHostToDevice, S()));
+  if ((rc = fr_reduce_dev(curve, na, d_a))) return rc;
+  if ((rc = fr_reduce_dev(curve, nb, d_b))) return rc;
+  if ((rc = vec_op_dev(curve, op, n, d_a, na, d_b, nb, nullptr, d_o))) return rc;
+  ZKB_CUDA(cudaMemcpyAsync(out, d_o, n * 32, cudaMemcpyDeviceToHost, S()));
+  ZKB_CUDA(cudaStreamSynchronize(S()));
+  return ZKB_OK;
+}
+
+int zkb_fr_reduce_dev(int curve, size_t n, void* d_inout) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  return fr_reduce_dev(curve, n, d_inout);
+}
+int zkb_fr_reduce(int curve, size_t n, uint64_t* inout) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  if (n == 0) return ZKB_OK;
+  void* d;
+  int rc;
+  if ((rc = stage(0, n * 32, &d))) return rc;
+  ZKB_CUDA(cudaMemcpyAsync(d, inout, n * 32, cudaMemcpyHostToDevice, S()));
+  if ((rc = fr_reduce_dev(curve, n, d))) return rc;
+  ZKB_CUDA(cudaMemcpyAsync(inout, d, n * 32, cudaMemcpyDeviceToHost, S()));
+  ZKB_CUDA(cudaStreamSynchronize(S()));
+  return ZKB_OK;
+}
+int zkb_fr_powers_dev(int curve, const uint64_t base[4], const uint64_t scale[4], size_t n, void* d_out) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  return fr_powers_dev(curve, base, scale, n, d_out);
+}
+
+// ---------------------------------------------------------------------------------------------------- points / MSM
+size_t zkb_affine_bytes(int curve, int group) { return affine_bytes(curve, group); }
+
+int zkb_points_upload(int curve, int group, const uint64_t* pts, size_t n, void* d_out) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  CHECK_GROUP(group);
+  if (n == 0) return ZKB_OK;
+  ZKB_CUDA(cudaMemcpyAsync(d_out, pts, n * affine_bytes(curve, group), cudaMemcpyHostToDevice, S()));
+  return points_to_mont_dev(curve, group, n, d_out);
+}
+int zkb_points_download(int curve, int group, const void* d_pts, size_t n, uint64_t* out) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  CHECK_GROUP(group);
+  if (n == 0) return ZKB_OK;
+  size_t bytes = n * affine_bytes(curve, group);
+  void* d_tmp;
+  int rc;
+  if ((rc = stage(3, bytes, &d_tmp))) return rc;
+  ZKB_CUDA(cudaMemcpyAsync(d_tmp, d_pts, bytes, cudaMemcpyDeviceToDevice, S()));
+  if ((rc = points_from_mont_dev(curve, group, n, d_tmp))) return rc;
+  ZKB_CUDA(cudaMemcpyAsync(out, d_tmp, bytes, cudaMemcpyDeviceToHost, S()));
+  ZKB_CUDA(cudaStreamSynchronize(S()));
+  return ZKB_OK;
+}
+
+int zkb_msm_dev(int curve, int group, const void* d_pts, const void* d_scalars, size_t n, uint64_t* out_xy, int* out_inf) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  CHECK_GROUP(group);
+  return msm_dev(curve, group, d_pts, d_scalars, n, out_xy, out_inf);
+}
+
+int zkb_msm(int curve, int group, const uint64_t* pts, size_t n_points, const uint64_t* scalars, size_t n_scalars,
+            uint64_t* out_xy, int* out_inf) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  CHECK_GROUP(group);
+  if (n_points != n_scalars) return set_error(ZKB_ERR_MISMATCH, "Number of points and scalars mismatch");
+  size_t n = n_points;
+  if (n == 0) {
+    memset(out_xy, 0, affine_bytes(curve, group));
+    *out_inf = 1;
+    return ZKB_OK;
+  }
+  void *d_p, *d_s;
+  int rc;
+  if ((rc = stage(3, n * affine_bytes(curve, group), &d_p))) return rc;
+  if ((rc = stage(4, n * 32, &d_s))) return rc;
+  ZKB_CUDA(cudaMemcpyAsync(d_p, pts, n * affine_bytes(curve, group), cudaMemcpyHostToDevice, S()));
+  ZKB_CUDA(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, S()));
+  if ((rc = points_to_mont_dev(curve, group, n, d_p))) return rc;
+  if ((rc = fr_reduce_dev(curve, n, d_s))) return rc;
+  return msm_dev(curve, group, d_p, d_s, n, out_xy, out_inf);
+}
+
+int zkb_batch_mul_dev(int curve, int group, const void* d_bases, int single_base, const void* d_scalars, size_t n,
+                      void* d_out) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  CHECK_GROUP(group);
+  return batch_mul_dev(curve, group, d_bases, single_base, d_scalars, n, d_out);
+}
+void zkb_msm_set_tuning(int window_bits, int segment, int reduce_chunk) { msm_set_tuning(window_bits, segment, reduce_chunk); }
+
+// ---------------------------------------------------------------------------------------------------- Groth16
+int zkb_groth16_h_dev(int curve, uint32_t log_n, const void* d_a, const void* d_b, const void* d_c, void* d_u, void* d_v,
+                      void* d_w, void* d_h, int check) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  return groth16_h_dev(curve, log_n, d_a, d_b, d_c, d_u, d_v, d_w, d_h, check);
+}
+
+int zkb_groth16_h(int curve, uint32_t log_n, const uint64_t* a, const uint64_t* b, const uint64_t* c, uint64_t* u,
+                  uint64_t* v, uint64_t* w, uint64_t* h) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  if (log_n > 30) return set_error(ZKB_ERR_DOMAIN, "Domain size is too large");
+  size_t n = (size_t)1 << log_n, bytes = n * 32;
+  void* d;
+  int rc;
+  if ((rc = stage(5, 7 * bytes, &d))) return rc;
+  char* p = (char*)d;
+  const uint64_t* src[3] = {a, b, c};
+  for (int i = 0; i < 3; i++) {
+    ZKB_CUDA(cudaMemcpyAsync(p + i * bytes, src[i], bytes, cudaMemcpyHostToDevice, S()));
+    if ((rc = fr_reduce_dev(curve, n, p + i * bytes))) return rc;
+  }
+  if ((rc = groth16_h_dev(curve, log_n, p, p + bytes, p + 2 * bytes, p + 3 * bytes, p + 4 * bytes, p + 5 * bytes,
+                          p + 6 * bytes, 1)))
+    return rc;
+  uint64_t* dst[4] = {u, v, w, h};
+  for (int i = 0; i < 4; i++)
+    if (dst[i]) ZKB_CUDA(cudaMemcpyAsync(dst[i], p + (3 + i) * bytes, bytes, cudaMemcpyDeviceToHost, S()));
+  ZKB_CUDA(cudaStreamSynchronize(S()));
+  return ZKB_OK;
+}
+
+struct zkb_groth16_pk {
+  int curve;
+  uint32_t log_n;
+  size_t n, n_kdelta;
+  const void *tau1, *tau2, *target1, *kdelta1;
+  uint64_t alpha1[12], beta1[12], beta2[24], delta1[12], delta2[24];
+  char* work;  // a, b, c, u, v, w, h (n each) + priv (n_kdelta)
+  uint64_t msm_xy[5][24];
+  int msm_inf[5];
+};
+
+int zkb_groth16_pk_create(int curve, uint32_t log_n, const void* d_tau1, const void* d_tau2, const void* d_target1,
+                          const void* d_kdelta1, size_t n_kdelta, const uint64_t* alpha1, const uint64_t* beta1,
+                          const uint64_t* beta2, const uint64_t* delta1, const uint64_t* delta2, zkb_groth16_pk** out) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  if (log_n > 28) return set_error(ZKB_ERR_DOMAIN, "Domain size is too large");
+  zkb_groth16_pk* pk = new zkb_groth16_pk();
+  memset(pk, 0, sizeof(*pk));
+  pk->curve = curve;
+  pk->log_n = log_n;
+  pk->n = (size_t)1 << log_n;
+  pk->n_kdelta = n_kdelta;
+  pk->tau1 = d_tau1;
+  pk->tau2 = d_tau2;
+  pk->target1 = d_target1;
+  pk->kdelta1 = d_kdelta1;
+  size_t g1 = affine_bytes(curve, 1), g2 = affine_bytes(curve, 2);
+  memcpy(pk->alpha1, alpha1, g1);
+  memcpy(pk->beta1, beta1, g1);
+  memcpy(pk->beta2, beta2, g2);
+  memcpy(pk->delta1, delta1, g1);
+  memcpy(pk->delta2, delta2, g2);
+  size_t bytes = (7 * pk->n + n_kdelta + 8) * 32;
+  cudaError_t e = cudaMalloc((void**)&pk->work, bytes);
+  if (e != cudaSuccess) {
+    delete pk;
+    return cuda_fail((int)e, "cudaMalloc(pk work)", __FILE__, __LINE__);
+  }
+  *out = pk;
+  return ZKB_OK;
+}
+
+void zkb_groth16_pk_free(zkb_groth16_pk* pk) {
+  if (!pk) return;
+  if (ctx_ready()) {
+    cudaStreamSynchronize(S());
+    cudaFree(pk->work);
+  }
+  delete pk;
+}
+
+static bool is_zero_pt(const uint64_t* p, size_t bytes) {
+  for (size_t i = 0; i < bytes / 8; i++)
+    if (p[i]) return false;
+  return true;
+}
+
+int zkb_groth16_prove_dev(zkb_groth16_pk* pk, const void* d_a, const void* d_b, const void* d_c, const void* d_priv,
+                          const uint64_t r[4], const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c,
+                          int out_inf[3]) {
+  NEED_INIT();
+  if (!pk) return set_error(ZKB_ERR_ARG, "null proving key");
+  const int curve = pk->curve;
+  const size_t n = pk->n, bytes = n * 32;
+  char* w = pk->work;
+  void *d_u = w + 3 * bytes, *d_v = w + 4 * bytes, *d_w = w + 5 * bytes, *d_h = w + 6 * bytes;
+  int rc;
+  if ((rc = groth16_h_dev(curve, pk->log_n, d_a, d_b, d_c, d_u, d_v, d_w, d_h, 1))) return rc;
+  // the five MSMs of protocol.py:133-155
+  if ((rc = msm_dev(curve, 1, pk->tau1, d_u, n, pk->msm_xy[0], &pk->msm_inf[0]))) return rc;
+  if ((rc = msm_dev(curve, 1, pk->tau1, d_v, n, pk->msm_xy[1], &pk->msm_inf[1]))) return rc;
+  if ((rc = msm_dev(curve, 2, pk->tau2, d_v, n, pk->msm_xy[2], &pk->msm_inf[2]))) return rc;
+  if ((rc = msm_dev(curve, 1, pk->target1, d_h, n, pk->msm_xy[3], &pk->msm_inf[3]))) return rc;
+  if ((rc = msm_dev(curve, 1, pk->kdelta1, d_priv, pk->n_kdelta, pk->msm_xy[4], &pk->msm_inf[4]))) return rc;
+  // proof assembly, protocol.py:133-165
+  const size_t g1 = affine_bytes(curve, 1), g2 = affine_bytes(curve, 2);
+  int inf_alpha = is_zero_pt(pk->alpha1, g1), inf_beta1 = is_zero_pt(pk->beta1, g1), inf_beta2 = is_zero_pt(pk->beta2, g2);
+  int inf_d1 = is_zero_pt(pk->delta1, g1), inf_d2 = is_zero_pt(pk->delta2, g2);
+  uint64_t A[12], B1[12];
+  int infA, infB1, infB2, infC;
+  {
+    const uint64_t* pts[3] = {pk->msm_xy[0], pk->alpha1, pk->delta1};
+    int infs[3] = {pk->msm_inf[0], inf_alpha, inf_d1};
+    const uint64_t* sc[3] = {nullptr, nullptr, r};
+    host_lincomb(curve, 1, 3, pts, infs, sc, A, &infA);
+  }
+  {
+    const uint64_t* pts[3] = {pk->msm_xy[1], pk->beta1, pk->delta1};
+    int infs[3] = {pk->msm_inf[1], inf_beta1, inf_d1};
+    const uint64_t* sc[3] = {nullptr, nullptr, s};
+    host_lincomb(curve, 1, 3, pts, infs, sc, B1, &infB1);
+  }
+  {
+    const uint64_t* pts[3] = {pk->msm_xy[2], pk->beta2, pk->delta2};
+    int infs[3] = {pk->msm_inf[2], inf_beta2, inf_d2};
+    const uint64_t* sc[3] = {nullptr, nullptr, s};
+    host_lincomb(curve, 2, 3, pts, infs, sc, out_b, &infB2);
+  }
+  {
+    // C = HZ + KW + s*A + r*B1 - (r*s)*delta1 ; the last term as (order - r*s) * delta1
+    uint64_t rs[4], neg_rs[4];
+    host_fr_mul(curve, r, s, rs);
+    static const uint64_t ORD[2][4] = {
+        {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull},
+        {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull, 0x73eda753299d7d48ull}};
+    unsigned __int128 br = 0;
+    bool rs_zero = !(rs[0] | rs[1] | rs[2] | rs[3]);
+    for (int i = 0; i < 4; i++) {
+      unsigned __int128 d = (unsigned __int128)ORD[curve][i] - rs[i] - (uint64_t)br;
+      neg_rs[i] = (uint64_t)d;
+      br = (d >> 64) & 1;
+    }
+    if (rs_zero) memset(neg_rs, 0, sizeof(neg_rs));
+    const uint64_t* pts[5] = {pk->msm_xy[3], pk->msm_xy[4], A, B1, pk->delta1};
+    int infs[5] = {pk->msm_inf[3], pk->msm_inf[4], infA, infB1, inf_d1};
+    const uint64_t* sc[5] = {nullptr, nullptr, s, r, neg_rs};
+    host_lincomb(curve, 1, 5, pts, infs, sc, out_c, &infC);
+  }
+  memcpy(out_a, A, g1);
+  out_inf[0] = infA;
+  out_inf[1] = infB2;
+  out_inf[2] = infC;
+  return ZKB_OK;
+}
+
+int zkb_groth16_prove(zkb_groth16_pk* pk, const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t* priv,
+                      const uint64_t r[4], const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c,
+                      int out_inf[3]) {
+  NEED_INIT();
+  if (!pk) return set_error(ZKB_ERR_ARG, "null proving key");
+  const size_t bytes = pk->n * 32;
+  char* w = pk->work;
+  char* d_priv = w + 7 * bytes;
+  ZKB_CUDA(cudaMemcpyAsync(w, a, bytes, cudaMemcpyHostToDevice, S()));
+  ZKB_CUDA(cudaMemcpyAsync(w + bytes, b, bytes, cudaMemcpyHostToDevice, S()));
+  ZKB_CUDA(cudaMemcpyAsync(w + 2 * bytes, c, bytes, cudaMemcpyHostToDevice, S()));
+  if (pk->n_kdelta) ZKB_CUDA(cudaMemcpyAsync(d_priv, priv, pk->n_kdelta * 32, cudaMemcpyHostToDevice, S()));
+  return zkb_groth16_prove_dev(pk, w, w + bytes, w + 2 * bytes, d_priv, r, s, out_a, out_b, out_c, out_inf);
+}
+
+int zkb_groth16_last_poly(zkb_groth16_pk* pk, int which, uint64_t* out) {
+  NEED_INIT();
+  if (!pk || which < 0 || which > 2) return set_error(ZKB_ERR_ARG, "bad argument");
+  const size_t bytes = pk->n * 32;
+  static const int slot[3] = {3, 4, 6};
+  ZKB_CUDA(cudaMemcpyAsync(out, pk->work + slot[which] * bytes, bytes, cudaMemcpyDeviceToHost, S()));
+  ZKB_CUDA(cudaStreamSynchronize(S()));
+  return ZKB_OK;
+}
+int zkb_groth16_last_msm(zkb_groth16_pk* pk, int which, uint64_t* out_xy, int* out_inf) {
+  if (!pk || which < 0 || which > 4) return set_error(ZKB_ERR_ARG, "bad argument");
+  memcpy(out_xy, pk->msm_xy[which], affine_bytes(pk->curve, which == 2 ? 2 : 1));
+  *out_inf = pk->msm_inf[which];
+  return ZKB_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------- self tests
+namespace {
+template <class F>
+__host__ __device__ F field_op(int op, const F& a, const F& b) {
+  F x = to_mont(a), y = to_mont(b), r;
+  if (op == 0) r = x * y;
+  else if (op == 1) r = x + y;
+  else if (op == 2) r = x - y;
+  else if (op == 3) r = inv(x);
+  else r = neg(x);
+  return from_mont(r);
+}
+template <class F>
+__global__ void field_op_kernel(int op, size_t n, const F* a, const F* b, F* out) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = field_op(op, a[i], b[i]);
+}
+template <class F>
+int field_op_host_t(int op, size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  const F* fa = (const F*)a;
+  const F* fb = (const F*)b;
+  F* fo = (F*)out;
+  for (size_t i = 0; i < n; i++) fo[i] = field_op(op, fa[i], fb[i]);
+  return ZKB_OK;
+}
+template <class F>
+int field_op_dev_t(int op, size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  F *da, *db, *dout;
+  size_t bytes = n * sizeof(F);
+  ZKB_CUDA(cudaMalloc((void**)&da, bytes));
+  ZKB_CUDA(cudaMalloc((void**)&db, bytes));
+  ZKB_CUDA(cudaMalloc((void**)&dout, bytes));
+  ZKB_CUDA(cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, S()));
+  ZKB_CUDA(cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, S()));
+  field_op_kernel<F><<<(unsigned)((n + 127) / 128), 128, 0, S()>>>(op, n, da, db, dout);
+  count_launch();
+  ZKB_CUDA(cudaGetLastError());
+  ZKB_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, S()));
+  ZKB_CUDA(cudaStreamSynchronize(S()));
+  cudaFree(da);
+  cudaFree(db);
+  cudaFree(dout);
+  return ZKB_OK;
+}
+}  // namespace
+
+extern "C" {
+int zkb_test_field_op_host(int field, int op, size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  switch (field) {
+    case 0: return field_op_host_t<fr_bn>(op, n, a, b, out);
+    case 1: return field_op_host_t<fq_bn>(op, n, a, b, out);
+    case 2: return field_op_host_t<fr_bls>(op, n, a, b, out);
+    case 3: return field_op_host_t<fq_bls>(op, n, a, b, out);
+  }
+  return set_error(ZKB_ERR_ARG, "unknown field id");
+}
+int zkb_test_field_op_dev(int field, int op, size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  NEED_INIT();
+  switch (field) {
+    case 0: return field_op_dev_t<fr_bn>(op, n, a, b, out);
+    case 1: return field_op_dev_t<fq_bn>(op, n, a, b, out);
+    case 2: return field_op_dev_t<fr_bls>(op, n, a, b, out);
+    case 3: return field_op_dev_t<fq_bls>(op, n, a, b, out);
+  }
+  return set_error(ZKB_ERR_ARG, "unknown field id");
+}
+
+// sum_i k_i P_i on the host path (has_scalar[i] == 0 means k_i = 1); exercises ec.cuh + ff_host.h without a GPU
+int zkb_test_lincomb_host(int curve, int group, int n_terms, const uint64_t* points, const int* infs,
+                          const uint64_t* scalars, const int* has_scalar, uint64_t* out_xy, int* out_inf) {
+  CHECK_CURVE(curve);
+  CHECK_GROUP(group);
+  size_t ab = affine_bytes(curve, group) / 8;
+  std::vector<const uint64_t*> pp(n_terms), ss(n_terms);
+  for (int i = 0; i < n_terms; i++) {
+    pp[i] = points + i * ab;
+    ss[i] = has_scalar[i] ? scalars + i * 4 : nullptr;
+  }
+  host_lincomb(curve, group, n_terms, pp.data(), infs, ss.data(), out_xy, out_inf);
+  return ZKB_OK;
+}
+}

@@ -1,0 +1,356 @@
+// ntt_host.cu -- host drivers for the Fr NTT passes, element-wise kernels and the Groth16 quotient pipeline.
+#include <cuda_runtime.h>
+#include <stdlib.h>
+#include <map>
+#include <vector>
+#include "ntt.cuh"
+#include "zkb_internal.h"
+
+namespace zkb {
+
+static inline cudaStream_t S() { return (cudaStream_t)ctx_stream(); }
+
+// ------------------------------------------------------------------------------------------------------
+// power tables
+// ------------------------------------------------------------------------------------------------------
+template <class F>
+struct DevTable {
+  F* lo = nullptr;
+  F* hi = nullptr;
+  uint32_t h = 0;
+  PowTable<F> view() const { PowTable<F> t; t.lo = lo; t.hi = hi; t.h = h; return t; }
+};
+
+// lo[j] = base^j (j < 2^h), hi[j] = scale * base^(j 2^h) (j < 2^(log_n - h))
+template <class F>
+static int build_table(DevTable<F>& t, const F& base, const F& scale, uint32_t log_n) {
+  uint32_t h = (log_n + 1) / 2;
+  t.h = h;
+  size_t nlo = (size_t)1 << h, nhi = (size_t)1 << (log_n - h);
+  ZKB_CUDA(cudaMalloc((void**)&t.lo, nlo * sizeof(F)));
+  ZKB_CUDA(cudaMalloc((void**)&t.hi, nhi * sizeof(F)));
+  pow_table_kernel<F><<<(unsigned)((nlo + 127) / 128), 128, 0, S()>>>(t.lo, base, F::one(), nlo, 0);
+  pow_table_kernel<F><<<(unsigned)((nhi + 127) / 128), 128, 0, S()>>>(t.hi, base, scale, nhi, h);
+  ZKB_CUDA(cudaGetLastError());
+  return ZKB_OK;
+}
+
+template <class F>
+struct Domain {
+  DevTable<F> fwd, inv;          // w^j, w^-j
+  DevTable<F> inv_scaled;        // w^-j * N^-1      (coset_ifft post-scale)
+  DevTable<F> gen_pre, gen_pre_r;  // g^j, g^j / R     (H pipeline coset, g = multiplicative generator)
+  DevTable<F> gen_post;          // g^-j * R / (N (g^N - 1))
+  F n_inv;                       // Montgomery(N^-1)
+  bool have_gen = false;
+};
+
+template <class F>
+static F host_root(uint32_t log_n, bool inverse) {
+  typedef typename F::Params P;
+  F w;
+  for (int i = 0; i < F::N; i++) w.v[i] = inverse ? P::ROOT_INV(i) : P::ROOT(i);
+  for (uint32_t i = log_n; i < (uint32_t)P::TWO_ADICITY; i++) w = sqr(w);
+  return w;
+}
+template <class F>
+static F host_small(uint64_t k) {  // Montgomery(k)
+  F x = F::zero();
+  x.v[0] = (uint32_t)k;
+  x.v[1] = (uint32_t)(k >> 32);
+  return to_mont(x);
+}
+template <class F> struct GenOf;
+template <> struct GenOf<fr_bn> { static constexpr uint64_t g = 5; };
+template <> struct GenOf<fr_bls> { static constexpr uint64_t g = 7; };
+
+template <class F>
+static std::map<uint32_t, Domain<F>>& domains() {
+  static std::map<uint32_t, Domain<F>> m;
+  return m;
+}
+
+template <class F>
+static int get_domain(uint32_t log_n, bool need_gen, Domain<F>** out) {
+  auto& m = domains<F>();
+  auto it = m.find(log_n);
+  if (it == m.end()) {
+    Domain<F> d;
+    F w = host_root<F>(log_n, false), wi = host_root<F>(log_n, true);
+    d.n_inv = inv(host_small<F>(1ull << log_n));
+    int rc;
+    if ((rc = build_table(d.fwd, w, F::one(), log_n))) return rc;
+    if ((rc = build_table(d.inv, wi, F::one(), log_n))) return rc;
+    if ((rc = build_table(d.inv_scaled, wi, d.n_inv, log_n))) return rc;
+    it = m.emplace(log_n, d).first;
+  }
+  Domain<F>& d = it->second;
+  if (need_gen && !d.have_gen) {
+    F g = host_small<F>(GenOf<F>::g);
+    F gi = inv(g);
+    F one_raw = F::zero();
+    one_raw.v[0] = 1;
+    // a stored (Montgomery-form) value m stands for m/R, so the stored integer 1 stands for 1/R
+    F r_inv = one_raw;
+    // Z on the coset: g^N - 1
+    F gn = g;
+    for (uint32_t i = 0; i < log_n; i++) gn = sqr(gn);
+    F z = gn - F::one();
+    // post constant: R / (N * Z)   (R restores the factor lost by the raw Montgomery product in the pointwise step)
+    F r_mont = F::r2();                 // stands for R
+    F post_c = r_mont * d.n_inv * inv(z);
+    int rc;
+    if ((rc = build_table(d.gen_pre, g, F::one(), log_n))) return rc;
+    if ((rc = build_table(d.gen_pre_r, g, r_inv, log_n))) return rc;
+    if ((rc = build_table(d.gen_post, gi, post_c, log_n))) return rc;
+    d.have_gen = true;
+  }
+  *out = &d;
+  return ZKB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// pass planning
+// ------------------------------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+struct Plan {
+  std::vector<uint32_t> k;   // radix bits per pass
+  std::vector<uint32_t> log_c;
+};
+
+static Plan make_plan(uint32_t log_n) {
+  Plan p;
+  uint32_t maxk = (uint32_t)env_int("ZKB_NTT_MAXK", 10);
+  if (maxk < 3) maxk = 3;
+  if (maxk > 10) maxk = 10;
+  uint32_t npass = log_n <= 10 ? 1 : (log_n + maxk - 1) / maxk;
+  if (npass > 4) npass = 4;
+  uint32_t rem = log_n;
+  for (uint32_t i = 0; i < npass; i++) {
+    uint32_t k = (rem + (npass - i) - 1) / (npass - i);
+    p.k.push_back(k);
+    rem -= k;
+  }
+  uint32_t max_tile = (uint32_t)env_int("ZKB_NTT_TILE", 2048);  // elements per tile
+  for (uint32_t i = 0; i < npass; i++) {
+    uint32_t lc = 0;
+    if (npass > 1) {
+      // C cannot exceed the column count of the pass (non-last passes) or R_1 (last pass)
+      uint32_t limit = 0;
+      if (i + 1 < npass) {
+        for (uint32_t j = i + 1; j < npass; j++) limit += p.k[j];
+      } else {
+        limit = p.k[0];
+      }
+      lc = limit < 3 ? limit : 3;
+      while (lc > 0 && ((1u << (p.k[i] + lc)) > max_tile)) lc--;
+      while (lc > 0 && (log_n - p.k[i] - lc) < 9) lc--;   // keep >= 512 tiles so that all 148 SMs stay busy
+    }
+    p.log_c.push_back(lc);
+  }
+  return p;
+}
+
+static size_t pass_smem(uint32_t k, uint32_t log_c) {
+  size_t tile = (size_t)1 << (k + log_c);
+  return 2 * (tile + 4) * 16 + 2 * (((size_t)1 << k) / 2 + 4) * 16;
+}
+
+size_t ntt_scratch_bytes(uint32_t log_n) { return ((size_t)32 << log_n) + 256; }
+
+template <class F>
+static int ntt_exec(const F* in, size_t in_len, F* out, uint32_t log_n, const PowTable<F>& tw, const PowTable<F>* pre,
+                    const PowTable<F>* post, const F* post_const, F* tmp) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    ZKB_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  Plan plan = make_plan(log_n);
+  const uint32_t P = (uint32_t)plan.k.size();
+  size_t n = (size_t)1 << log_n;
+  if (in_len > n) in_len = n;  // ark truncates inputs longer than the domain
+  uint32_t log_b = 0, log_m = log_n;
+  PowTable<F> none;
+  none.lo = none.hi = nullptr;
+  none.h = 0;
+  for (uint32_t p = 0; p < P; p++) {
+    NttPass pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.log_n = log_n;
+    pp.k = plan.k[p];
+    pp.log_c = plan.log_c[p];
+    log_m -= pp.k;
+    pp.log_m = log_m;
+    pp.log_b = log_b;
+    pp.last = (p + 1 == P);
+    pp.k1 = (P > 1) ? plan.k[0] : 0;
+    pp.nmid = (P > 2) ? (P - 2) : 0;
+    pp.kmid[0] = P > 2 ? plan.k[1] : 0;
+    pp.kmid[1] = P > 3 ? plan.k[2] : 0;
+    pp.pre = (p == 0 && pre) ? 1 : 0;
+    pp.post = 0;
+    if (pp.last) pp.post = post ? 1 : (post_const ? 2 : 0);
+    pp.in_len = (p == 0) ? in_len : n;
+    const F* src = (p == 0) ? in : tmp;
+    F* dst = pp.last ? out : tmp;
+    size_t tiles = n >> (pp.k + pp.log_c);
+    uint32_t half = 1u << (pp.k + pp.log_c) >> 1;
+    uint32_t threads = half < 32 ? 32 : (half > 512 ? 512 : half);
+    size_t smem = pass_smem(pp.k, pp.log_c);
+    ntt_pass_kernel<F><<<(unsigned)tiles, threads, smem, S()>>>(src, dst, pp, tw, pre ? *pre : none, post ? *post : none,
+                                                                post_const ? *post_const : F::zero());
+    count_launch();
+    log_b += pp.k;
+  }
+  ZKB_CUDA(cudaGetLastError());
+  return ZKB_OK;
+}
+
+template <class F>
+static int ntt_dev_t(int inverse, int coset, uint32_t log_n, const void* d_in, size_t in_len, void* d_out) {
+  typedef typename F::Params P;
+  if (log_n > (uint32_t)P::TWO_ADICITY || log_n > 30)
+    return set_error(ZKB_ERR_DOMAIN, "Domain size is too large");
+  Domain<F>* d;
+  int rc = get_domain<F>(log_n, false, &d);
+  if (rc) return rc;
+  F* tmp = nullptr;
+  if (log_n > 10) {
+    if ((rc = scratch_reserve(ntt_scratch_bytes(log_n)))) return rc;
+    scratch_reset();
+    tmp = (F*)scratch_take((size_t)32 << log_n);
+  }
+  PowTable<F> fwd = d->fwd.view(), inv_t = d->inv.view(), inv_s = d->inv_scaled.view();
+  if (!inverse) return ntt_exec<F>((const F*)d_in, in_len, (F*)d_out, log_n, fwd, coset ? &fwd : nullptr, nullptr, nullptr, tmp);
+  if (coset) return ntt_exec<F>((const F*)d_in, in_len, (F*)d_out, log_n, inv_t, nullptr, &inv_s, nullptr, tmp);
+  return ntt_exec<F>((const F*)d_in, in_len, (F*)d_out, log_n, inv_t, nullptr, nullptr, &d->n_inv, tmp);
+}
+
+int ntt_dev(int curve, int inverse, int coset, uint32_t log_n, const void* d_in, size_t in_len, void* d_out) {
+  if (curve == ZKB_BN254) return ntt_dev_t<fr_bn>(inverse, coset, log_n, d_in, in_len, d_out);
+  if (curve == ZKB_BLS12_381) return ntt_dev_t<fr_bls>(inverse, coset, log_n, d_in, in_len, d_out);
+  return set_error(ZKB_ERR_ARG, "unknown curve id");
+}
+
+// ------------------------------------------------------------------------------------------------------
+// element-wise
+// ------------------------------------------------------------------------------------------------------
+template <class F>
+static int vec_op_t(int op, size_t n, const void* a, size_t na, const void* b, size_t nb, const void* c, void* out) {
+  if (n == 0) return ZKB_OK;
+  unsigned blocks = (unsigned)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  vec_op_kernel<F><<<blocks, 256, 0, S()>>>(op, n, (const F*)a, na, (const F*)b, nb, (const F*)c, (F*)out);
+  count_launch();
+  ZKB_CUDA(cudaGetLastError());
+  return ZKB_OK;
+}
+int vec_op_dev(int curve, int op, size_t n, const void* a, size_t na, const void* b, size_t nb, const void* c, void* out) {
+  if (curve == ZKB_BN254) return vec_op_t<fr_bn>(op, n, a, na, b, nb, c, out);
+  if (curve == ZKB_BLS12_381) return vec_op_t<fr_bls>(op, n, a, na, b, nb, c, out);
+  return set_error(ZKB_ERR_ARG, "unknown curve id");
+}
+
+template <class F>
+static int reduce_t(size_t n, void* v) {
+  if (n == 0) return ZKB_OK;
+  reduce_kernel<F><<<(unsigned)((n + 255) / 256), 256, 0, S()>>>(n, (F*)v);
+  count_launch();
+  ZKB_CUDA(cudaGetLastError());
+  return ZKB_OK;
+}
+int fr_reduce_dev(int curve, size_t n, void* v) {
+  if (curve == ZKB_BN254) return reduce_t<fr_bn>(n, v);
+  if (curve == ZKB_BLS12_381) return reduce_t<fr_bls>(n, v);
+  return set_error(ZKB_ERR_ARG, "unknown curve id");
+}
+
+// out[i] = scale * base^i, canonical
+template <class F>
+__global__ void powers_canonical_kernel(F* out, F base, F scale, unsigned long long n) {
+  unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  F r = from_mont(pow_u64(base, j) * scale);
+  ntt_st(out + j, r);
+}
+template <class F>
+static int powers_t(const uint64_t* base, const uint64_t* scale, size_t n, void* d_out) {
+  F b, s;
+  memcpy(b.v, base, 32);
+  memcpy(s.v, scale, 32);
+  b = to_mont(b);
+  s = to_mont(s);
+  if (n == 0) return ZKB_OK;
+  powers_canonical_kernel<F><<<(unsigned)((n + 127) / 128), 128, 0, S()>>>((F*)d_out, b, s, n);
+  count_launch();
+  ZKB_CUDA(cudaGetLastError());
+  return ZKB_OK;
+}
+int fr_powers_dev(int curve, const uint64_t* base, const uint64_t* scale, size_t n, void* d_out) {
+  if (curve == ZKB_BN254) return powers_t<fr_bn>(base, scale, n, d_out);
+  if (curve == ZKB_BLS12_381) return powers_t<fr_bls>(base, scale, n, d_out);
+  return set_error(ZKB_ERR_ARG, "unknown curve id");
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Groth16 quotient:  H = (U V - W) / (X^n - 1)
+//   reference: QAP.evaluate_witness, /root/reference/python/zksnake/groth16/qap.py:42-71 (3 iNTT(n), 2 NTT(2n), pointwise,
+//   iNTT(2n), subtract, divide_by_vanishing_poly).  H is unique, so it is computed here on the coset g*<w> of the SAME size n:
+//   3 iNTT(n) + 3 coset-NTT(n) + pointwise + 1 coset-iNTT(n); Z is the constant g^n - 1 on that coset.
+// ------------------------------------------------------------------------------------------------------
+template <class F>
+static int groth16_h_t(uint32_t log_n, const void* d_a, const void* d_b, const void* d_c, void* d_u, void* d_v, void* d_w,
+                       void* d_h, int check) {
+  typedef typename F::Params P;
+  if (log_n > (uint32_t)P::TWO_ADICITY || log_n > 30) return set_error(ZKB_ERR_DOMAIN, "Domain size is too large");
+  size_t n = (size_t)1 << log_n;
+  Domain<F>* d;
+  int rc = get_domain<F>(log_n, true, &d);
+  if (rc) return rc;
+  size_t need = 3 * ((size_t)32 << log_n) + 4096;
+  if ((rc = scratch_reserve(need))) return rc;
+  scratch_reset();
+  F* tmp = (F*)scratch_take(n * sizeof(F));
+  F* ea = (F*)scratch_take(n * sizeof(F));
+  F* eb = (F*)scratch_take(n * sizeof(F));
+  int* flag = (int*)scratch_take(256);
+  if (!tmp || !ea || !eb || !flag) return set_error(ZKB_ERR_CUDA, "scratch exhausted");
+  if (check) {
+    ZKB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), S()));
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    check_abc_kernel<F><<<blocks, 256, 0, S()>>>(n, (const F*)d_a, (const F*)d_b, (const F*)d_c, flag);
+    count_launch();
+  }
+  PowTable<F> fwd = d->fwd.view(), inv_t = d->inv.view();
+  PowTable<F> gpre = d->gen_pre.view(), gpre_r = d->gen_pre_r.view(), gpost = d->gen_post.view();
+  F* U = (F*)d_u; F* V = (F*)d_v; F* W = (F*)d_w; F* H = (F*)d_h;
+  if ((rc = ntt_exec<F>((const F*)d_a, n, U, log_n, inv_t, nullptr, nullptr, &d->n_inv, tmp))) return rc;
+  if ((rc = ntt_exec<F>((const F*)d_b, n, V, log_n, inv_t, nullptr, nullptr, &d->n_inv, tmp))) return rc;
+  if ((rc = ntt_exec<F>((const F*)d_c, n, W, log_n, inv_t, nullptr, nullptr, &d->n_inv, tmp))) return rc;
+  if ((rc = ntt_exec<F>(U, n, ea, log_n, fwd, &gpre, nullptr, nullptr, tmp))) return rc;
+  if ((rc = ntt_exec<F>(V, n, eb, log_n, fwd, &gpre, nullptr, nullptr, tmp))) return rc;
+  if ((rc = ntt_exec<F>(W, n, H, log_n, fwd, &gpre_r, nullptr, nullptr, tmp))) return rc;   // W(g w^i) / R
+  if ((rc = vec_op_t<F>(VEC_MULSUB_RAW, n, ea, n, eb, n, H, ea))) return rc;                 // (U V - W)/R on the coset
+  if ((rc = ntt_exec<F>(ea, n, H, log_n, inv_t, nullptr, &gpost, nullptr, tmp))) return rc;
+  if (check) {
+    int hflag = 0;
+    ZKB_CUDA(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, S()));
+    ZKB_CUDA(cudaStreamSynchronize(S()));
+    if (hflag) return set_error(ZKB_ERR_NOT_DIVISIBLE, "(U * V - W) did not divided by Z to zero");
+  }
+  return ZKB_OK;
+}
+int groth16_h_dev(int curve, uint32_t log_n, const void* d_a, const void* d_b, const void* d_c, void* d_u, void* d_v,
+                  void* d_w, void* d_h, int check) {
+  if (curve == ZKB_BN254) return groth16_h_t<fr_bn>(log_n, d_a, d_b, d_c, d_u, d_v, d_w, d_h, check);
+  if (curve == ZKB_BLS12_381) return groth16_h_t<fr_bls>(log_n, d_a, d_b, d_c, d_u, d_v, d_w, d_h, check);
+  return set_error(ZKB_ERR_ARG, "unknown curve id");
+}
+
+}  // namespace zkb

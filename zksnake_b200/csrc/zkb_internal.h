@@ -1,0 +1,70 @@
+// zkb_internal.h -- internal (non-ABI) interfaces shared by the translation units of libzkb200.so.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include <string>
+
+#define ZKB_BN254 0
+#define ZKB_BLS12_381 1
+
+#define ZKB_OK 0
+#define ZKB_ERR_CUDA (-1)
+#define ZKB_ERR_ARG (-2)
+#define ZKB_ERR_MISMATCH (-3)     // "Number of points and scalars mismatch"  (curve.rs:369-371)
+#define ZKB_ERR_DOMAIN (-4)       // "Domain size is too large"              (polynomial.rs:638-639)
+#define ZKB_ERR_NOT_DIVISIBLE (-5)  // "(U * V - W) did not divided by Z to zero" (qap.py:68-69)
+#define ZKB_ERR_NOINIT (-6)
+
+namespace zkb {
+
+// sizes in bytes of one element for (curve, group)
+inline size_t fq_bytes(int curve) { return curve == ZKB_BN254 ? 32 : 48; }
+inline size_t affine_bytes(int curve, int group) { return fq_bytes(curve) * 2 * (group == 2 ? 2 : 1); }
+inline size_t xyzz_bytes(int curve, int group) { return affine_bytes(curve, group) * 2; }
+
+int set_error(int code, const std::string& msg);
+int cuda_fail(int cuda_err, const char* what, const char* file, int line);
+#define ZKB_CUDA(x)                                                           \
+  do {                                                                         \
+    cudaError_t e_ = (x);                                                      \
+    if (e_ != cudaSuccess) return zkb::cuda_fail((int)e_, #x, __FILE__, __LINE__); \
+  } while (0)
+
+void* ctx_stream();                 // cudaStream_t
+bool ctx_ready();
+// grow-only device scratch arena; `scratch_reset` starts a new allocation epoch (pointers from the previous epoch die)
+int scratch_reserve(size_t bytes);  // make sure the arena holds at least `bytes` (may reallocate; sync)
+void scratch_reset();
+void* scratch_take(size_t bytes);   // 256-byte aligned bump allocation; nullptr when exhausted
+void count_launch(int n = 1);
+unsigned long long launches();
+
+// ---- NTT (ntt_host.cu) ----
+// coset: 0 none | 1 reference coset (offset = group generator of the same domain, polynomial.rs:553-556, 579-582)
+int ntt_dev(int curve, int inverse, int coset, uint32_t log_n, const void* d_in, size_t in_len, void* d_out);
+int vec_op_dev(int curve, int op, size_t n, const void* a, size_t na, const void* b, size_t nb, const void* c, void* out);
+int fr_reduce_dev(int curve, size_t n, void* v);
+int fr_powers_dev(int curve, const uint64_t* base, const uint64_t* scale, size_t n, void* d_out);
+// H = (U*V - W)/Z from the evaluation vectors a,b,c (canonical, n = 2^log_n each, device).  Writes U,V (n coeffs each, the
+// MSM scalars) and H (n coeffs, top one zero).  d_w is scratch for W.  Returns ZKB_ERR_NOT_DIVISIBLE when a.b != c.
+int groth16_h_dev(int curve, uint32_t log_n, const void* d_a, const void* d_b, const void* d_c, void* d_u, void* d_v,
+                  void* d_w, void* d_h, int check);
+size_t ntt_scratch_bytes(uint32_t log_n);
+
+// ---- MSM (msm_host.cuh instantiations) ----
+// d_points: affine, Montgomery form; d_scalars: canonical 4 x u64.  Result: affine canonical coordinates on the host.
+int msm_dev(int curve, int group, const void* d_points, const void* d_scalars, size_t n, uint64_t* out_xy, int* out_inf);
+int points_to_mont_dev(int curve, int group, size_t n, void* d_points);
+int points_from_mont_dev(int curve, int group, size_t n, void* d_points);
+int batch_mul_dev(int curve, int group, const void* d_bases, int single_base, const void* d_scalars, size_t n, void* d_out);
+void msm_set_tuning(int c, int seg, int kchunk);
+
+// ---- host math (host_math.cpp, plain g++) ----
+// recombine W window sums (XYZZ, Montgomery) into one affine canonical point
+void host_msm_finish(int curve, int group, const void* win_sums, uint32_t nwin, uint32_t c, uint64_t* out_xy, int* out_inf);
+// out = sum_i k_i * P_i + sum_j Q_j over a handful of canonical affine points (proof assembly)
+void host_lincomb(int curve, int group, int n_terms, const uint64_t* const* points, const int* infs,
+                  const uint64_t* const* scalars, uint64_t* out_xy, int* out_inf);
+void host_fr_mul(int curve, const uint64_t* a, const uint64_t* b, uint64_t* out);
+
+}  // namespace zkb

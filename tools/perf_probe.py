@@ -1,0 +1,101 @@
+"""Quick device-side timing probe (not the bench contract): NTT and MSM kernels with device-resident data."""
+import ctypes
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from zksnake_b200 import _native as nat  # noqa: E402
+
+
+def rand_fr(n, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a = rng.integers(0, 2 ** 63, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 59) - 1)
+    return a
+
+
+def time_ntt(curve, log_n, reps=10):
+    n = 1 << log_n
+    d_in = nat.DeviceBuffer(n * 32).upload(rand_fr(n, log_n))
+    d_out = nat.DeviceBuffer(n * 32)
+    for _ in range(3):
+        nat.check(nat.lib.zkb_ntt_dev(curve, 0, 0, log_n, d_in.ptr, n, d_out.ptr))
+    with nat.Timer() as t:
+        for _ in range(reps):
+            nat.check(nat.lib.zkb_ntt_dev(curve, 0, 0, log_n, d_in.ptr, n, d_out.ptr))
+    ms = t.ms / reps
+    print(f"ntt curve={curve} 2^{log_n}: {ms*1e3:9.1f} us  {64*n/ms/1e6:8.1f} GB/s(alg)  {n/ms/1e6:8.2f} Gelem/s", flush=True)
+    d_in.free(); d_out.free()
+    return ms
+
+
+def make_points(curve, grp, n, seed):
+    ab = nat.lib.zkb_affine_bytes(curve, grp)
+    gens = {
+        (0, 1): [1, 2],
+        (1, 1): [0x17F1D3A73197D7942695638C4FA9AC0FC3688C4F9774B905A14E3A3F171BAC586C55E83FF97A1AEFFB3AF00ADB22C6BB,
+                 0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1],
+        (0, 2): [10857046999023057135944570762232829481370756359578518086990519993285655852781,
+                 11559732032986387107991004021392285783925812861821192530917403151452391805634,
+                 8495653923123431417604973247489272438418190587263600148770280649306958101930,
+                 4082367875863433681332203403145435568316851327593401208105741076214120093531],
+        (1, 2): [0x024AA2B2F08F0A91260805272DC51051C6E47AD4FA403B02B4510B647AE3D1770BAC0326A805BBEFD48056C8C121BDB8,
+                 0x13E02B6052719F607DACD3A088274F65596BD0D09920B61AB5DA61BBDC7F5049334CF11213945D57E5AC7D055D042B7E,
+                 0x0CE5D527727D6E118CC9CDC6DA2E351AADFD9BAA8CBDD3A76D429A695160D12C923AC9CC3BACA289E193548608B82801,
+                 0x0606C4A02EA734CC32ACD2B02BC28B99CB3E287E85A763AF267492AB572E99AB3F370D275CEC1DA1AAA9075FF05F79BE],
+    }[(curve, grp)]
+    nb = 32 if curve == 0 else 48
+    gen = np.frombuffer(b"".join(c.to_bytes(nb, "little") for c in gens), dtype=np.uint64).copy()
+    d_gen = nat.DeviceBuffer(ab)
+    nat.check(nat.lib.zkb_points_upload(curve, grp, nat.ptr(gen), 1, d_gen.ptr))
+    d_k = nat.DeviceBuffer(n * 32).upload(rand_fr(n, seed))
+    d_pts = nat.DeviceBuffer(n * ab)
+    t0 = time.time()
+    nat.check(nat.lib.zkb_batch_mul_dev(curve, grp, d_gen.ptr, 1, d_k.ptr, n, d_pts.ptr))
+    nat.check(nat.lib.zkb_sync())
+    print(f"  batch_mul curve={curve} g{grp} n={n}: {time.time()-t0:.3f} s", flush=True)
+    d_k.free(); d_gen.free()
+    return d_pts
+
+
+def time_msm(curve, grp, log_n, reps=3, tunings=((0, 0, 0),)):
+    n = 1 << log_n
+    ab = nat.lib.zkb_affine_bytes(curve, grp)
+    d_pts = make_points(curve, grp, n, 1)
+    d_s = nat.DeviceBuffer(n * 32).upload(rand_fr(n, 2))
+    out = np.zeros(ab // 8, dtype=np.uint64)
+    inf = ctypes.c_int()
+    for tun in tunings:
+        nat.lib.zkb_msm_set_tuning(*tun)
+        nat.check(nat.lib.zkb_msm_dev(curve, grp, d_pts.ptr, d_s.ptr, n, nat.ptr(out), ctypes.byref(inf)))
+        t0 = time.perf_counter()
+        with nat.Timer() as t:
+            for _ in range(reps):
+                nat.check(nat.lib.zkb_msm_dev(curve, grp, d_pts.ptr, d_s.ptr, n, nat.ptr(out), ctypes.byref(inf)))
+        wall = (time.perf_counter() - t0) / reps * 1e3
+        ms = t.ms / reps
+        print(f"msm curve={curve} g{grp} 2^{log_n} tuning={tun}: {ms:8.3f} ms (wall {wall:8.3f})  {n/ms/1e3:8.2f} Mpts/s", flush=True)
+    nat.lib.zkb_msm_set_tuning(0, 0, 0)
+    d_pts.free(); d_s.free()
+
+
+if __name__ == "__main__":
+    nat.ensure_init()
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("ntt", "all"):
+        for maxk in (10, 8, 7):
+            os.environ["ZKB_NTT_MAXK"] = str(maxk)
+            print("ZKB_NTT_MAXK", maxk)
+            for ln in (16, 20, 22, 24):
+                time_ntt(0, ln)
+        os.environ["ZKB_NTT_MAXK"] = "10"
+        time_ntt(1, 20)
+    if what in ("msm", "all"):
+        time_msm(0, 1, 20, tunings=((0, 0, 0), (16, 16, 16), (16, 64, 16), (14, 32, 16), (16, 32, 8), (16, 32, 32)))
+        time_msm(0, 1, 16)
+        time_msm(0, 2, 18)
+        time_msm(1, 1, 20)
+        time_msm(1, 2, 18)

@@ -125,6 +125,20 @@ int zkb_groth16_prove(zkb_groth16_pk* pk, const uint64_t* a, const uint64_t* b, 
 int zkb_groth16_prove_dev(zkb_groth16_pk* pk, const void* d_a, const void* d_b, const void* d_c, const void* d_priv,
                           const uint64_t r[4], const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c,
                           int out_inf[3]);
+/* Device-resident R1CS (A, B, C in CSR form: row_ptr has n_rows+1 uint64 entries, col uint32, val canonical Fr), replacing the
+ * pure-Python SparseArray.dot of python/zksnake/array.py:36-43 as called from qap.py:53-55.  n_rows <= 2^log_n of the key it is
+ * used with; n_cols = witness length m. */
+typedef struct zkb_r1cs zkb_r1cs;
+int zkb_r1cs_create(int curve, size_t n_rows, size_t n_cols, const uint64_t* const row_ptr[3], const uint32_t* const col[3],
+                    const uint64_t* const val[3], zkb_r1cs** out);
+void zkb_r1cs_free(zkb_r1cs* r1cs);
+/* a = A.w etc. into host buffers (n_out elements each, rows >= n_rows are zero) */
+int zkb_r1cs_eval(zkb_r1cs* r1cs, const uint64_t* witness, size_t n_out, uint64_t* a, uint64_t* b, uint64_t* c);
+/* Groth16.prove(public + private witness) end to end: witness (m = n_cols canonical scalars, public part first, n_public of
+ * them) is the ONLY per-proof host->device traffic; outputs as zkb_groth16_prove. */
+int zkb_groth16_prove_witness(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const uint64_t* witness, size_t n_public,
+                              const uint64_t r[4], const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c,
+                              int out_inf[3]);
 /* intermediate results of the last prove on this key, for parity tests: which = 0 U, 1 V, 2 H (n coefficients each) */
 int zkb_groth16_last_poly(zkb_groth16_pk* pk, int which, uint64_t* out);
 /* the five raw MSM results of the last prove (A, B1, B2, HZ, KW) as affine canonical points + infinity flags */
@@ -135,8 +149,9 @@ int zkb_groth16_last_msm(zkb_groth16_pk* pk, int which, uint64_t* out_xy, int* o
 int zkb_test_field_op_host(int field, int op, size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out);
 int zkb_test_field_op_dev(int field, int op, size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out);
 
-/* sum_i k_i P_i computed by the host-side group code (has_scalar[i] == 0: k_i = 1); needs no GPU */
-int zkb_test_lincomb_host(int curve, int group, int n_terms, const uint64_t* points, const int* infs,
+/* sum_i k_i P_i over a handful of canonical affine points, on the host (has_scalar[i] == 0: k_i = 1).  Backs the
+ * PointG1/PointG2 operators of src/bn254/curve.rs:74-118, :249-292 (+ - neg * int); needs no GPU. */
+int zkb_point_lincomb(int curve, int group, int n_terms, const uint64_t* points, const int* infs,
                           const uint64_t* scalars, const int* has_scalar, uint64_t* out_xy, int* out_inf);
 
 #ifdef __cplusplus

@@ -79,7 +79,7 @@ def test_host_lincomb(native, curve, g2):
         has = np.array([0 if s is None else 1 for s in scs], dtype=np.int32)
         out = np.zeros(len(_flat_point(G, None)) // 8, dtype=np.uint64)
         inf = ctypes.c_int(0)
-        rc = native.lib.zkb_test_lincomb_host(curve, 2 if g2 else 1, n, native.ptr(pbuf), native.ptr(infs), native.ptr(sbuf),
+        rc = native.lib.zkb_point_lincomb(curve, 2 if g2 else 1, n, native.ptr(pbuf), native.ptr(infs), native.ptr(sbuf),
                                               native.ptr(has), native.ptr(out), ctypes.byref(inf))
         assert rc == 0
         exp = None

@@ -1,0 +1,4 @@
+"""Mirror of the reference's `zksnake._algebra.ec_bn254` submodule (/root/reference/src/lib.rs) over libzkb200.so."""
+from ._ec import build as _build
+
+globals().update(_build(0))

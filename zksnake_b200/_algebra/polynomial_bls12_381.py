@@ -1,0 +1,4 @@
+"""Mirror of the reference's `zksnake._algebra.polynomial_bls12_381` submodule (/root/reference/src/lib.rs) over libzkb200.so."""
+from ._poly import build as _build
+
+globals().update(_build(1))

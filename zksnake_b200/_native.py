@@ -67,11 +67,15 @@ def _load():
         "zkb_groth16_pk_free": (None, [c_vp]),
         "zkb_groth16_prove": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "zkb_groth16_prove_dev": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+        "zkb_r1cs_create": (c_int, [c_int, c_sz, c_sz, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)]),
+        "zkb_r1cs_free": (None, [c_vp]),
+        "zkb_r1cs_eval": (c_int, [c_vp, c_vp, c_sz, c_vp, c_vp, c_vp]),
+        "zkb_groth16_prove_witness": (c_int, [c_vp, c_vp, c_vp, c_sz, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "zkb_groth16_last_poly": (c_int, [c_vp, c_int, c_vp]),
         "zkb_groth16_last_msm": (c_int, [c_vp, c_int, c_vp, ctypes.POINTER(c_int)]),
         "zkb_test_field_op_host": (c_int, [c_int, c_int, c_sz, c_vp, c_vp, c_vp]),
         "zkb_test_field_op_dev": (c_int, [c_int, c_int, c_sz, c_vp, c_vp, c_vp]),
-        "zkb_test_lincomb_host": (c_int, [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_int)]),
+        "zkb_point_lincomb": (c_int, [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_int)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = header and library out of sync

@@ -360,6 +360,114 @@ int zkb_groth16_prove(zkb_groth16_pk* pk, const uint64_t* a, const uint64_t* b, 
   return zkb_groth16_prove_dev(pk, w, w + bytes, w + 2 * bytes, d_priv, r, s, out_a, out_b, out_c, out_inf);
 }
 
+struct zkb_r1cs {
+  int curve;
+  size_t n_rows, n_cols;
+  unsigned long long* row_ptr[3];
+  uint32_t* col[3];
+  void* val[3];
+  void* w;  // witness staging (n_cols)
+};
+
+void zkb_r1cs_free(zkb_r1cs* r) {
+  if (!r) return;
+  if (ctx_ready()) {
+    cudaStreamSynchronize(S());
+    for (int i = 0; i < 3; i++) {
+      cudaFree(r->row_ptr[i]);
+      cudaFree(r->col[i]);
+      cudaFree(r->val[i]);
+    }
+    cudaFree(r->w);
+  }
+  delete r;
+}
+
+int zkb_r1cs_create(int curve, size_t n_rows, size_t n_cols, const uint64_t* const row_ptr[3], const uint32_t* const col[3],
+                    const uint64_t* const val[3], zkb_r1cs** out) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  if (n_cols >= ((size_t)1 << 32)) return set_error(ZKB_ERR_ARG, "r1cs: too many columns");
+  zkb_r1cs* r = new zkb_r1cs();
+  memset(r, 0, sizeof(*r));
+  r->curve = curve;
+  r->n_rows = n_rows;
+  r->n_cols = n_cols;
+  int rc = ZKB_OK;
+  for (int i = 0; i < 3 && rc == ZKB_OK; i++) {
+    size_t nnz = (size_t)row_ptr[i][n_rows];
+    for (size_t k = 0; k < nnz; k++)
+      if (col[i][k] >= n_cols) rc = set_error(ZKB_ERR_ARG, "r1cs: column index out of range");
+    if (rc) break;
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&r->row_ptr[i], (n_rows + 1) * 8)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&r->col[i], (nnz ? nnz : 1) * 4)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&r->val[i], (nnz ? nnz : 1) * 32)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(r->row_ptr[i], row_ptr[i], (n_rows + 1) * 8, cudaMemcpyHostToDevice, S())) != cudaSuccess ||
+        (nnz && (e = cudaMemcpyAsync(r->col[i], col[i], nnz * 4, cudaMemcpyHostToDevice, S())) != cudaSuccess) ||
+        (nnz && (e = cudaMemcpyAsync(r->val[i], val[i], nnz * 32, cudaMemcpyHostToDevice, S())) != cudaSuccess)) {
+      rc = cuda_fail((int)e, "r1cs upload", __FILE__, __LINE__);
+      break;
+    }
+    rc = fr_reduce_dev(curve, nnz, r->val[i]);
+  }
+  if (rc == ZKB_OK) {
+    cudaError_t e = cudaMalloc(&r->w, (n_cols ? n_cols : 1) * 32);
+    if (e != cudaSuccess) rc = cuda_fail((int)e, "r1cs witness buffer", __FILE__, __LINE__);
+  }
+  if (rc == ZKB_OK) {
+    cudaError_t e = cudaStreamSynchronize(S());
+    if (e != cudaSuccess) rc = cuda_fail((int)e, "r1cs sync", __FILE__, __LINE__);
+  }
+  if (rc) {
+    zkb_r1cs_free(r);
+    return rc;
+  }
+  *out = r;
+  return ZKB_OK;
+}
+
+static int r1cs_eval_dev(zkb_r1cs* r, const uint64_t* witness, size_t n_out, void* d_a, void* d_b, void* d_c) {
+  if (n_out < r->n_rows) return set_error(ZKB_ERR_ARG, "r1cs: output shorter than the row count");
+  ZKB_CUDA(cudaMemcpyAsync(r->w, witness, r->n_cols * 32, cudaMemcpyHostToDevice, S()));
+  int rc;
+  if ((rc = fr_reduce_dev(r->curve, r->n_cols, r->w))) return rc;
+  void* outs[3] = {d_a, d_b, d_c};
+  for (int i = 0; i < 3; i++)
+    if ((rc = spmv_dev(r->curve, n_out, r->n_rows, r->row_ptr[i], r->col[i], r->val[i], r->w, outs[i]))) return rc;
+  return ZKB_OK;
+}
+
+int zkb_r1cs_eval(zkb_r1cs* r, const uint64_t* witness, size_t n_out, uint64_t* a, uint64_t* b, uint64_t* c) {
+  NEED_INIT();
+  if (!r) return set_error(ZKB_ERR_ARG, "null r1cs");
+  void* d;
+  int rc;
+  if ((rc = stage(5, 3 * n_out * 32, &d))) return rc;
+  char* p = (char*)d;
+  if ((rc = r1cs_eval_dev(r, witness, n_out, p, p + n_out * 32, p + 2 * n_out * 32))) return rc;
+  uint64_t* dst[3] = {a, b, c};
+  for (int i = 0; i < 3; i++) ZKB_CUDA(cudaMemcpyAsync(dst[i], p + i * n_out * 32, n_out * 32, cudaMemcpyDeviceToHost, S()));
+  ZKB_CUDA(cudaStreamSynchronize(S()));
+  return ZKB_OK;
+}
+
+int zkb_groth16_prove_witness(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const uint64_t* witness, size_t n_public,
+                              const uint64_t r[4], const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c,
+                              int out_inf[3]) {
+  NEED_INIT();
+  if (!pk || !r1cs) return set_error(ZKB_ERR_ARG, "null proving key or r1cs");
+  if (pk->curve != r1cs->curve) return set_error(ZKB_ERR_ARG, "proving key and r1cs are on different curves");
+  if (n_public > r1cs->n_cols || r1cs->n_cols - n_public != pk->n_kdelta)
+    return set_error(ZKB_ERR_ARG, "Length of kdelta_1 and private_witness must be equal");
+  const size_t bytes = pk->n * 32;
+  char* w = pk->work;
+  int rc;
+  if ((rc = r1cs_eval_dev(r1cs, witness, pk->n, w, w + bytes, w + 2 * bytes))) return rc;
+  return zkb_groth16_prove_dev(pk, w, w + bytes, w + 2 * bytes, (char*)r1cs->w + n_public * 32, r, s, out_a, out_b, out_c,
+                               out_inf);
+}
+
 int zkb_groth16_last_poly(zkb_groth16_pk* pk, int which, uint64_t* out) {
   NEED_INIT();
   if (!pk || which < 0 || which > 2) return set_error(ZKB_ERR_ARG, "bad argument");
@@ -446,7 +554,7 @@ int zkb_test_field_op_dev(int field, int op, size_t n, const uint32_t* a, const 
 }
 
 // sum_i k_i P_i on the host path (has_scalar[i] == 0 means k_i = 1); exercises ec.cuh + ff_host.h without a GPU
-int zkb_test_lincomb_host(int curve, int group, int n_terms, const uint64_t* points, const int* infs,
+int zkb_point_lincomb(int curve, int group, int n_terms, const uint64_t* points, const int* infs,
                           const uint64_t* scalars, const int* has_scalar, uint64_t* out_xy, int* out_inf) {
   CHECK_CURVE(curve);
   CHECK_GROUP(group);

@@ -281,4 +281,22 @@ __global__ void check_abc_kernel(unsigned long long n, const F* __restrict__ a, 
   if (bad) atomicOr(flag, 1);
 }
 
+// out[row] = sum_k val[k] * w[col[k]] over the CSR row -- SparseArray.dot of /root/reference/python/zksnake/array.py:36-43
+// (the A.w, B.w, C.w products of qap.py:53-55).  Rows past n_rows_csr (domain padding) are zero.  Canonical in and out:
+// the raw Montgomery products val*w/R are summed and one multiplication by R^2 restores the scale.
+template <class F>
+__global__ void spmv_kernel(unsigned long long n_out, unsigned long long n_rows_csr, const unsigned long long* __restrict__ row_ptr,
+                            const uint32_t* __restrict__ col, const F* __restrict__ val, const F* __restrict__ w,
+                            F* __restrict__ out) {
+  unsigned long long row = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (row >= n_out) return;
+  F acc = F::zero();
+  if (row < n_rows_csr) {
+    unsigned long long lo = row_ptr[row], hi = row_ptr[row + 1];
+    for (unsigned long long k = lo; k < hi; k++) acc = acc + ntt_ldg(val + k) * ntt_ld(w + col[k]);
+    acc = acc * F::r2();
+  }
+  ntt_st(out + row, acc);
+}
+
 }  // namespace zkb

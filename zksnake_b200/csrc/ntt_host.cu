@@ -353,4 +353,20 @@ int groth16_h_dev(int curve, uint32_t log_n, const void* d_a, const void* d_b, c
   return set_error(ZKB_ERR_ARG, "unknown curve id");
 }
 
+template <class F>
+static int spmv_t(size_t n_out, size_t n_rows, const void* row_ptr, const void* col, const void* val, const void* w, void* out) {
+  if (n_out == 0) return ZKB_OK;
+  spmv_kernel<F><<<(unsigned)((n_out + 127) / 128), 128, 0, S()>>>(n_out, n_rows, (const unsigned long long*)row_ptr,
+                                                                   (const uint32_t*)col, (const F*)val, (const F*)w, (F*)out);
+  count_launch();
+  ZKB_CUDA(cudaGetLastError());
+  return ZKB_OK;
+}
+int spmv_dev(int curve, size_t n_out, size_t n_rows, const void* row_ptr, const void* col, const void* val, const void* w,
+             void* out) {
+  if (curve == ZKB_BN254) return spmv_t<fr_bn>(n_out, n_rows, row_ptr, col, val, w, out);
+  if (curve == ZKB_BLS12_381) return spmv_t<fr_bls>(n_out, n_rows, row_ptr, col, val, w, out);
+  return set_error(ZKB_ERR_ARG, "unknown curve id");
+}
+
 }  // namespace zkb

@@ -50,6 +50,8 @@ int fr_powers_dev(int curve, const uint64_t* base, const uint64_t* scale, size_t
 int groth16_h_dev(int curve, uint32_t log_n, const void* d_a, const void* d_b, const void* d_c, void* d_u, void* d_v,
                   void* d_w, void* d_h, int check);
 size_t ntt_scratch_bytes(uint32_t log_n);
+int spmv_dev(int curve, size_t n_out, size_t n_rows, const void* row_ptr, const void* col, const void* val, const void* w,
+             void* out);
 
 // ---- MSM (msm_host.cuh instantiations) ----
 // d_points: affine, Montgomery form; d_scalars: canonical 4 x u64.  Result: affine canonical coordinates on the host.

@@ -1,0 +1,233 @@
+"""Groth16 over libzkb200.so -- same public surface as the reference's `zksnake.groth16`
+(/root/reference/python/zksnake/groth16/protocol.py: Groth16(r1cs, curve).setup() / .prove(public, private) / .verify(proof,
+public); serialization.py: Proof, ProvingKey, VerifyingKey).
+
+What differs is where the work happens: the proving key lives in HBM (four device-resident point vectors), the R1CS lives
+there too (CSR), and prove() is ONE call into the C ABI (zkb_groth16_prove_witness): witness up, three points down.  The
+randomness hook is the module-level `get_random_int`, the name the reference's harnesses monkeypatch (protocol.py:11).
+"""
+import ctypes
+import random
+
+import numpy as np
+
+from . import _native as nat
+from ._algebra import ec_bls12_381, ec_bn254, polynomial_bls12_381, polynomial_bn254
+from .r1cs import R1CS
+
+_CURVES = {"BN128": 0, "BN254": 0, "ALT_BN128": 0, "BLS12_381": 1}
+_EC = {0: ec_bn254, 1: ec_bls12_381}
+_POLY = {0: polynomial_bn254, 1: polynomial_bls12_381}
+POINT_SIZE = {0: 32, 1: 48}  # CurvePointSize, /root/reference/python/zksnake/ecc.py:40-44
+
+
+def get_random_int(n_max):
+    """utils.py:6-9"""
+    return random.SystemRandom().randint(1, n_max)
+
+
+def next_power_of_two(n):
+    """utils.py:26-28"""
+    return 1 << (n - 1).bit_length()
+
+
+class Proof:
+    """serialization.py:5-42: A (G1) || B (G2) || C (G1), compressed."""
+
+    def __init__(self, A, B, C):
+        self.A, self.B, self.C = A, B, C
+
+    def __str__(self):
+        return f"A = {self.A}\nB = {self.B}\nC = {self.C}"
+
+    __repr__ = __str__
+
+    def to_bytes(self):
+        return bytes(self.A.to_bytes() + self.B.to_bytes() + self.C.to_bytes())
+
+    @classmethod
+    def from_bytes(cls, s, crv="BN254"):
+        ec = _EC[_CURVES[crv]]
+        n = POINT_SIZE[_CURVES[crv]]
+        assert len(s) == n * 4, f"Length of the Proof must equal {n * 4} bytes"
+        return cls(ec.PointG1.from_bytes(s[:n]), ec.PointG2.from_bytes(s[n:3 * n]), ec.PointG1.from_bytes(s[3 * n:]))
+
+
+class ProvingKey:
+    """serialization.py:45-66.  The four vectors are device-resident PointVectors (zksnake_b200._algebra._ec.PointVector)."""
+
+    def __init__(self, alpha_G1, beta_G1, beta_G2, delta_G1, delta_G2, tau_G1, tau_G2, target_G1, k_delta_G1):
+        self.alpha_1, self.beta_1, self.beta_2 = alpha_G1, beta_G1, beta_G2
+        self.delta_1, self.delta_2 = delta_G1, delta_G2
+        self.tau_1, self.tau_2, self.target_1, self.kdelta_1 = tau_G1, tau_G2, target_G1, k_delta_G1
+
+
+class VerifyingKey:
+    """serialization.py:162-220."""
+
+    def __init__(self, alpha_G1, beta_G2, gamma_G2, delta_G2, ic):
+        self.alpha_1, self.beta_2, self.gamma_2, self.delta_2, self.ic = alpha_G1, beta_G2, gamma_G2, delta_G2, ic
+
+
+class Groth16:
+    def __init__(self, r1cs: R1CS, curve: str = "BN254"):
+        self.curve_name = curve
+        self.curve = _CURVES[curve]
+        self.ec = _EC[self.curve]
+        self.poly = _POLY[self.curve]
+        self.order = self.ec.ORDER
+        assert r1cs.A is not None, "R1CS is not compiled"
+        self.r1cs = r1cs
+        self.n_public = r1cs.n_public
+        # QAP.from_r1cs (qap.py:32-40) rounds the row count up to the NTT domain, in place
+        n = next_power_of_two(r1cs.A.n_row)
+        r1cs.A.n_row = r1cs.B.n_row = r1cs.C.n_row = n
+        self.n = n
+        self.log_n = n.bit_length() - 1
+        self.m = r1cs.A.n_col
+        self.proving_key = None
+        self.verifying_key = None
+        self._pk_handle = None
+        self._r1cs_handle = None
+        self.toxic = None  # (tau, alpha, beta, gamma, delta) kept for closed-form parity checks in tests
+
+    # ------------------------------------------------------------------------------------------------ setup
+    def setup(self):
+        """protocol.py:32-113 with every batch_mul on the GPU fixed-base kernel and the keys left resident."""
+        nat.ensure_init()
+        o = self.order
+        ec = self.ec
+        G1, G2 = ec.g1(), ec.g2()
+        tau, alpha, beta, gamma, delta = (get_random_int(o - 1) for _ in range(5))
+        self.toxic = (tau, alpha, beta, gamma, delta)
+        inv_gamma, inv_delta = pow(gamma, -1, o), pow(delta, -1, o)
+        n, m = self.n, self.m
+        lagrange = self.poly.evaluate_lagrange_coefficients(n, tau)
+        L, R, O = [0] * m, [0] * m, [0] * m
+        for arr, acc in ((self.r1cs.A, L), (self.r1cs.B, R), (self.r1cs.C, O)):
+            for row, col, value in arr.triplets:
+                acc[col] += lagrange[row] * value
+        K = [(L[i] * beta + R[i] * alpha + O[i]) % o for i in range(m)]
+        t = self.poly.evaluate_vanishing_polynomial(n, tau)
+
+        def powers(scale):
+            d = nat.DeviceBuffer(n * 32)
+            nat.check(nat.lib.zkb_fr_powers_dev(self.curve, nat.ptr(nat.ints_to_limbs([tau])), nat.ptr(nat.ints_to_limbs([scale])),
+                                                n, d.ptr))
+            return d
+
+        def batch(base, group, d_scalars, count):
+            bases = ec.upload_points([base], group)
+            out = ec.PointVector(self.curve, group, count)
+            nat.check(nat.lib.zkb_batch_mul_dev(self.curve, group, bases.ptr, 1, d_scalars.ptr, count, out.ptr))
+            nat.check(nat.lib.zkb_sync())
+            return out
+
+        d_pow = powers(1)
+        tau_G1 = batch(G1, 1, d_pow, n)
+        tau_G2 = batch(G2, 2, d_pow, n)
+        d_tgt = powers(t * inv_delta % o)
+        target_G1 = batch(G1, 1, d_tgt, n)
+        n_priv = m - self.n_public
+        d_k = nat.DeviceBuffer(max(n_priv, 1) * 32)
+        if n_priv:
+            d_k.upload(nat.ints_to_limbs([k * inv_delta % o for k in K[self.n_public:]]))
+        k_delta_G1 = batch(G1, 1, d_k, n_priv)
+        k_gamma_G1 = [G1 * (k * inv_gamma % o) for k in K[:self.n_public]]
+        for d in (d_pow, d_tgt, d_k):
+            d.free()
+        self.proving_key = ProvingKey(G1 * alpha, G1 * beta, G2 * beta, G1 * delta, G2 * delta, tau_G1, tau_G2, target_G1,
+                                      k_delta_G1)
+        self.verifying_key = VerifyingKey(G1 * alpha, G2 * beta, G2 * gamma, G2 * delta, k_gamma_G1)
+        self._bind()
+
+    def _bind(self):
+        """Create the device-side prover objects (proving-key handle + CSR R1CS)."""
+        pk = self.proving_key
+        flat = lambda pt: np.frombuffer(pt._flat(), dtype=np.uint64).copy()  # noqa: E731
+        singles = [flat(pk.alpha_1), flat(pk.beta_1), flat(pk.beta_2), flat(pk.delta_1), flat(pk.delta_2)]
+        h = ctypes.c_void_p()
+        nat.check(nat.lib.zkb_groth16_pk_create(self.curve, self.log_n, pk.tau_1.ptr, pk.tau_2.ptr, pk.target_1.ptr,
+                                                pk.kdelta_1.ptr, len(pk.kdelta_1), *[nat.ptr(s) for s in singles],
+                                                ctypes.byref(h)))
+        self._pk_handle = h
+        self._singles = singles
+        n_rows = max((t[0] for arr in (self.r1cs.A, self.r1cs.B, self.r1cs.C) for t in arr.triplets), default=-1) + 1
+        csr = [arr.to_csr(n_rows) for arr in (self.r1cs.A, self.r1cs.B, self.r1cs.C)]
+        self._csr = csr
+        vp3 = ctypes.c_void_p * 3
+        rp = vp3(*[c[0].ctypes.data for c in csr])
+        col = vp3(*[c[1].ctypes.data if len(c[1]) else None for c in csr])
+        val = vp3(*[c[2].ctypes.data if len(c[2]) else None for c in csr])
+        hr = ctypes.c_void_p()
+        nat.check(nat.lib.zkb_r1cs_create(self.curve, n_rows, self.m, rp, col, val, ctypes.byref(hr)))
+        self._r1cs_handle = hr
+
+    # ------------------------------------------------------------------------------------------------ prove
+    def prove(self, public_witness: list, private_witness: list) -> Proof:
+        """protocol.py:115-165."""
+        assert self.proving_key, "ProvingKey has not been generated"
+        assert len(self.proving_key.kdelta_1) == len(private_witness), \
+            "Length of kdelta_1 and private_witness must be equal"
+        r = get_random_int(self.order - 1)
+        s = get_random_int(self.order - 1)
+        w = nat.ints_to_limbs([int(x) % self.order for x in list(public_witness) + list(private_witness)])
+        try:
+            return self.prove_packed(w, r, s)
+        except ValueError as exc:
+            raise ValueError("Failed to evaluate with the given witness") from exc
+
+    def prove_packed(self, witness_limbs, r, s):
+        """witness as a (m, 4) uint64 array (already canonical) -- the zero-marshalling entry used by bench.py."""
+        g1b = nat.lib.zkb_affine_bytes(self.curve, 1) // 8
+        g2b = nat.lib.zkb_affine_bytes(self.curve, 2) // 8
+        oa, ob, oc = np.zeros(g1b, np.uint64), np.zeros(g2b, np.uint64), np.zeros(g1b, np.uint64)
+        inf = (ctypes.c_int * 3)()
+        rr, ss = nat.ints_to_limbs([r]), nat.ints_to_limbs([s])
+        nat.check(nat.lib.zkb_groth16_prove_witness(self._pk_handle, self._r1cs_handle, nat.ptr(witness_limbs), self.n_public,
+                                                    nat.ptr(rr), nat.ptr(ss), nat.ptr(oa), nat.ptr(ob), nat.ptr(oc), inf))
+        ec = self.ec
+        return Proof(ec.PointG1._from_flat(oa, inf[0]), ec.PointG2._from_flat(ob, inf[1]), ec.PointG1._from_flat(oc, inf[2]))
+
+    def last_polys(self):
+        """U, V, H coefficient lists of the last prove (n entries each, unstripped) for parity tests."""
+        out = []
+        for which in range(3):
+            buf = np.zeros((self.n, 4), dtype=np.uint64)
+            nat.check(nat.lib.zkb_groth16_last_poly(self._pk_handle, which, nat.ptr(buf)))
+            out.append(nat.limbs_to_ints(buf))
+        return out
+
+    def last_msms(self):
+        """The five raw MSM results (A, B1, B2, HZ, sum_delta_witness) of the last prove as points."""
+        ec = self.ec
+        res = []
+        for which in range(5):
+            grp = 2 if which == 2 else 1
+            buf = np.zeros(nat.lib.zkb_affine_bytes(self.curve, grp) // 8, dtype=np.uint64)
+            inf = ctypes.c_int()
+            nat.check(nat.lib.zkb_groth16_last_msm(self._pk_handle, which, nat.ptr(buf), ctypes.byref(inf)))
+            res.append((ec.PointG2 if grp == 2 else ec.PointG1)._from_flat(buf, inf.value))
+        return res
+
+    # ------------------------------------------------------------------------------------------------ verify
+    def verify(self, proof: Proof, public_witness: list) -> bool:
+        """protocol.py:167-186 (pairing on the host; not a proving-path operation)."""
+        assert self.verifying_key, "VerifyingKey has not been generated"
+        vk = self.verifying_key
+        assert len(vk.ic) == len(public_witness), "Length of IC and public_witness must be equal"
+        ec = self.ec
+        acc = ec.PointG1.identity()
+        for pt, w in zip(vk.ic, public_witness):   # tiny MSM (n_public terms) -- host group code
+            acc = acc + pt * (int(w) % self.order)
+        return ec.pairing(proof.A, proof.B) == ec.multi_pairing([vk.alpha_1, acc, proof.C],
+                                                               [vk.beta_2, vk.gamma_2, vk.delta_2])
+
+    def __del__(self):
+        try:
+            if self._r1cs_handle:
+                nat.lib.zkb_r1cs_free(self._r1cs_handle)
+            if self._pk_handle:
+                nat.lib.zkb_groth16_pk_free(self._pk_handle)
+        except Exception:
+            pass

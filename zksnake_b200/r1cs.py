@@ -1,0 +1,126 @@
+"""R1CS containers with the layout Groth16 consumes in the reference, plus the synthetic circuits of the benchmark configs.
+
+`SparseArray` mirrors /root/reference/python/zksnake/array.py:4-43 (triplets, triplets_map, n_row, n_col, dot); `R1CS` carries
+what /root/reference/python/zksnake/arithmetization/r1cs.py:9-64 exposes to the prover: A, B, C, n_public and the witness
+column order [1, outputs..., public inputs..., private inputs..., intermediates...] (src/arithmetization/r1cs.rs:133-167).
+The symbolic circuit front end that normally produces these is out of scope; circuits are given as
+triplets.
+"""
+import random
+
+import numpy as np
+
+from . import _native as nat
+from ._algebra._poly import _R
+
+
+class SparseArray:
+    def __init__(self, matrix, n_row, n_col, p):
+        self.p = p
+        self.n_row = n_row
+        self.n_col = n_col
+        self.triplets_map = {}
+        self.triplets = []
+        for i, row in enumerate(matrix):
+            for j, v in enumerate(row):
+                if v != 0:
+                    self.triplets.append((i, j, v))
+
+    def append(self, triplets):
+        for row, col, value in triplets:
+            if value != 0:
+                self.triplets_map.setdefault(row, []).append((col, value))
+                self.triplets.append((row, col, value))
+
+    def dot(self, vector):
+        """array.py:36-43 -- kept for small circuits and as documentation; the prover uses the device SpMV."""
+        result = [0] * self.n_row
+        for row, col, value in self.triplets:
+            result[row] += vector[col] * value
+        return [x % self.p for x in result]
+
+    def to_csr(self, n_rows):
+        """(row_ptr uint64[n_rows+1], col uint32[nnz], val uint64[nnz,4]) sorted by row."""
+        p = self.p
+        trip = sorted(self.triplets, key=lambda t: t[0])
+        row_ptr = np.zeros(n_rows + 1, dtype=np.uint64)
+        for row, _, _ in trip:
+            row_ptr[row + 1] += 1
+        row_ptr = np.cumsum(row_ptr, dtype=np.uint64)
+        col = np.array([t[1] for t in trip], dtype=np.uint32)
+        val = nat.ints_to_limbs([t[2] % p for t in trip], 32) if trip else np.zeros((0, 4), dtype=np.uint64)
+        return row_ptr, col, val
+
+
+class R1CS:
+    """Compiled R1CS: three SparseArrays, the number of public columns (constant 1 included) and the column count."""
+
+    def __init__(self, A, B, C, n_public, p):
+        self.A, self.B, self.C = A, B, C
+        self.n_public = n_public
+        self.p = p
+
+    @classmethod
+    def from_triplets(cls, a, b, c, n_row, n_col, n_public, curve="BN254"):
+        p = _R[0 if curve in ("BN254", "BN128", "ALT_BN128") else 1]
+        arrays = []
+        for trip in (a, b, c):
+            s = SparseArray([], n_row, n_col, p)
+            s.append(trip)
+            arrays.append(s)
+        return cls(arrays[0], arrays[1], arrays[2], n_public, p)
+
+    def is_sat(self, witness):
+        a, b, c = self.A.dot(witness), self.B.dot(witness), self.C.dot(witness)
+        return all(x * y % self.p == z for x, y, z in zip(a, b, c))
+
+
+def readme_circuit(curve="BN254", x=3):
+    """y == x^3 + x + 5 (/root/reference/README.md:18-35) as the compiler lays it out: columns [1, y, x, v1], rows
+    v1 = x*x ; y - x - 5 = v1*x   (A.w=[3,9], B.w=[3,3], C.w=[9,27] for x=3)."""
+    p = _R[0 if curve in ("BN254", "BN128", "ALT_BN128") else 1]
+    a = [(0, 2, 1), (1, 3, 1)]
+    b = [(0, 2, 1), (1, 2, 1)]
+    c = [(0, 3, 1), (1, 1, 1), (1, 2, p - 1), (1, 0, p - 5)]
+    r1cs = R1CS.from_triplets(a, b, c, 2, 4, 2, curve)
+    y = (x ** 3 + x + 5) % p
+    return r1cs, [1, y], [x % p, x * x % p]
+
+
+def chain_circuit(n_constraints, curve="BN254", inp=2):
+    """/root/reference/benchmarks/benchmark_groth16.py:11-24: v0 = inp*inp, v_i = v_{i-1}*inp, out == v_{N-2}.
+    Columns [1, out, inp, v0..v_{N-2}], n_public = 2.  Returns (r1cs, public, private)."""
+    p = _R[0 if curve in ("BN254", "BN128", "ALT_BN128") else 1]
+    N = n_constraints
+    assert N >= 2
+    a, b, c = [(0, 2, 1)], [(0, 2, 1)], [(0, 3, 1)]
+    for i in range(1, N - 1):
+        a.append((i, 3 + i - 1, 1))
+        b.append((i, 2, 1))
+        c.append((i, 3 + i, 1))
+    a.append((N - 1, 3 + N - 2, 1))
+    b.append((N - 1, 0, 1))
+    c.append((N - 1, 1, 1))
+    r1cs = R1CS.from_triplets(a, b, c, N, N + 2, 2, curve)
+    v, cur = [], inp % p
+    for _ in range(N - 1):
+        cur = cur * inp % p
+        v.append(cur)
+    return r1cs, [1, v[-1]], [inp % p] + v
+
+
+def dense_random_circuit(n_constraints, curve="BN254", seed=20):
+    """Dense-random variant of SURVEY.md section 8d config 3: row i is  w_{1+i} * w_{1+N+i} = w_{1+2N+i}  with uniform random
+    factors, so that A.w, B.w (hence U, V, H) are full-size random field elements -- the realistic MSM scalar distribution.
+    Columns [1, x_0..x_{N-1}, y_0..y_{N-1}, z_0..z_{N-1}], n_public = 1."""
+    p = _R[0 if curve in ("BN254", "BN128", "ALT_BN128") else 1]
+    N = n_constraints
+    rnd = random.Random(seed)
+    xs = [rnd.randrange(p) for _ in range(N)]
+    ys = [rnd.randrange(p) for _ in range(N)]
+    zs = [x * y % p for x, y in zip(xs, ys)]
+    a = [(i, 1 + i, 1) for i in range(N)]
+    b = [(i, 1 + N + i, 1) for i in range(N)]
+    c = [(i, 1 + 2 * N + i, 1) for i in range(N)]
+    r1cs = R1CS.from_triplets(a, b, c, N, 3 * N + 1, 1, curve)
+    return r1cs, [1], xs + ys + zs

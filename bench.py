@@ -1,0 +1,427 @@
+"""bench.py -- the measurement contract.
+
+Workload (BASELINE.json `metric`: "Groth16 prove ms @2^20 BN254 at 1/2/4/8 GPU; MSM Mpts/s; NTT GB/s"):
+one Groth16 proof of the reference's benchmark circuit (benchmarks/benchmark_groth16.py:11-24, the multiplication chain) with
+2^20 constraints on BN254.  A "step" is one prove: witness -> A.w,B.w,C.w (SpMV) -> quotient H (7 NTTs) -> 5 MSMs -> proof.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--log-n 20] [--curve BN254]
+  python bench.py --impl reference ...      # the CPU arm: the C++ restatement of the reference's arkworks path (oracle/cport)
+
+Own arm, N ranks (torchrun): every rank holds 1/N of each proving-key vector, computes the witness polynomials redundantly
+(~1 ms of NTT work) and its slice of the five MSMs; one NCCL all-gather of the partial sums (< 1 KiB per rank) finishes the
+proof.  One proof is split over N GPUs, so `scaling` is "strong" and `value` is the latency of that one proof.
+
+JSON keys beyond the base contract: `roofline` (dominant kernel: MSM bucket accumulation, integer-pipe bound, SURVEY.md section
+8d), `roofline_ntt` (HBM bound), `cpu_baseline`, `breakdown_ms`, `msm_mpts_s`, `ntt_gelem_s`.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CURVE_IDS = {"BN254": 0, "BLS12_381": 1}
+METRIC = "groth16_prove_ms"
+UNIT = "ms"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="zkb200", choices=["zkb200", "reference"])
+    ap.add_argument("--log-n", type=int, default=20)
+    ap.add_argument("--curve", default="BN254", choices=sorted(CURVE_IDS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="CPU seconds (wall) the cpu_baseline sample may take")
+    return ap.parse_args()
+
+
+def workload_config(args):
+    return {
+        "workload": f"groth16-prove chain circuit (benchmarks/benchmark_groth16.py) 2^{args.log_n} constraints {args.curve}",
+        "log_n": args.log_n,
+        "curve": args.curve,
+        "msm": "4 x G1 + 1 x G2 of 2^%d points" % args.log_n,
+        "ntt": "7 x 2^%d (3 inverse, 3 coset forward, 1 coset inverse)" % args.log_n,
+    }
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# synthetic circuit in packed form (no Python big-int lists at 2^20: numpy all the way)
+# ------------------------------------------------------------------------------------------------------------------------
+def chain_csr(n_constraints):
+    """CSR (row_ptr u64, col u32, val (nnz,4) u64) of A, B, C for the chain circuit -- same layout as
+    zksnake_b200.r1cs.chain_circuit: columns [1, out, inp, v0..v_{N-2}]."""
+    N = n_constraints
+    row_ptr = np.arange(N + 1, dtype=np.uint64)
+    one = np.zeros((N, 4), dtype=np.uint64)
+    one[:, 0] = 1
+    a_col = np.empty(N, dtype=np.uint32)
+    a_col[0] = 2
+    a_col[1:] = 3 + np.arange(N - 1, dtype=np.uint32)
+    b_col = np.full(N, 2, dtype=np.uint32)
+    b_col[N - 1] = 0
+    c_col = np.empty(N, dtype=np.uint32)
+    c_col[:N - 1] = 3 + np.arange(N - 1, dtype=np.uint32)
+    c_col[N - 1] = 1
+    return [(row_ptr, a_col, one.copy()), (row_ptr, b_col, one.copy()), (row_ptr, c_col, one.copy())]
+
+
+def chain_witness(n_constraints, r, inp=2):
+    """[1, out, inp, v0..v_{N-2}] with v_i = inp^(i+2) mod r, as an (N+2, 4) uint64 array."""
+    N = n_constraints
+    vals = bytearray()
+    cur = inp % r
+    vs = []
+    for _ in range(N - 1):
+        cur = cur * inp % r
+        vs.append(cur)
+    w = [1, vs[-1], inp % r] + vs
+    for x in w:
+        vals += x.to_bytes(32, "little")
+    return np.frombuffer(bytes(vals), dtype=np.uint64).reshape(N + 2, 4).copy()
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.15] or self.rows
+        for _, line in rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# CPU arm (C++ restatement of the reference's arkworks path) -- also the cpu_baseline of the own arm
+# ------------------------------------------------------------------------------------------------------------------------
+class CpuProver:
+    """Groth16.prove of the chain circuit on the host cores through oracle/cport (kind "port").  The proving-key vectors are
+    synthetic ((k0+i)*G: the MSM cost does not depend on which points they are); everything else is the real pipeline."""
+
+    def __init__(self, curve, log_n):
+        from oracle import cport
+        from oracle.fields import PARAMS
+        self.cport = cport
+        cport.build()
+        self.curve, self.log_n = curve, log_n
+        self.n = n = 1 << log_n
+        self.r = PARAMS[curve].r
+        self.csr = chain_csr(n)
+        self.witness = chain_witness(n, self.r)
+        self.m = n + 2
+        self.threads = cport.threads()
+        g1 = lambda k0, cnt: cport.chain_points(curve, 1, k0, cnt)  # noqa: E731
+        self.key = {
+            "tau1": g1(1, n), "tau2": cport.chain_points(curve, 2, 1, n), "target1": g1(7, n), "kdelta1": g1(11, self.m - 2),
+            "alpha1": g1(3, 1)[0], "beta1": g1(5, 1)[0], "beta2": cport.chain_points(curve, 2, 5, 1)[0],
+            "delta1": g1(9, 1)[0], "delta2": cport.chain_points(curve, 2, 9, 1)[0],
+        }
+
+    def prove(self):
+        t0 = time.perf_counter()
+        out = self.cport.groth16_prove(self.curve, self.log_n, self.csr, self.m, 2, self.witness, self.key, 12345, 67890)
+        return (time.perf_counter() - t0) * 1e3, out
+
+
+def cpu_sample_log_n(curve, target_log_n, budget_s):
+    """Largest log_n <= target whose single prove is predicted to fit the budget (calibrated on a 2^12 prove; prove time is
+    ~linear in n at these sizes)."""
+    probe = CpuProver(curve, 12)
+    probe.prove()
+    ms, _ = probe.prove()
+    log_n = 12
+    while log_n < target_log_n and ms * (1 << (log_n + 1 - 12)) / 1e3 <= budget_s:
+        log_n += 1
+    return log_n
+
+
+def run_cpu_arm(args, steps, warmup, budget_total_s):
+    """Times the CPU prover.  Each step is one prove at the sample size; the reported value is scaled linearly to the
+    workload size when the sample is smaller (Pippenger's per-point cost falls slowly with n, so linear scaling from a smaller
+    n slightly OVERSTATES the CPU time at full size -- stated in `sample`)."""
+    curve = CURVE_IDS[args.curve]
+    per_step = budget_total_s / max(1, steps + warmup)
+    s_log = cpu_sample_log_n(curve, args.log_n, per_step)
+    prover = CpuProver(curve, s_log)
+    for _ in range(warmup):
+        prover.prove()
+    times = [prover.prove()[0] for _ in range(steps)]
+    scale = 1 << (args.log_n - s_log)
+    ms = float(np.mean(times)) * scale
+    sample = (f"full Groth16.prove (SpMV + QAP quotient on the 2n domain + 5 ark-style Pippenger MSMs + assembly) at "
+              f"2^{s_log} constraints, {steps} runs, mean"
+              + ("" if scale == 1 else f", scaled x{scale} linearly to 2^{args.log_n} (slightly overstates the CPU time)")
+              + "; synthetic key points (k0+i)*G; OpenMP over MSM windows / FFT butterflies (the shipped reference wheel runs "
+                "these single-threaded)")
+    return ms, {"value": ms, "unit": UNIT, "cores": prover.threads, "kind": "port", "sample": sample,
+                "sample_ms_unscaled": float(np.mean(times)), "host_cpus": os.cpu_count()}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps, warmup = args.steps, args.warmup
+    ms, base = run_cpu_arm(args, steps, warmup, budget_total_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u64 limbs (int)",
+        "data": "synthetic", "config": workload_config(args), "cpu_baseline": base,
+        "e2e": {"value": ms, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------------------------------
+def load_traffic():
+    """Per-launch DRAM bytes of the dominant kernels from the committed `ncu --set full` capture (profiles/traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
+def main_own(args):
+    import random
+
+    from zksnake_b200 import _native as nat
+    from zksnake_b200 import groth16 as zg
+    from zksnake_b200.r1cs import chain_circuit
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not nat.gpu_available():
+        raise SystemExit("bench.py: no CUDA device visible -- zksnake_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    td = None
+    torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as td
+        torch.cuda.set_device(local_rank)
+        td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    nat.ensure_init(local_rank)
+    curve = CURVE_IDS[args.curve]
+    n = 1 << args.log_n
+
+    def barrier():
+        if td is not None:
+            td.barrier()
+            torch.cuda.synchronize()
+        nat.check(nat.lib.zkb_sync())
+
+    # ---- setup (untimed): circuit, device-resident proving key slice, device-resident R1CS ----
+    t_setup = time.perf_counter()
+    r1cs, pub, priv = chain_circuit(n, args.curve)
+    rnd = random.Random(1)
+    toxic = [rnd.randint(1, r1cs.p - 1) for _ in range(5)]
+    seq = iter(toxic)
+    zg.get_random_int = lambda n_max: next(seq)
+    prover = zg.Groth16(r1cs, args.curve, shard=(rank, world))
+    prover.setup()
+    rs = random.Random(2)
+    r_rand, s_rand = rs.randint(1, r1cs.p - 1), rs.randint(1, r1cs.p - 1)
+    m = n + 2
+    w_host_np = nat.ints_to_limbs(pub + priv)
+    # pinned host copy of the witness (the e2e path copies from here every step) and a device-resident copy (the `value` path)
+    pinned = ctypes.c_void_p()
+    nat.check(nat.lib.zkb_host_alloc(m * 32, ctypes.byref(pinned)))
+    w_pinned = np.ctypeslib.as_array(ctypes.cast(pinned, ctypes.POINTER(ctypes.c_uint64)), shape=(m, 4))
+    w_pinned[:] = w_host_np
+    w_dev = nat.DeviceBuffer(m * 32).upload(w_host_np)
+    setup_s = time.perf_counter() - t_setup
+
+    # ---- warm-up ----
+    proof = None
+    for _ in range(max(args.warmup, 1)):
+        proof = prover.prove_packed(w_dev, r_rand, s_rand)
+        proof_e2e = prover.prove_packed(w_pinned, r_rand, s_rand)
+    assert proof.to_bytes() == proof_e2e.to_bytes()
+    proof_hex = proof.to_bytes().hex()
+
+    # ---- timed: device-resident ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    nat.check(nat.lib.zkb_prof_enable(1))
+    barrier()
+    launches0 = nat.lib.zkb_launch_count()
+    t0 = time.perf_counter()
+    with nat.Timer() as tm:
+        for _ in range(args.steps):
+            prover.prove_packed(w_dev, r_rand, s_rand)
+    barrier()
+    t1 = time.perf_counter()
+    launches = nat.lib.zkb_launch_count() - launches0
+    dev_ms = tm.ms / args.steps
+    wall_ms = (t1 - t0) * 1e3 / args.steps
+    prof = nat.prof_read()
+    nat.check(nat.lib.zkb_prof_enable(0))
+
+    # ---- timed: end to end from pinned host memory through the public API ----
+    barrier()
+    t2 = time.perf_counter()
+    for _ in range(args.steps):
+        p2 = prover.prove_packed(w_pinned, r_rand, s_rand)
+        _ = p2.to_bytes()
+    barrier()
+    t3 = time.perf_counter()
+    e2e_ms = (t3 - t2) * 1e3 / args.steps
+    clocks = sampler.stop(t0, t3) if rank == 0 else None
+
+    if td is not None:
+        t = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device="cuda")
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        dev_ms, wall_ms, e2e_ms = t.tolist()
+        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        td.all_reduce(lt)
+        launches = int(lt.item())
+
+    if rank != 0:
+        if td is not None:
+            td.destroy_process_group()
+        return 0
+
+    # ---- roofline (rank 0's kernels) ----
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except (OSError, ValueError):
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"
+    imad = ctypes.c_double()
+    nat.check(nat.lib.zkb_imad_peak(0, ctypes.byref(imad)))
+    imad_wide = ctypes.c_double()
+    nat.check(nat.lib.zkb_imad_peak(1, ctypes.byref(imad_wide)))
+    traffic = load_traffic()
+    lo, hi = prover._slice
+    pts_per_launch = hi - lo
+    # canonical algorithmic work of a G1 MSM = W*10 Fq products per point with c = 16 (W = 16), one
+    # product = 2L^2+L 32-bit multiply-adds (L = 8 limbs BN254, 12 BLS12-381)  => 21760 / 48000 per point
+    L = 8 if curve == 0 else 12
+    ops_per_pt = 16 * 10 * (2 * L * L + L)
+    acc_ms, acc_cnt = prof["msm_accum_g1"]
+    roofline = None
+    if acc_cnt:
+        per_launch_ms = acc_ms / acc_cnt
+        achieved = pts_per_launch * ops_per_pt / (per_launch_ms * 1e-3) / 1e12
+        roofline = {"kernel": "msm_accumulate_kernel<G1>", "bound": "int32-pipe", "achieved": achieved, "peak": imad.value / 1e12,
+                    "unit": "T int32 multiply-add lane-ops/s", "frac": achieved / (imad.value / 1e12),
+                    "peak_source": "zkb_imad_peak microbenchmark run inside this bench (mad.lo.u32, 8 chains/thread)",
+                    "imad_wide_peak": imad_wide.value / 1e12,
+                    "algorithmic_ops_per_point": ops_per_pt, "points_per_launch": pts_per_launch,
+                    "launch_ms": per_launch_ms, "launches": acc_cnt,
+                    "traffic": traffic.get("msm_accumulate_g1"), "share_of_step": acc_ms / args.steps / dev_ms}
+    ntt_ms, ntt_cnt = prof["ntt"]
+    roofline_ntt = None
+    if ntt_cnt:
+        per = ntt_ms / ntt_cnt
+        ach = 64.0 * n / (per * 1e-3) / 1e9
+        roofline_ntt = {"kernel": "ntt_pass_kernel (all passes of one 2^%d transform)" % args.log_n, "bound": "hbm",
+                        "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": hbm_src,
+                        "algorithmic_bytes": 64 * n, "launch_ms": per, "launches": ntt_cnt,
+                        "traffic": traffic.get("ntt"), "share_of_step": ntt_ms / args.steps / dev_ms}
+    breakdown = {k: v[0] / args.steps for k, v in prof.items()}
+    msm_ms_total = breakdown["msm_sort"] + breakdown["msm_accum_g1"] + breakdown["msm_accum_g2"] + breakdown["msm_reduce"]
+
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            _, cpu_base = run_cpu_arm(args, steps=1, warmup=0, budget_total_s=args.cpu_budget_s)
+        except Exception as exc:  # the CPU checker is not the product: report, do not fail the bench
+            cpu_base = {"unavailable": repr(exc)}
+
+    g1b = nat.lib.zkb_affine_bytes(curve, 1)
+    g2b = nat.lib.zkb_affine_bytes(curve, 2)
+    line = {
+        "metric": METRIC, "value": dev_ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": wall_ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32 limbs (int32 pipe)", "data": "synthetic",
+        "config": dict(workload_config(args), parallelism=f"msm-shard{world}", l2="working set 450 MiB (key 320 + scalars 130) exceeds L2; no flush"),
+        "timing": "CUDA events on the library stream around the K steps (value); wall clock between barriers (ms_per_step, e2e)",
+        "clocks": clocks,
+        "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": m * 32,
+                "d2h_bytes_per_step": 2 * g1b + g2b + 4 + 5 * 20 * 4 * (g2b // 2),
+                "api": "zksnake_b200.groth16.Groth16.prove_packed(pinned witness) -> Proof.to_bytes()"},
+        "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_ntt": roofline_ntt, "cpu_baseline": cpu_base,
+        "breakdown_ms": breakdown,
+        "msm_mpts_s": (4 + 1) * pts_per_launch / (msm_ms_total * 1e-3) / 1e6 if msm_ms_total else None,
+        "ntt_gelem_s": n / (ntt_ms / ntt_cnt * 1e-3) / 1e9 if ntt_cnt else None,
+        "proof_sha": __import__("hashlib").sha256(bytes.fromhex(proof_hex)).hexdigest()[:16],
+        "setup_s": setup_s,
+    }
+    print(json.dumps(line), flush=True)
+    if td is not None:
+        td.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_own(a))

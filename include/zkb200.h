@@ -63,6 +63,14 @@ int zkb_sync(void);
 unsigned long long zkb_launch_count(void); /* kernels launched by this library so far */
 int zkb_timer_start(void);                /* CUDA events on the library stream */
 int zkb_timer_stop(float* ms);
+/* Per-kernel-family device time (CUDA events on the library stream around every launch of the family), for bench.py's
+ * roofline lines.  tag: 0 NTT (one record per whole transform), 1 MSM digit sort (count/scan/scatter), 2 MSM bucket
+ * accumulation G1, 3 the same G2, 4 MSM bucket reduction, 5 R1CS SpMV, 6 element-wise Fr kernels, 7 other. */
+int zkb_prof_enable(int on);              /* also clears the records */
+int zkb_prof_read(int tag, float* total_ms, unsigned long long* count);
+/* Integer-pipe microbenchmark: sustained 32-bit multiply-add lane-operations per second of this GPU (the MSM roofline
+ * denominator).  which: 0 = IMAD (mad.lo.u32), 1 = IMAD.WIDE (mad.wide.u32 counted as one op). */
+int zkb_imad_peak(int which, double* ops_per_s);
 
 /* ---- raw memory ------------------------------------------------------------------------------------------- */
 int zkb_dev_alloc(size_t bytes, void** out);
@@ -114,6 +122,12 @@ typedef struct zkb_groth16_pk zkb_groth16_pk;
 int zkb_groth16_pk_create(int curve, uint32_t log_n, const void* d_tau1, const void* d_tau2, const void* d_target1,
                           const void* d_kdelta1, size_t n_kdelta, const uint64_t* alpha1, const uint64_t* beta1,
                           const uint64_t* beta2, const uint64_t* delta1, const uint64_t* delta2, zkb_groth16_pk** out);
+/* One rank's slice of the key for multi-GPU proving: d_tau1 / d_tau2 / d_target1 hold elements
+ * [off, off+len) of the n-point vectors, d_kdelta1 holds elements [koff, koff+klen) of the n_kdelta-point vector. */
+int zkb_groth16_pk_create_sharded(int curve, uint32_t log_n, const void* d_tau1, const void* d_tau2, const void* d_target1,
+                                  size_t off, size_t len, const void* d_kdelta1, size_t n_kdelta, size_t koff, size_t klen,
+                                  const uint64_t* alpha1, const uint64_t* beta1, const uint64_t* beta2, const uint64_t* delta1,
+                                  const uint64_t* delta2, zkb_groth16_pk** out);
 void zkb_groth16_pk_free(zkb_groth16_pk* pk);
 /* Groth16.prove from host buffers: a, b, c = A.w, B.w, C.w (n each), priv = private witness (n_kdelta scalars), r, s = the
  * prover's randomness.  Outputs canonical affine A (G1), B (G2), C (G1) and their infinity flags.  The timed e2e region of
@@ -139,6 +153,18 @@ int zkb_r1cs_eval(zkb_r1cs* r1cs, const uint64_t* witness, size_t n_out, uint64_
 int zkb_groth16_prove_witness(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const uint64_t* witness, size_t n_public,
                               const uint64_t r[4], const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c,
                               int out_inf[3]);
+/* same with the witness already resident on the device (bench.py's device-resident `value`) */
+int zkb_groth16_prove_witness_dev(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const void* d_witness, size_t n_public,
+                                  const uint64_t r[4], const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c,
+                                  int out_inf[3]);
+/* Multi-GPU split of Groth16.prove: every rank evaluates the witness polynomials (SpMV + quotient) and runs the five MSMs of
+ * protocol.py:133-155 over ITS key slice (zkb_groth16_partial: msm_xy = 5 x 24 uint64, canonical affine, G2 in slot 2;
+ * msm_inf = 5 flags); the per-rank partial sums are exchanged (a few hundred bytes, NCCL all-gather in zksnake_b200/dist.py),
+ * added with zkb_point_lincomb and turned into the proof by zkb_groth16_assemble (protocol.py:133-165). */
+int zkb_groth16_partial(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const void* witness, int witness_on_device, size_t n_public,
+                        uint64_t* msm_xy, int* msm_inf);
+int zkb_groth16_assemble(zkb_groth16_pk* pk, const uint64_t* msm_xy, const int* msm_inf, const uint64_t r[4],
+                         const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c, int out_inf[3]);
 /* intermediate results of the last prove on this key, for parity tests: which = 0 U, 1 V, 2 H (n coefficients each) */
 int zkb_groth16_last_poly(zkb_groth16_pk* pk, int which, uint64_t* out);
 /* the five raw MSM results of the last prove (A, B1, B2, HZ, KW) as affine canonical points + infinity flags */

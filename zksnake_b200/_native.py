@@ -38,6 +38,9 @@ def _load():
         "zkb_launch_count": (ctypes.c_ulonglong, []),
         "zkb_timer_start": (c_int, []),
         "zkb_timer_stop": (c_int, [ctypes.POINTER(ctypes.c_float)]),
+        "zkb_prof_enable": (c_int, [c_int]),
+        "zkb_prof_read": (c_int, [c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_ulonglong)]),
+        "zkb_imad_peak": (c_int, [c_int, ctypes.POINTER(ctypes.c_double)]),
         "zkb_dev_alloc": (c_int, [c_sz, ctypes.POINTER(c_vp)]),
         "zkb_dev_free": (c_int, [c_vp]),
         "zkb_host_alloc": (c_int, [c_sz, ctypes.POINTER(c_vp)]),
@@ -64,6 +67,8 @@ def _load():
         "zkb_groth16_h_dev": (c_int, [c_int, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int]),
         "zkb_groth16_pk_create": (c_int, [c_int, c_u32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp, c_vp, c_vp, c_vp, c_vp,
                                           ctypes.POINTER(c_vp)]),
+        "zkb_groth16_pk_create_sharded": (c_int, [c_int, c_u32, c_vp, c_vp, c_vp, c_sz, c_sz, c_vp, c_sz, c_sz, c_sz, c_vp, c_vp,
+                                                  c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)]),
         "zkb_groth16_pk_free": (None, [c_vp]),
         "zkb_groth16_prove": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "zkb_groth16_prove_dev": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -71,6 +76,9 @@ def _load():
         "zkb_r1cs_free": (None, [c_vp]),
         "zkb_r1cs_eval": (c_int, [c_vp, c_vp, c_sz, c_vp, c_vp, c_vp]),
         "zkb_groth16_prove_witness": (c_int, [c_vp, c_vp, c_vp, c_sz, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+        "zkb_groth16_prove_witness_dev": (c_int, [c_vp, c_vp, c_vp, c_sz, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+        "zkb_groth16_partial": (c_int, [c_vp, c_vp, c_vp, c_int, c_sz, c_vp, c_vp]),
+        "zkb_groth16_assemble": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "zkb_groth16_last_poly": (c_int, [c_vp, c_int, c_vp]),
         "zkb_groth16_last_msm": (c_int, [c_vp, c_int, c_vp, ctypes.POINTER(c_int)]),
         "zkb_test_field_op_host": (c_int, [c_int, c_int, c_sz, c_vp, c_vp, c_vp]),
@@ -171,6 +179,19 @@ class DeviceBuffer:
             self.free()
         except Exception:
             pass
+
+
+PROF_TAGS = {"ntt": 0, "msm_sort": 1, "msm_accum_g1": 2, "msm_accum_g2": 3, "msm_reduce": 4, "spmv": 5, "vec": 6, "misc": 7}
+
+
+def prof_read():
+    """{family: (total_ms, launches)} since the last zkb_prof_enable(1)."""
+    out = {}
+    for name, tag in PROF_TAGS.items():
+        ms, cnt = ctypes.c_float(), ctypes.c_ulonglong()
+        check(lib.zkb_prof_read(tag, ctypes.byref(ms), ctypes.byref(cnt)))
+        out[name] = (ms.value, cnt.value)
+    return out
 
 
 class Timer:

@@ -223,6 +223,7 @@ struct zkb_groth16_pk {
   int curve;
   uint32_t log_n;
   size_t n, n_kdelta;
+  size_t off, len, koff, klen;  // this rank's slice of the n-point vectors / of the n_kdelta-point vector
   const void *tau1, *tau2, *target1, *kdelta1;
   uint64_t alpha1[12], beta1[12], beta2[24], delta1[12], delta2[24];
   char* work;  // a, b, c, u, v, w, h (n each) + priv (n_kdelta)
@@ -230,18 +231,24 @@ struct zkb_groth16_pk {
   int msm_inf[5];
 };
 
-int zkb_groth16_pk_create(int curve, uint32_t log_n, const void* d_tau1, const void* d_tau2, const void* d_target1,
-                          const void* d_kdelta1, size_t n_kdelta, const uint64_t* alpha1, const uint64_t* beta1,
-                          const uint64_t* beta2, const uint64_t* delta1, const uint64_t* delta2, zkb_groth16_pk** out) {
+int zkb_groth16_pk_create_sharded(int curve, uint32_t log_n, const void* d_tau1, const void* d_tau2, const void* d_target1,
+                                  size_t off, size_t len, const void* d_kdelta1, size_t n_kdelta, size_t koff, size_t klen,
+                                  const uint64_t* alpha1, const uint64_t* beta1, const uint64_t* beta2, const uint64_t* delta1,
+                                  const uint64_t* delta2, zkb_groth16_pk** out) {
   NEED_INIT();
   CHECK_CURVE(curve);
   if (log_n > 28) return set_error(ZKB_ERR_DOMAIN, "Domain size is too large");
+  if (off + len > ((size_t)1 << log_n) || koff + klen > n_kdelta) return set_error(ZKB_ERR_ARG, "proving-key slice out of range");
   zkb_groth16_pk* pk = new zkb_groth16_pk();
   memset(pk, 0, sizeof(*pk));
   pk->curve = curve;
   pk->log_n = log_n;
   pk->n = (size_t)1 << log_n;
   pk->n_kdelta = n_kdelta;
+  pk->off = off;
+  pk->len = len;
+  pk->koff = koff;
+  pk->klen = klen;
   pk->tau1 = d_tau1;
   pk->tau2 = d_tau2;
   pk->target1 = d_target1;
@@ -262,6 +269,14 @@ int zkb_groth16_pk_create(int curve, uint32_t log_n, const void* d_tau1, const v
   return ZKB_OK;
 }
 
+int zkb_groth16_pk_create(int curve, uint32_t log_n, const void* d_tau1, const void* d_tau2, const void* d_target1,
+                          const void* d_kdelta1, size_t n_kdelta, const uint64_t* alpha1, const uint64_t* beta1,
+                          const uint64_t* beta2, const uint64_t* delta1, const uint64_t* delta2, zkb_groth16_pk** out) {
+  if (log_n > 28) return set_error(ZKB_ERR_DOMAIN, "Domain size is too large");
+  return zkb_groth16_pk_create_sharded(curve, log_n, d_tau1, d_tau2, d_target1, 0, (size_t)1 << log_n, d_kdelta1, n_kdelta, 0,
+                                       n_kdelta, alpha1, beta1, beta2, delta1, delta2, out);
+}
+
 void zkb_groth16_pk_free(zkb_groth16_pk* pk) {
   if (!pk) return;
   if (ctx_ready()) {
@@ -277,44 +292,49 @@ static bool is_zero_pt(const uint64_t* p, size_t bytes) {
   return true;
 }
 
-int zkb_groth16_prove_dev(zkb_groth16_pk* pk, const void* d_a, const void* d_b, const void* d_c, const void* d_priv,
-                          const uint64_t r[4], const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c,
-                          int out_inf[3]) {
-  NEED_INIT();
+// the five MSMs of protocol.py:133-155 over this key's slice; scalars are the full-length U, V, H in pk->work and d_priv
+static int groth16_msms(zkb_groth16_pk* pk, const void* d_priv) {
+  const int curve = pk->curve;
+  const size_t bytes = pk->n * 32;
+  char* w = pk->work;
+  const char *d_u = w + 3 * bytes + pk->off * 32, *d_v = w + 4 * bytes + pk->off * 32, *d_h = w + 6 * bytes + pk->off * 32;
+  int rc;
+  if ((rc = msm_dev(curve, 1, pk->tau1, d_u, pk->len, pk->msm_xy[0], &pk->msm_inf[0]))) return rc;
+  if ((rc = msm_dev(curve, 1, pk->tau1, d_v, pk->len, pk->msm_xy[1], &pk->msm_inf[1]))) return rc;
+  if ((rc = msm_dev(curve, 2, pk->tau2, d_v, pk->len, pk->msm_xy[2], &pk->msm_inf[2]))) return rc;
+  if ((rc = msm_dev(curve, 1, pk->target1, d_h, pk->len, pk->msm_xy[3], &pk->msm_inf[3]))) return rc;
+  if ((rc = msm_dev(curve, 1, pk->kdelta1, (const char*)d_priv + pk->koff * 32, pk->klen, pk->msm_xy[4], &pk->msm_inf[4])))
+    return rc;
+  return ZKB_OK;
+}
+
+int zkb_groth16_assemble(zkb_groth16_pk* pk, const uint64_t* msm_xy, const int* msm_inf, const uint64_t r[4], const uint64_t s[4],
+                         uint64_t* out_a, uint64_t* out_b, uint64_t* out_c, int out_inf[3]) {
   if (!pk) return set_error(ZKB_ERR_ARG, "null proving key");
   const int curve = pk->curve;
-  const size_t n = pk->n, bytes = n * 32;
-  char* w = pk->work;
-  void *d_u = w + 3 * bytes, *d_v = w + 4 * bytes, *d_w = w + 5 * bytes, *d_h = w + 6 * bytes;
-  int rc;
-  if ((rc = groth16_h_dev(curve, pk->log_n, d_a, d_b, d_c, d_u, d_v, d_w, d_h, 1))) return rc;
-  // the five MSMs of protocol.py:133-155
-  if ((rc = msm_dev(curve, 1, pk->tau1, d_u, n, pk->msm_xy[0], &pk->msm_inf[0]))) return rc;
-  if ((rc = msm_dev(curve, 1, pk->tau1, d_v, n, pk->msm_xy[1], &pk->msm_inf[1]))) return rc;
-  if ((rc = msm_dev(curve, 2, pk->tau2, d_v, n, pk->msm_xy[2], &pk->msm_inf[2]))) return rc;
-  if ((rc = msm_dev(curve, 1, pk->target1, d_h, n, pk->msm_xy[3], &pk->msm_inf[3]))) return rc;
-  if ((rc = msm_dev(curve, 1, pk->kdelta1, d_priv, pk->n_kdelta, pk->msm_xy[4], &pk->msm_inf[4]))) return rc;
   // proof assembly, protocol.py:133-165
   const size_t g1 = affine_bytes(curve, 1), g2 = affine_bytes(curve, 2);
+  const uint64_t* mx[5];
+  for (int i = 0; i < 5; i++) mx[i] = msm_xy + i * 24;
   int inf_alpha = is_zero_pt(pk->alpha1, g1), inf_beta1 = is_zero_pt(pk->beta1, g1), inf_beta2 = is_zero_pt(pk->beta2, g2);
   int inf_d1 = is_zero_pt(pk->delta1, g1), inf_d2 = is_zero_pt(pk->delta2, g2);
   uint64_t A[12], B1[12];
   int infA, infB1, infB2, infC;
   {
-    const uint64_t* pts[3] = {pk->msm_xy[0], pk->alpha1, pk->delta1};
-    int infs[3] = {pk->msm_inf[0], inf_alpha, inf_d1};
+    const uint64_t* pts[3] = {mx[0], pk->alpha1, pk->delta1};
+    int infs[3] = {msm_inf[0], inf_alpha, inf_d1};
     const uint64_t* sc[3] = {nullptr, nullptr, r};
     host_lincomb(curve, 1, 3, pts, infs, sc, A, &infA);
   }
   {
-    const uint64_t* pts[3] = {pk->msm_xy[1], pk->beta1, pk->delta1};
-    int infs[3] = {pk->msm_inf[1], inf_beta1, inf_d1};
+    const uint64_t* pts[3] = {mx[1], pk->beta1, pk->delta1};
+    int infs[3] = {msm_inf[1], inf_beta1, inf_d1};
     const uint64_t* sc[3] = {nullptr, nullptr, s};
     host_lincomb(curve, 1, 3, pts, infs, sc, B1, &infB1);
   }
   {
-    const uint64_t* pts[3] = {pk->msm_xy[2], pk->beta2, pk->delta2};
-    int infs[3] = {pk->msm_inf[2], inf_beta2, inf_d2};
+    const uint64_t* pts[3] = {mx[2], pk->beta2, pk->delta2};
+    int infs[3] = {msm_inf[2], inf_beta2, inf_d2};
     const uint64_t* sc[3] = {nullptr, nullptr, s};
     host_lincomb(curve, 2, 3, pts, infs, sc, out_b, &infB2);
   }
@@ -333,8 +353,8 @@ int zkb_groth16_prove_dev(zkb_groth16_pk* pk, const void* d_a, const void* d_b, 
       br = (d >> 64) & 1;
     }
     if (rs_zero) memset(neg_rs, 0, sizeof(neg_rs));
-    const uint64_t* pts[5] = {pk->msm_xy[3], pk->msm_xy[4], A, B1, pk->delta1};
-    int infs[5] = {pk->msm_inf[3], pk->msm_inf[4], infA, infB1, inf_d1};
+    const uint64_t* pts[5] = {mx[3], mx[4], A, B1, pk->delta1};
+    int infs[5] = {msm_inf[3], msm_inf[4], infA, infB1, inf_d1};
     const uint64_t* sc[5] = {nullptr, nullptr, s, r, neg_rs};
     host_lincomb(curve, 1, 5, pts, infs, sc, out_c, &infC);
   }
@@ -343,6 +363,22 @@ int zkb_groth16_prove_dev(zkb_groth16_pk* pk, const void* d_a, const void* d_b, 
   out_inf[1] = infB2;
   out_inf[2] = infC;
   return ZKB_OK;
+}
+
+int zkb_groth16_prove_dev(zkb_groth16_pk* pk, const void* d_a, const void* d_b, const void* d_c, const void* d_priv,
+                          const uint64_t r[4], const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c,
+                          int out_inf[3]) {
+  NEED_INIT();
+  if (!pk) return set_error(ZKB_ERR_ARG, "null proving key");
+  if (pk->len != pk->n || pk->klen != pk->n_kdelta)
+    return set_error(ZKB_ERR_ARG, "this proving key holds one slice only: use zkb_groth16_partial + zkb_groth16_assemble");
+  const size_t bytes = pk->n * 32;
+  char* w = pk->work;
+  void *d_u = w + 3 * bytes, *d_v = w + 4 * bytes, *d_w = w + 5 * bytes, *d_h = w + 6 * bytes;
+  int rc;
+  if ((rc = groth16_h_dev(pk->curve, pk->log_n, d_a, d_b, d_c, d_u, d_v, d_w, d_h, 1))) return rc;
+  if ((rc = groth16_msms(pk, d_priv))) return rc;
+  return zkb_groth16_assemble(pk, &pk->msm_xy[0][0], pk->msm_inf, r, s, out_a, out_b, out_c, out_inf);
 }
 
 int zkb_groth16_prove(zkb_groth16_pk* pk, const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t* priv,
@@ -427,15 +463,23 @@ int zkb_r1cs_create(int curve, size_t n_rows, size_t n_cols, const uint64_t* con
   return ZKB_OK;
 }
 
-static int r1cs_eval_dev(zkb_r1cs* r, const uint64_t* witness, size_t n_out, void* d_a, void* d_b, void* d_c) {
+// witness (n_cols canonical-or-not 256-bit values, host or device) -> r->w, reduced mod r
+static int r1cs_load_witness(zkb_r1cs* r, const void* witness, int on_device) {
+  ZKB_CUDA(cudaMemcpyAsync(r->w, witness, r->n_cols * 32, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, S()));
+  return fr_reduce_dev(r->curve, r->n_cols, r->w);
+}
+static int r1cs_spmv3(zkb_r1cs* r, size_t n_out, void* d_a, void* d_b, void* d_c) {
   if (n_out < r->n_rows) return set_error(ZKB_ERR_ARG, "r1cs: output shorter than the row count");
-  ZKB_CUDA(cudaMemcpyAsync(r->w, witness, r->n_cols * 32, cudaMemcpyHostToDevice, S()));
-  int rc;
-  if ((rc = fr_reduce_dev(r->curve, r->n_cols, r->w))) return rc;
   void* outs[3] = {d_a, d_b, d_c};
+  int rc;
   for (int i = 0; i < 3; i++)
     if ((rc = spmv_dev(r->curve, n_out, r->n_rows, r->row_ptr[i], r->col[i], r->val[i], r->w, outs[i]))) return rc;
   return ZKB_OK;
+}
+static int r1cs_eval_dev(zkb_r1cs* r, const uint64_t* witness, size_t n_out, void* d_a, void* d_b, void* d_c) {
+  int rc;
+  if ((rc = r1cs_load_witness(r, witness, 0))) return rc;
+  return r1cs_spmv3(r, n_out, d_a, d_b, d_c);
 }
 
 int zkb_r1cs_eval(zkb_r1cs* r, const uint64_t* witness, size_t n_out, uint64_t* a, uint64_t* b, uint64_t* c) {
@@ -452,20 +496,62 @@ int zkb_r1cs_eval(zkb_r1cs* r, const uint64_t* witness, size_t n_out, uint64_t* 
   return ZKB_OK;
 }
 
-int zkb_groth16_prove_witness(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const uint64_t* witness, size_t n_public,
-                              const uint64_t r[4], const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c,
-                              int out_inf[3]) {
-  NEED_INIT();
+static int prove_witness_checks(zkb_groth16_pk* pk, zkb_r1cs* r1cs, size_t n_public) {
   if (!pk || !r1cs) return set_error(ZKB_ERR_ARG, "null proving key or r1cs");
   if (pk->curve != r1cs->curve) return set_error(ZKB_ERR_ARG, "proving key and r1cs are on different curves");
   if (n_public > r1cs->n_cols || r1cs->n_cols - n_public != pk->n_kdelta)
     return set_error(ZKB_ERR_ARG, "Length of kdelta_1 and private_witness must be equal");
+  return ZKB_OK;
+}
+
+// witness already canonical and resident in r1cs->w: SpMV x3 -> quotient -> the slice's five MSMs
+static int partial_from_resident_witness(zkb_groth16_pk* pk, zkb_r1cs* r1cs, size_t n_public) {
   const size_t bytes = pk->n * 32;
   char* w = pk->work;
   int rc;
-  if ((rc = r1cs_eval_dev(r1cs, witness, pk->n, w, w + bytes, w + 2 * bytes))) return rc;
-  return zkb_groth16_prove_dev(pk, w, w + bytes, w + 2 * bytes, (char*)r1cs->w + n_public * 32, r, s, out_a, out_b, out_c,
-                               out_inf);
+  if ((rc = r1cs_spmv3(r1cs, pk->n, w, w + bytes, w + 2 * bytes))) return rc;
+  if ((rc = groth16_h_dev(pk->curve, pk->log_n, w, w + bytes, w + 2 * bytes, w + 3 * bytes, w + 4 * bytes, w + 5 * bytes,
+                          w + 6 * bytes, 1)))
+    return rc;
+  return groth16_msms(pk, (char*)r1cs->w + n_public * 32);
+}
+
+int zkb_groth16_partial(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const void* witness, int witness_on_device, size_t n_public,
+                        uint64_t* msm_xy, int* msm_inf) {
+  NEED_INIT();
+  int rc;
+  if ((rc = prove_witness_checks(pk, r1cs, n_public))) return rc;
+  if ((rc = r1cs_load_witness(r1cs, witness, witness_on_device))) return rc;
+  if ((rc = partial_from_resident_witness(pk, r1cs, n_public))) return rc;
+  memcpy(msm_xy, pk->msm_xy, sizeof(pk->msm_xy));
+  memcpy(msm_inf, pk->msm_inf, sizeof(pk->msm_inf));
+  return ZKB_OK;
+}
+
+int zkb_groth16_prove_witness(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const uint64_t* witness, size_t n_public,
+                              const uint64_t r[4], const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c,
+                              int out_inf[3]) {
+  NEED_INIT();
+  int rc;
+  if ((rc = prove_witness_checks(pk, r1cs, n_public))) return rc;
+  if (pk->len != pk->n || pk->klen != pk->n_kdelta)
+    return set_error(ZKB_ERR_ARG, "this proving key holds one slice only: use zkb_groth16_partial + zkb_groth16_assemble");
+  if ((rc = r1cs_load_witness(r1cs, witness, 0))) return rc;
+  if ((rc = partial_from_resident_witness(pk, r1cs, n_public))) return rc;
+  return zkb_groth16_assemble(pk, &pk->msm_xy[0][0], pk->msm_inf, r, s, out_a, out_b, out_c, out_inf);
+}
+
+int zkb_groth16_prove_witness_dev(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const void* d_witness, size_t n_public,
+                                  const uint64_t r[4], const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c,
+                                  int out_inf[3]) {
+  NEED_INIT();
+  int rc;
+  if ((rc = prove_witness_checks(pk, r1cs, n_public))) return rc;
+  if (pk->len != pk->n || pk->klen != pk->n_kdelta)
+    return set_error(ZKB_ERR_ARG, "this proving key holds one slice only: use zkb_groth16_partial + zkb_groth16_assemble");
+  if ((rc = r1cs_load_witness(r1cs, d_witness, 1))) return rc;
+  if ((rc = partial_from_resident_witness(pk, r1cs, n_public))) return rc;
+  return zkb_groth16_assemble(pk, &pk->msm_xy[0][0], pk->msm_inf, r, s, out_a, out_b, out_c, out_inf);
 }
 
 int zkb_groth16_last_poly(zkb_groth16_pk* pk, int which, uint64_t* out) {

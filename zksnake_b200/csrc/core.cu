@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <mutex>
+#include <vector>
 #include "../../include/zkb200.h"
 #include "zkb_internal.h"
 
@@ -35,6 +36,43 @@ bool ctx_ready() { return g_ctx.ready; }
 void count_launch(int n) { g_ctx.launches += n; }
 unsigned long long launches() { return g_ctx.launches; }
 
+// ---- per-kernel-family device timing (CUDA events on the library stream), off by default ----------------------------
+struct ProfRec { int tag; cudaEvent_t e0, e1; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t g_prof_open[PROF_NTAGS];
+static cudaEvent_t prof_event() {
+  cudaEvent_t e = nullptr;
+  if (!g_prof_pool.empty()) {
+    e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+  } else {
+    cudaEventCreate(&e);
+  }
+  return e;
+}
+void prof_begin(int tag) {
+  if (!g_prof_on) return;
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, g_ctx.stream);
+  g_prof_open[tag] = e;
+}
+void prof_end(int tag) {
+  if (!g_prof_on || !g_prof_open[tag]) return;
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, g_ctx.stream);
+  g_prof.push_back({tag, g_prof_open[tag], e});
+  g_prof_open[tag] = nullptr;
+}
+static void prof_clear() {
+  for (auto& r : g_prof) {
+    g_prof_pool.push_back(r.e0);
+    g_prof_pool.push_back(r.e1);
+  }
+  g_prof.clear();
+}
+
 int scratch_reserve(size_t bytes) {
   if (bytes <= g_ctx.arena_cap) return ZKB_OK;
   ZKB_CUDA(cudaStreamSynchronize(g_ctx.stream));
@@ -58,6 +96,41 @@ void* scratch_take(size_t bytes) {
 }  // namespace zkb
 
 using namespace zkb;
+
+// ---- integer-pipe peak microbenchmark (MSM roofline denominator) ---------------------------------------------------------
+// 8 independent multiply-add chains per thread, fully unrolled; the result is written so nothing is dead code.
+template <int WIDE>
+__global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, uint32_t a, uint32_t b, int iters) {
+  uint32_t x0 = threadIdx.x, x1 = a ^ 1, x2 = a ^ 2, x3 = a ^ 3, x4 = a ^ 4, x5 = a ^ 5, x6 = a ^ 6, x7 = a ^ 7;
+  unsigned long long y0 = threadIdx.x, y1 = 1, y2 = 2, y3 = 3, y4 = 4, y5 = 5, y6 = 6, y7 = 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      if (WIDE) {
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y0) : "r"(a), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y1) : "r"(a), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y2) : "r"(a), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y3) : "r"(a), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y4) : "r"(a), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y5) : "r"(a), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y6) : "r"(a), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y7) : "r"(a), "r"(b));
+      } else {
+        asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x0) : "r"(a), "r"(b));
+        asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x1) : "r"(a), "r"(b));
+        asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x2) : "r"(a), "r"(b));
+        asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x3) : "r"(a), "r"(b));
+        asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x4) : "r"(a), "r"(b));
+        asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x5) : "r"(a), "r"(b));
+        asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x6) : "r"(a), "r"(b));
+        asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x7) : "r"(a), "r"(b));
+      }
+    }
+  }
+  uint32_t r = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7 ^ (uint32_t)(y0 ^ y1 ^ y2 ^ y3 ^ y4 ^ y5 ^ y6 ^ y7) ^
+               (uint32_t)((y0 ^ y1 ^ y2 ^ y3 ^ y4 ^ y5 ^ y6 ^ y7) >> 32);
+  if (r == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
 
 extern "C" {
 
@@ -161,6 +234,51 @@ int zkb_d2d(void* dst, const void* src, size_t bytes) {
 int zkb_memset(void* dst, int value, size_t bytes) {
   NEED_INIT();
   ZKB_CUDA(cudaMemsetAsync(dst, value, bytes, g_ctx.stream));
+  return ZKB_OK;
+}
+int zkb_prof_enable(int on) {
+  NEED_INIT();
+  ZKB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  prof_clear();
+  g_prof_on = on != 0;
+  return ZKB_OK;
+}
+int zkb_prof_read(int tag, float* total_ms, unsigned long long* count) {
+  NEED_INIT();
+  if (tag < 0 || tag >= PROF_NTAGS) return set_error(ZKB_ERR_ARG, "unknown profile tag");
+  ZKB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  float sum = 0;
+  unsigned long long n = 0;
+  for (auto& r : g_prof) {
+    if (r.tag != tag) continue;
+    float ms = 0;
+    ZKB_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    sum += ms;
+    n++;
+  }
+  *total_ms = sum;
+  *count = n;
+  return ZKB_OK;
+}
+int zkb_imad_peak(int which, double* ops_per_s) {
+  NEED_INIT();
+  uint32_t* d = nullptr;
+  const int blocks = 148 * 8, threads = 256, iters = 4096;
+  ZKB_CUDA(cudaMalloc((void**)&d, (size_t)blocks * threads * 4));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    ZKB_CUDA(cudaEventRecord(g_ctx.ev0, g_ctx.stream));
+    if (which) imad_peak_kernel<1><<<blocks, threads, 0, g_ctx.stream>>>(d, 0x9e3779b9u, 0x7f4a7c15u, iters);
+    else imad_peak_kernel<0><<<blocks, threads, 0, g_ctx.stream>>>(d, 0x9e3779b9u, 0x7f4a7c15u, iters);
+    ZKB_CUDA(cudaEventRecord(g_ctx.ev1, g_ctx.stream));
+    ZKB_CUDA(cudaEventSynchronize(g_ctx.ev1));
+    float ms = 0;
+    ZKB_CUDA(cudaEventElapsedTime(&ms, g_ctx.ev0, g_ctx.ev1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  count_launch(5);
+  ZKB_CUDA(cudaFree(d));
+  *ops_per_s = (double)blocks * threads * iters * 64.0 / (best * 1e-3);
   return ZKB_OK;
 }
 int zkb_timer_start(void) {

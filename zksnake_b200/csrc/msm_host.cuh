@@ -82,6 +82,7 @@ int msm_run(int curve, int group, const void* d_points, const void* d_scalars, s
   ZKB_CUDA(cudaMemsetAsync(cnt, 0, (nb + 1) * 4, st));
   ZKB_CUDA(cudaMemsetAsync(hot_count, 0, 4, st));
   unsigned pblocks = (unsigned)((n + 255) / 256);
+  prof_begin(PROF_MSM_SORT);
   msm_count_kernel<<<pblocks, 256, 0, st>>>(pl, sc, cnt);
   scan_kernel<<<1, 1024, 0, st>>>(cnt, start, nb);
   ZKB_CUDA(cudaMemcpyAsync(cursor, start, (nb + 1) * 4, cudaMemcpyDeviceToDevice, st));
@@ -90,12 +91,18 @@ int msm_run(int curve, int group, const void* d_points, const void* d_scalars, s
   msm_nseg_kernel<<<bblocks, 256, 0, st>>>(pl, cnt, nseg);
   scan_kernel<<<1, 1024, 0, st>>>(nseg, segstart, nb);
   msm_segfill_kernel<<<bblocks, 256, 0, st>>>(pl, nseg, segstart, seg_bucket, hot_list, hot_count);
+  prof_end(PROF_MSM_SORT);
   unsigned ablocks = (unsigned)((pl.max_segs + 127) / 128);
+  const int acc_tag = group == 2 ? PROF_MSM_ACCUM_G2 : PROF_MSM_ACCUM_G1;
+  prof_begin(acc_tag);
   msm_accumulate_kernel<F><<<ablocks, 128, 0, st>>>(pl, (const Affine<F>*)d_points, refs, cnt, start, segstart, seg_bucket,
                                                     seg_sum);
+  prof_end(acc_tag);
+  prof_begin(PROF_MSM_REDUCE);
   msm_hot_kernel<F><<<296, 128, 128 * sizeof(X), st>>>(hot_list, hot_count, nseg, segstart, seg_sum);
   msm_bucket_reduce_kernel<F><<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(pl, nseg, segstart, seg_sum, contrib);
   msm_window_sum_kernel<F><<<pl.nwin, 128, 128 * sizeof(X), st>>>(chunks_per_win, contrib, win_sum);
+  prof_end(PROF_MSM_REDUCE);
   count_launch(9);
   ZKB_CUDA(cudaGetLastError());
   std::vector<unsigned char> host(pl.nwin * sizeof(X));

@@ -178,6 +178,7 @@ static int ntt_exec(const F* in, size_t in_len, F* out, uint32_t log_n, const Po
   PowTable<F> none;
   none.lo = none.hi = nullptr;
   none.h = 0;
+  prof_begin(PROF_NTT);
   for (uint32_t p = 0; p < P; p++) {
     NttPass pp;
     memset(&pp, 0, sizeof(pp));
@@ -207,6 +208,7 @@ static int ntt_exec(const F* in, size_t in_len, F* out, uint32_t log_n, const Po
     count_launch();
     log_b += pp.k;
   }
+  prof_end(PROF_NTT);
   ZKB_CUDA(cudaGetLastError());
   return ZKB_OK;
 }
@@ -245,7 +247,9 @@ static int vec_op_t(int op, size_t n, const void* a, size_t na, const void* b, s
   if (n == 0) return ZKB_OK;
   unsigned blocks = (unsigned)((n + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
+  prof_begin(PROF_VEC);
   vec_op_kernel<F><<<blocks, 256, 0, S()>>>(op, n, (const F*)a, na, (const F*)b, nb, (const F*)c, (F*)out);
+  prof_end(PROF_VEC);
   count_launch();
   ZKB_CUDA(cudaGetLastError());
   return ZKB_OK;
@@ -259,7 +263,9 @@ int vec_op_dev(int curve, int op, size_t n, const void* a, size_t na, const void
 template <class F>
 static int reduce_t(size_t n, void* v) {
   if (n == 0) return ZKB_OK;
+  prof_begin(PROF_VEC);
   reduce_kernel<F><<<(unsigned)((n + 255) / 256), 256, 0, S()>>>(n, (F*)v);
+  prof_end(PROF_VEC);
   count_launch();
   ZKB_CUDA(cudaGetLastError());
   return ZKB_OK;
@@ -324,7 +330,9 @@ static int groth16_h_t(uint32_t log_n, const void* d_a, const void* d_b, const v
     ZKB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), S()));
     unsigned blocks = (unsigned)((n + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
+    prof_begin(PROF_VEC);
     check_abc_kernel<F><<<blocks, 256, 0, S()>>>(n, (const F*)d_a, (const F*)d_b, (const F*)d_c, flag);
+    prof_end(PROF_VEC);
     count_launch();
   }
   PowTable<F> fwd = d->fwd.view(), inv_t = d->inv.view();
@@ -356,8 +364,10 @@ int groth16_h_dev(int curve, uint32_t log_n, const void* d_a, const void* d_b, c
 template <class F>
 static int spmv_t(size_t n_out, size_t n_rows, const void* row_ptr, const void* col, const void* val, const void* w, void* out) {
   if (n_out == 0) return ZKB_OK;
+  prof_begin(PROF_SPMV);
   spmv_kernel<F><<<(unsigned)((n_out + 127) / 128), 128, 0, S()>>>(n_out, n_rows, (const unsigned long long*)row_ptr,
                                                                    (const uint32_t*)col, (const F*)val, (const F*)w, (F*)out);
+  prof_end(PROF_SPMV);
   count_launch();
   ZKB_CUDA(cudaGetLastError());
   return ZKB_OK;

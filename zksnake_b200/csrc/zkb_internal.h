@@ -37,6 +37,11 @@ int scratch_reserve(size_t bytes);  // make sure the arena holds at least `bytes
 void scratch_reset();
 void* scratch_take(size_t bytes);   // 256-byte aligned bump allocation; nullptr when exhausted
 void count_launch(int n = 1);
+// device-time accounting per kernel family (zkb_prof_enable / zkb_prof_read); no-ops unless enabled
+enum { PROF_NTT = 0, PROF_MSM_SORT = 1, PROF_MSM_ACCUM_G1 = 2, PROF_MSM_ACCUM_G2 = 3, PROF_MSM_REDUCE = 4, PROF_SPMV = 5,
+       PROF_VEC = 6, PROF_MISC = 7, PROF_NTAGS = 8 };
+void prof_begin(int tag);
+void prof_end(int tag);
 unsigned long long launches();
 
 // ---- NTT (ntt_host.cu) ----

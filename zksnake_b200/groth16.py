@@ -12,6 +12,7 @@ import random
 import numpy as np
 
 from . import _native as nat
+from . import dist
 from ._algebra import ec_bls12_381, ec_bn254, polynomial_bls12_381, polynomial_bn254
 from .r1cs import R1CS
 
@@ -70,7 +71,10 @@ class VerifyingKey:
 
 
 class Groth16:
-    def __init__(self, r1cs: R1CS, curve: str = "BN254"):
+    def __init__(self, r1cs: R1CS, curve: str = "BN254", shard=None):
+        """shard = (rank, world): this process keeps only its contiguous slice of the four proving-key vectors and proves
+        cooperatively with the other ranks (zksnake_b200/dist.py).  Default: the torch.distributed world, else (0, 1)."""
+        self.rank, self.world = shard if shard is not None else dist.world()
         self.curve_name = curve
         self.curve = _CURVES[curve]
         self.ec = _EC[self.curve]
@@ -110,10 +114,14 @@ class Groth16:
         K = [(L[i] * beta + R[i] * alpha + O[i]) % o for i in range(m)]
         t = self.poly.evaluate_vanishing_polynomial(n, tau)
 
-        def powers(scale):
-            d = nat.DeviceBuffer(n * 32)
-            nat.check(nat.lib.zkb_fr_powers_dev(self.curve, nat.ptr(nat.ints_to_limbs([tau])), nat.ptr(nat.ints_to_limbs([scale])),
-                                                n, d.ptr))
+        lo, hi = dist.shard_range(n, self.rank, self.world)
+        self._slice = (lo, hi)
+
+        def powers(scale):  # scale * tau^i for i in this rank's slice
+            d = nat.DeviceBuffer(max(hi - lo, 1) * 32)
+            first = scale * pow(tau, lo, o) % o
+            nat.check(nat.lib.zkb_fr_powers_dev(self.curve, nat.ptr(nat.ints_to_limbs([tau])), nat.ptr(nat.ints_to_limbs([first])),
+                                                hi - lo, d.ptr))
             return d
 
         def batch(base, group, d_scalars, count):
@@ -124,15 +132,17 @@ class Groth16:
             return out
 
         d_pow = powers(1)
-        tau_G1 = batch(G1, 1, d_pow, n)
-        tau_G2 = batch(G2, 2, d_pow, n)
+        tau_G1 = batch(G1, 1, d_pow, hi - lo)
+        tau_G2 = batch(G2, 2, d_pow, hi - lo)
         d_tgt = powers(t * inv_delta % o)
-        target_G1 = batch(G1, 1, d_tgt, n)
+        target_G1 = batch(G1, 1, d_tgt, hi - lo)
         n_priv = m - self.n_public
-        d_k = nat.DeviceBuffer(max(n_priv, 1) * 32)
-        if n_priv:
-            d_k.upload(nat.ints_to_limbs([k * inv_delta % o for k in K[self.n_public:]]))
-        k_delta_G1 = batch(G1, 1, d_k, n_priv)
+        klo, khi = dist.shard_range(n_priv, self.rank, self.world)
+        self._kslice = (klo, khi)
+        d_k = nat.DeviceBuffer(max(khi - klo, 1) * 32)
+        if khi > klo:
+            d_k.upload(nat.ints_to_limbs([k * inv_delta % o for k in K[self.n_public + klo:self.n_public + khi]]))
+        k_delta_G1 = batch(G1, 1, d_k, khi - klo)
         k_gamma_G1 = [G1 * (k * inv_gamma % o) for k in K[:self.n_public]]
         for d in (d_pow, d_tgt, d_k):
             d.free()
@@ -147,9 +157,11 @@ class Groth16:
         flat = lambda pt: np.frombuffer(pt._flat(), dtype=np.uint64).copy()  # noqa: E731
         singles = [flat(pk.alpha_1), flat(pk.beta_1), flat(pk.beta_2), flat(pk.delta_1), flat(pk.delta_2)]
         h = ctypes.c_void_p()
-        nat.check(nat.lib.zkb_groth16_pk_create(self.curve, self.log_n, pk.tau_1.ptr, pk.tau_2.ptr, pk.target_1.ptr,
-                                                pk.kdelta_1.ptr, len(pk.kdelta_1), *[nat.ptr(s) for s in singles],
-                                                ctypes.byref(h)))
+        lo, hi = self._slice
+        klo, khi = self._kslice
+        nat.check(nat.lib.zkb_groth16_pk_create_sharded(self.curve, self.log_n, pk.tau_1.ptr, pk.tau_2.ptr, pk.target_1.ptr, lo,
+                                                        hi - lo, pk.kdelta_1.ptr, self.m - self.n_public, klo, khi - klo,
+                                                        *[nat.ptr(s) for s in singles], ctypes.byref(h)))
         self._pk_handle = h
         self._singles = singles
         n_rows = max((t[0] for arr in (self.r1cs.A, self.r1cs.B, self.r1cs.C) for t in arr.triplets), default=-1) + 1
@@ -167,7 +179,7 @@ class Groth16:
     def prove(self, public_witness: list, private_witness: list) -> Proof:
         """protocol.py:115-165."""
         assert self.proving_key, "ProvingKey has not been generated"
-        assert len(self.proving_key.kdelta_1) == len(private_witness), \
+        assert self.m - self.n_public == len(private_witness), \
             "Length of kdelta_1 and private_witness must be equal"
         r = get_random_int(self.order - 1)
         s = get_random_int(self.order - 1)
@@ -178,14 +190,29 @@ class Groth16:
             raise ValueError("Failed to evaluate with the given witness") from exc
 
     def prove_packed(self, witness_limbs, r, s):
-        """witness as a (m, 4) uint64 array (already canonical) -- the zero-marshalling entry used by bench.py."""
+        """witness as a (m, 4) uint64 array (host; pinned for full H2D speed) or a DeviceBuffer holding the same bytes -- the
+        zero-marshalling entry used by bench.py."""
         g1b = nat.lib.zkb_affine_bytes(self.curve, 1) // 8
         g2b = nat.lib.zkb_affine_bytes(self.curve, 2) // 8
         oa, ob, oc = np.zeros(g1b, np.uint64), np.zeros(g2b, np.uint64), np.zeros(g1b, np.uint64)
         inf = (ctypes.c_int * 3)()
         rr, ss = nat.ints_to_limbs([r]), nat.ints_to_limbs([s])
-        nat.check(nat.lib.zkb_groth16_prove_witness(self._pk_handle, self._r1cs_handle, nat.ptr(witness_limbs), self.n_public,
-                                                    nat.ptr(rr), nat.ptr(ss), nat.ptr(oa), nat.ptr(ob), nat.ptr(oc), inf))
+        on_dev = isinstance(witness_limbs, nat.DeviceBuffer)
+        wptr = witness_limbs.ptr if on_dev else nat.ptr(witness_limbs)
+        if self.world == 1:
+            fn = nat.lib.zkb_groth16_prove_witness_dev if on_dev else nat.lib.zkb_groth16_prove_witness
+            nat.check(fn(self._pk_handle, self._r1cs_handle, wptr, self.n_public, nat.ptr(rr), nat.ptr(ss), nat.ptr(oa),
+                         nat.ptr(ob), nat.ptr(oc), inf))
+        else:
+            # every rank: witness polynomials + the five MSMs over its key slice; one all-gather; identical assembly everywhere
+            xy = np.zeros((dist.MSM_SLOTS, dist.SLOT_LIMBS), dtype=np.uint64)
+            flags = np.zeros(dist.MSM_SLOTS, dtype=np.int32)
+            nat.check(nat.lib.zkb_groth16_partial(self._pk_handle, self._r1cs_handle, wptr, int(on_dev), self.n_public,
+                                                  nat.ptr(xy), nat.ptr(flags)))
+            all_xy, all_inf = dist.all_gather_partials(xy, flags)
+            sxy, sinf = dist.add_partials(self.curve, all_xy, all_inf)
+            nat.check(nat.lib.zkb_groth16_assemble(self._pk_handle, nat.ptr(sxy), nat.ptr(sinf), nat.ptr(rr), nat.ptr(ss),
+                                                   nat.ptr(oa), nat.ptr(ob), nat.ptr(oc), inf))
         ec = self.ec
         return Proof(ec.PointG1._from_flat(oa, inf[0]), ec.PointG2._from_flat(ob, inf[1]), ec.PointG1._from_flat(oc, inf[2]))
 

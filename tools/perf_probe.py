@@ -10,10 +10,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from zksnake_b200 import _native as nat  # noqa: E402
 
 
-def rand_fr(n, seed):
+TOP_LIMB = {0: 0x30644e72e131a029, 1: 0x73eda753299d7d48}
+
+
+def rand_fr(n, seed, curve=0):
+    """uniform 256-bit values below (top limb of r) * 2^192: the digit statistics of uniform scalars mod r"""
     rng = np.random.Generator(np.random.PCG64(seed))
-    a = rng.integers(0, 2 ** 63, size=(n, 4), dtype=np.uint64)
-    a[:, 3] &= np.uint64((1 << 59) - 1)
+    a = rng.integers(0, 2 ** 64, size=(n, 4), dtype=np.uint64)
+    a[:, 3] %= np.uint64(TOP_LIMB[curve])
     return a
 
 
@@ -51,7 +55,7 @@ def make_points(curve, grp, n, seed):
     gen = np.frombuffer(b"".join(c.to_bytes(nb, "little") for c in gens), dtype=np.uint64).copy()
     d_gen = nat.DeviceBuffer(ab)
     nat.check(nat.lib.zkb_points_upload(curve, grp, nat.ptr(gen), 1, d_gen.ptr))
-    d_k = nat.DeviceBuffer(n * 32).upload(rand_fr(n, seed))
+    d_k = nat.DeviceBuffer(n * 32).upload(rand_fr(n, seed, curve))
     d_pts = nat.DeviceBuffer(n * ab)
     t0 = time.time()
     nat.check(nat.lib.zkb_batch_mul_dev(curve, grp, d_gen.ptr, 1, d_k.ptr, n, d_pts.ptr))
@@ -61,11 +65,11 @@ def make_points(curve, grp, n, seed):
     return d_pts
 
 
-def time_msm(curve, grp, log_n, reps=3, tunings=((0, 0, 0),)):
+def time_msm(curve, grp, log_n, reps=3, tunings=((0, 0, 0),), scalars=None, label=""):
     n = 1 << log_n
     ab = nat.lib.zkb_affine_bytes(curve, grp)
     d_pts = make_points(curve, grp, n, 1)
-    d_s = nat.DeviceBuffer(n * 32).upload(rand_fr(n, 2))
+    d_s = nat.DeviceBuffer(n * 32).upload(scalars if scalars is not None else rand_fr(n, 2, curve))
     out = np.zeros(ab // 8, dtype=np.uint64)
     inf = ctypes.c_int()
     for tun in tunings:
@@ -77,7 +81,17 @@ def time_msm(curve, grp, log_n, reps=3, tunings=((0, 0, 0),)):
                 nat.check(nat.lib.zkb_msm_dev(curve, grp, d_pts.ptr, d_s.ptr, n, nat.ptr(out), ctypes.byref(inf)))
         wall = (time.perf_counter() - t0) / reps * 1e3
         ms = t.ms / reps
-        print(f"msm curve={curve} g{grp} 2^{log_n} tuning={tun}: {ms:8.3f} ms (wall {wall:8.3f})  {n/ms/1e3:8.2f} Mpts/s", flush=True)
+        nat.check(nat.lib.zkb_prof_enable(1))
+        nat.check(nat.lib.zkb_msm_dev(curve, grp, d_pts.ptr, d_s.ptr, n, nat.ptr(out), ctypes.byref(inf)))
+        parts = []
+        for tag, name in ((1, "sort"), (2, "accG1"), (3, "accG2"), (4, "reduce")):
+            tms = ctypes.c_float()
+            cnt = ctypes.c_ulonglong()
+            nat.check(nat.lib.zkb_prof_read(tag, ctypes.byref(tms), ctypes.byref(cnt)))
+            if cnt.value:
+                parts.append(f"{name}={tms.value:.3f}")
+        nat.check(nat.lib.zkb_prof_enable(0))
+        print(f"msm{label} curve={curve} g{grp} 2^{log_n} tuning={tun}: {ms:8.3f} ms (wall {wall:8.3f})  {n/ms/1e3:8.2f} Mpts/s  [{' '.join(parts)}]", flush=True)
     nat.lib.zkb_msm_set_tuning(0, 0, 0)
     d_pts.free(); d_s.free()
 
@@ -93,9 +107,18 @@ if __name__ == "__main__":
                 time_ntt(0, ln)
         os.environ["ZKB_NTT_MAXK"] = "10"
         time_ntt(1, 20)
+    if what == "msm1":
+        time_msm(0, 1, 20, reps=1)
     if what in ("msm", "all"):
-        time_msm(0, 1, 20, tunings=((0, 0, 0), (16, 16, 16), (16, 64, 16), (14, 32, 16), (16, 32, 8), (16, 32, 32)))
+        time_msm(0, 1, 20, tunings=((0, 0, 0), (16, 32, 2), (15, 32, 3), (17, 32, 3), (18, 32, 3), (16, 64, 3), (16, 24, 3)))
+        n = 1 << 20
+        ones = np.zeros((n, 4), dtype=np.uint64); ones[:, 0] = 1
+        time_msm(0, 1, 20, scalars=ones, label="[all ones]")
+        bits = np.zeros((n, 4), dtype=np.uint64); bits[:, 0] = np.arange(n) % 3
+        time_msm(0, 1, 20, scalars=bits, label="[0/1/2]")
         time_msm(0, 1, 16)
+        time_msm(0, 1, 22)
+        time_msm(0, 1, 24, reps=2)
         time_msm(0, 2, 18)
         time_msm(1, 1, 20)
         time_msm(1, 2, 18)

@@ -298,14 +298,20 @@ static int groth16_msms(zkb_groth16_pk* pk, const void* d_priv) {
   const size_t bytes = pk->n * 32;
   char* w = pk->work;
   const char *d_u = w + 3 * bytes + pk->off * 32, *d_v = w + 4 * bytes + pk->off * 32, *d_h = w + 6 * bytes + pk->off * 32;
+  // enqueue MSM i+1 before recombining MSM i on the host: the host Horner steps (~0.2 ms each) hide behind GPU work
+  static MsmTicket tk[5];
+  struct { int group; const void* pts; const void* sc; size_t n; } job[5] = {
+      {1, pk->tau1, d_u, pk->len},
+      {1, pk->tau1, d_v, pk->len},
+      {2, pk->tau2, d_v, pk->len},
+      {1, pk->target1, d_h, pk->len},
+      {1, pk->kdelta1, (const char*)d_priv + pk->koff * 32, pk->klen}};
   int rc;
-  if ((rc = msm_dev(curve, 1, pk->tau1, d_u, pk->len, pk->msm_xy[0], &pk->msm_inf[0]))) return rc;
-  if ((rc = msm_dev(curve, 1, pk->tau1, d_v, pk->len, pk->msm_xy[1], &pk->msm_inf[1]))) return rc;
-  if ((rc = msm_dev(curve, 2, pk->tau2, d_v, pk->len, pk->msm_xy[2], &pk->msm_inf[2]))) return rc;
-  if ((rc = msm_dev(curve, 1, pk->target1, d_h, pk->len, pk->msm_xy[3], &pk->msm_inf[3]))) return rc;
-  if ((rc = msm_dev(curve, 1, pk->kdelta1, (const char*)d_priv + pk->koff * 32, pk->klen, pk->msm_xy[4], &pk->msm_inf[4])))
-    return rc;
-  return ZKB_OK;
+  for (int i = 0; i < 5; i++) {
+    if ((rc = msm_enqueue(curve, job[i].group, job[i].pts, job[i].sc, job[i].n, &tk[i]))) return rc;
+    if (i > 0 && (rc = msm_finish(&tk[i - 1], pk->msm_xy[i - 1], &pk->msm_inf[i - 1]))) return rc;
+  }
+  return msm_finish(&tk[4], pk->msm_xy[4], &pk->msm_inf[4]);
 }
 
 int zkb_groth16_assemble(zkb_groth16_pk* pk, const uint64_t* msm_xy, const int* msm_inf, const uint64_t r[4], const uint64_t s[4],

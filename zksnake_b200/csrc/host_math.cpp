@@ -9,13 +9,28 @@
 namespace zkb {
 
 template <class F>
-static void finish_t(const void* win_sums, uint32_t nwin, uint32_t c, uint64_t* out_xy, int* out_inf) {
-  const XYZZ<F>* w = (const XYZZ<F>*)win_sums;
+static void finish_t(const void* sums_, uint32_t nwin, uint32_t c, uint32_t nlev, const uint32_t* logk, uint32_t nbits,
+                     uint64_t* out_xy, int* out_inf) {
+  const XYZZ<F>* sums = (const XYZZ<F>*)sums_;
+  const uint32_t njobs = nlev + nbits + 1;
   XYZZ<F> acc = XYZZ<F>::inf();
   for (int i = (int)nwin - 1; i >= 0; i--) {
     if (!acc.is_inf())
       for (uint32_t k = 0; k < c; k++) acc = dbl(acc);
-    acc = add(acc, w[i]);
+    const XYZZ<F>* s = sums + (size_t)i * njobs;
+    // ws = sum_beta 2^beta A_beta
+    XYZZ<F> ws = XYZZ<F>::inf();
+    for (int beta = (int)nbits - 1; beta >= 0; beta--) {
+      if (!ws.is_inf()) ws = dbl(ws);
+      ws = add(ws, s[nlev + beta]);
+    }
+    for (int l = (int)nlev - 1; l >= 0; l--) {
+      if (!ws.is_inf())
+        for (uint32_t k = 0; k < logk[l]; k++) ws = dbl(ws);
+      ws = add(ws, s[l]);
+    }
+    ws = add(ws, s[njobs - 1]);
+    acc = add(acc, ws);
   }
   Affine<F> a = to_affine(acc);
   *out_inf = a.is_inf() ? 1 : 0;
@@ -24,11 +39,12 @@ static void finish_t(const void* win_sums, uint32_t nwin, uint32_t c, uint64_t* 
   memcpy(out_xy, &a, sizeof(a));
 }
 
-void host_msm_finish(int curve, int group, const void* win_sums, uint32_t nwin, uint32_t c, uint64_t* out_xy, int* out_inf) {
-  if (curve == ZKB_BN254 && group == 1) finish_t<Fh<FqBN254>>(win_sums, nwin, c, out_xy, out_inf);
-  else if (curve == ZKB_BN254) finish_t<Fh2<FqBN254>>(win_sums, nwin, c, out_xy, out_inf);
-  else if (group == 1) finish_t<Fh<FqBLS381>>(win_sums, nwin, c, out_xy, out_inf);
-  else finish_t<Fh2<FqBLS381>>(win_sums, nwin, c, out_xy, out_inf);
+void host_msm_finish(int curve, int group, const void* sums, uint32_t nwin, uint32_t c, uint32_t nlev, const uint32_t* logk,
+                     uint32_t nbits, uint64_t* out_xy, int* out_inf) {
+  if (curve == ZKB_BN254 && group == 1) finish_t<Fh<FqBN254>>(sums, nwin, c, nlev, logk, nbits, out_xy, out_inf);
+  else if (curve == ZKB_BN254) finish_t<Fh2<FqBN254>>(sums, nwin, c, nlev, logk, nbits, out_xy, out_inf);
+  else if (group == 1) finish_t<Fh<FqBLS381>>(sums, nwin, c, nlev, logk, nbits, out_xy, out_inf);
+  else finish_t<Fh2<FqBLS381>>(sums, nwin, c, nlev, logk, nbits, out_xy, out_inf);
 }
 
 // sum_i k_i * P_i ; scalars[i] == nullptr means k_i = 1.  Interleaved (Straus) double-and-add over all terms.

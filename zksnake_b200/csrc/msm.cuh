@@ -5,32 +5,44 @@
 // the pipeline here is
 //   1. signed-digit decomposition of every scalar into W windows of c bits (digits in [-2^(c-1), 2^(c-1)]),
 //   2. a counting sort (one radix pass keyed by (window, |digit|)) of the N*W (point, sign) references:
-//      histogram -> exclusive scan -> warp-aggregated scatter,
-//   3. bucket accumulation: every bucket is cut into segments of <= SEG references; one thread per segment
-//      runs XYZZ mixed additions (8M+2S) over its gathered affine points,
-//   4. hot buckets (many segments, e.g. all-ones witness vectors) are pre-reduced by one CTA each,
-//   5. running-sum reduction of buckets to one point per window (chunks of K buckets per thread + a tree),
-//   6. the W window sums are recombined (c doublings per window) by the host side of the C-ABI.
+//      histogram -> multi-CTA exclusive scan -> warp-aggregated scatter,
+//   3. bucket accumulation over the SORTED reference array cut into equal runs of K references: every lane of every
+//      warp adds exactly K points (XYZZ mixed additions, 8M+2S), whatever the bucket sizes are, and emits one partial
+//      sum ("piece") per bucket its run touches.  Bucket b owns the contiguous piece slots [pstart[b], pstart[b+1]):
+//      slot pstart[b] + (t - floor(start[b]/K)) for the run t.  Warps fetch runs from a global counter (persistent grid).
+//   4. buckets with more than ZKB_MSM_HOT pieces (skewed scalars, e.g. an all-ones witness vector) are folded to one
+//      piece: one warp per bucket (lane-strided sums + shuffle tree), 64 CTAs + 1 for buckets beyond ZKB_MSM_VHOT,
+//   5. bucket reduction sum_b (b+1) S_b per window.  Every XYZZ addition is ~14 dependent field multiplications, so the
+//      reduction is organised for DEPTH, not operation count: radix-8 running-sum levels while a window still has more
+//      than 512 inputs (a thread turns 8 adjacent inputs into their total R_j and the zero-based weighted sum T_j;
+//      the totals feed the next level), then one kernel of plain tree sums: U_l = sum_j T_j for every level, the
+//      bit sums A_beta = sum_{j : bit beta of j set} R_j of the last level's totals, and R_top = sum_j R_j:
+//        sum_b (b+1) S_b = R_top + U_0 + 8 (U_1 + ... + 8 (sum_beta 2^beta A_beta)),
+//   6. the per-window sums (a few KiB) go to the host, which applies the Horner steps and the c doublings per window
+//      (host_math.cpp) while the GPU already runs the next MSM.
 // Exact group law everywhere (identity operands, P+P, P-P), so results are bit-exact after affine conversion.
 #pragma once
 #include "ec.cuh"
 
 namespace zkb {
 
+#define ZKB_MSM_MAXLEV 8
+#define ZKB_MSM_MAXJOBS 32     // plain-sum jobs per window: <= MAXLEV U sums + <= 16 bit sums + R_top
+#define ZKB_MSM_HOT 4u         // buckets with more pieces are folded by a warp
+#define ZKB_MSM_VHOT 2048u     // ... by 64 CTAs
+#define ZKB_MSM_VHOT_SPLIT 64u
 struct MsmPlan {
   uint32_t c;        // window bits
   uint32_t nwin;     // W
   uint32_t nbuck;    // buckets per window = 2^(c-1)
-  uint32_t seg;      // max references per segment
-  uint32_t kchunk;   // buckets per thread in the running-sum reduction (power of two)
+  uint32_t krun;     // K: references per accumulation run
+  uint32_t nlev;     // levels of the bucket reduction
+  uint32_t logk[ZKB_MSM_MAXLEV];   // log2 of the chunk size of level l
+  uint32_t lsize[ZKB_MSM_MAXLEV + 1];  // inputs per window at level l (lsize[0] = nbuck); lsize[nlev] <= 512 are bit-summed
   unsigned long long n;         // points
-  unsigned long long max_segs;  // upper bound on the segment count
+  unsigned long long max_runs;  // upper bound on the run count  ceil(n*W / K)
 };
 
-// signed digit of window w for a canonical little-endian scalar (8 x u32); carry handled by recomputation:
-// digit_w = raw_w + carry_{w-1}, carry_w = digit_w > 2^(c-1).  carry_{w-1} depends only on lower bits, and can be
-// computed without a sequential scan: carry_{w-1} = 1 iff the scalar's low (w*c) bits, read as a number, are
-// > 2^(w*c-1) ... which is NOT equivalent in general, so the kernels below walk the windows sequentially instead.
 __device__ __forceinline__ uint32_t scalar_bits(const uint32_t* s, uint32_t pos, uint32_t c) {
   // bits [pos, pos+c) of a 256-bit value, c <= 24
   uint32_t limb = pos >> 5, off = pos & 31;
@@ -47,7 +59,7 @@ __device__ __forceinline__ void load_scalar(const uint32_t* p, uint32_t* s) {
   s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
 }
 
-// pass 1: histogram of (window, bucket)
+// pass 1: histogram of (window, bucket).  The signed digits are produced by walking the windows with a carry.
 static __global__ void msm_count_kernel(MsmPlan pl, const uint32_t* __restrict__ scalars, uint32_t* __restrict__ cnt) {
   unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   if (i >= pl.n) return;
@@ -93,51 +105,120 @@ static __global__ void msm_scatter_kernel(MsmPlan pl, const uint32_t* __restrict
   }
 }
 
-// single-CTA exclusive scan of n u32 (n up to a few million); also writes the total to out[n]
-static __global__ void __launch_bounds__(1024) scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                                    unsigned long long n) {
-  __shared__ unsigned long long part[1024];
-  const uint32_t t = threadIdx.x;
-  unsigned long long per = (n + 1023) / 1024;
-  unsigned long long lo = t * per, hi = lo + per;
-  if (hi > n) hi = n;
-  unsigned long long sum = 0;
-  for (unsigned long long i = lo; i < hi; i++) sum += in[i];
-  part[t] = sum;
-  __syncthreads();
-  // Hillis-Steele inclusive scan over 1024 partials
-  for (uint32_t off = 1; off < 1024; off <<= 1) {
-    unsigned long long v = (t >= off) ? part[t - off] : 0;
-    __syncthreads();
-    part[t] += v;
-    __syncthreads();
+// ------------------------------------------------------------------------------------------------------
+// exclusive scan of n u32 into out[0..n] (out[n] = total): per-CTA partial sums, one CTA scans the partials, per-CTA
+// rescan with its offset.  SCAN_TILE elements per CTA.
+// ------------------------------------------------------------------------------------------------------
+#define ZKB_SCAN_THREADS 256
+#define ZKB_SCAN_ITEMS 8
+#define ZKB_SCAN_TILE (ZKB_SCAN_THREADS * ZKB_SCAN_ITEMS)
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* total, uint32_t* sh /* >= 9 words */) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= (uint32_t)o) x += y;
   }
-  unsigned long long run = part[t] - sum;
-  for (unsigned long long i = lo; i < hi; i++) {
-    uint32_t v = in[i];
-    out[i] = (uint32_t)run;
+  if (lane == 31) sh[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t s = lane < (blockDim.x >> 5) ? sh[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= (uint32_t)o) s += y;
+    }
+    if (lane < (blockDim.x >> 5)) sh[lane] = s;   // inclusive over warps
+  }
+  __syncthreads();
+  uint32_t warp_off = warp ? sh[warp - 1] : 0;
+  *total = sh[(blockDim.x >> 5) - 1];
+  uint32_t r = warp_off + x - v;
+  __syncthreads();
+  return r;
+}
+
+static __global__ void __launch_bounds__(ZKB_SCAN_THREADS) scan_partial_kernel(const uint32_t* __restrict__ in,
+                                                                        uint32_t* __restrict__ part, unsigned long long n) {
+  __shared__ uint32_t sh[32];
+  unsigned long long base = (unsigned long long)blockIdx.x * ZKB_SCAN_TILE + threadIdx.x * ZKB_SCAN_ITEMS;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < ZKB_SCAN_ITEMS; k++)
+    if (base + k < n) s += in[base + k];
+  uint32_t total;
+  block_exclusive_scan_256(s, &total, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = total;
+}
+
+// one CTA of 256 threads: exclusive scan of `m` partials in place (m <= 65536), part[m] = grand total
+static __global__ void __launch_bounds__(ZKB_SCAN_THREADS) scan_spine_kernel(uint32_t* part, uint32_t m) {
+  __shared__ uint32_t sh[32];
+  uint32_t per = (m + ZKB_SCAN_THREADS - 1) / ZKB_SCAN_THREADS;
+  uint32_t lo = threadIdx.x * per, hi = lo + per;
+  if (hi > m) hi = m;
+  uint32_t s = 0;
+  for (uint32_t i = lo; i < hi; i++) s += part[i];
+  uint32_t total;
+  uint32_t run = block_exclusive_scan_256(s, &total, sh);
+  for (uint32_t i = lo; i < hi; i++) {
+    uint32_t v = part[i];
+    part[i] = run;
     run += v;
   }
-  if (t == 1023) out[n] = (uint32_t)part[1023];
+  if (threadIdx.x == 0) part[m] = total;
 }
 
-// nseg[b] = ceil(cnt[b] / seg)
-static __global__ void msm_nseg_kernel(MsmPlan pl, const uint32_t* __restrict__ cnt, uint32_t* __restrict__ nseg) {
-  unsigned long long b = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-  if (b >= (unsigned long long)pl.nwin * pl.nbuck) return;
-  nseg[b] = (cnt[b] + pl.seg - 1) / pl.seg;
+static __global__ void __launch_bounds__(ZKB_SCAN_THREADS) scan_final_kernel(const uint32_t* __restrict__ in,
+                                                                      uint32_t* __restrict__ out,
+                                                                      const uint32_t* __restrict__ part,
+                                                                      unsigned long long n, uint32_t nparts) {
+  __shared__ uint32_t sh[32];
+  unsigned long long base = (unsigned long long)blockIdx.x * ZKB_SCAN_TILE + threadIdx.x * ZKB_SCAN_ITEMS;
+  uint32_t v[ZKB_SCAN_ITEMS];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < ZKB_SCAN_ITEMS; k++) {
+    v[k] = (base + k < n) ? in[base + k] : 0;
+    s += v[k];
+  }
+  uint32_t total;
+  uint32_t run = block_exclusive_scan_256(s, &total, sh) + part[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < ZKB_SCAN_ITEMS; k++) {
+    if (base + k < n) out[base + k] = run;
+    run += v[k];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = part[nparts];
 }
 
-// seg_bucket[segstart[b] + k] = b ; buckets with more than HOT segments are appended to the hot list
-#define ZKB_MSM_HOT 8u
-static __global__ void msm_segfill_kernel(MsmPlan pl, const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ segstart,
-                                   uint32_t* __restrict__ seg_bucket, uint32_t* __restrict__ hot_list,
-                                   uint32_t* __restrict__ hot_count) {
+// ------------------------------------------------------------------------------------------------------
+// piece planning: bucket b with references [start, start+cnt) is touched by the runs floor(start/K) .. floor((start+cnt-1)/K)
+//   npieces[b] = that count (0 for an empty bucket), np_eff[b] = the same (rewritten to 1 by the folds),
+//   run_bucket[t] = b for every run t whose first reference t*K lies in b,
+//   buckets with more than ZKB_MSM_HOT / ZKB_MSM_VHOT pieces are appended to the hot / very hot list.
+//   counters: [0] hot count, [1] accumulate work counter, [2] very hot count
+// ------------------------------------------------------------------------------------------------------
+static __global__ void msm_piece_plan_kernel(MsmPlan pl, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ start,
+                                      uint32_t* __restrict__ npieces, uint32_t* __restrict__ np_eff,
+                                      uint32_t* __restrict__ run_bucket, uint32_t* __restrict__ hot_list,
+                                      uint32_t* __restrict__ vhot_list, uint32_t* __restrict__ counters) {
   unsigned long long b = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   if (b >= (unsigned long long)pl.nwin * pl.nbuck) return;
-  uint32_t ns = nseg[b], st = segstart[b];
-  for (uint32_t k = 0; k < ns; k++) seg_bucket[st + k] = (uint32_t)b;
-  if (ns > ZKB_MSM_HOT) hot_list[atomicAdd(hot_count, 1u)] = (uint32_t)b;
+  uint32_t n = cnt[b], st = start[b];
+  uint32_t np = 0;
+  if (n) {
+    uint32_t first = st / pl.krun, last = (st + n - 1) / pl.krun;
+    np = last - first + 1;
+    uint32_t t0 = (st % pl.krun) ? first + 1 : first;   // runs that BEGIN inside this bucket
+    for (uint32_t t = t0; t <= last; t++) run_bucket[t] = (uint32_t)b;
+    if (np > ZKB_MSM_VHOT) vhot_list[atomicAdd(counters + 2, 1u)] = (uint32_t)b;
+    else if (np > ZKB_MSM_HOT) hot_list[atomicAdd(counters, 1u)] = (uint32_t)b;
+  }
+  npieces[b] = np;
+  np_eff[b] = np;
 }
 
 template <class F>
@@ -150,103 +231,257 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F>* p) {
   for (int i = 0; i < (int)(sizeof(Affine<F>) / 16); i++) d[i] = __ldg(q + i);
   return r;
 }
+template <class T>
+__device__ __forceinline__ void store_vec(T* dst, const T& v) {
+  const uint4* s = reinterpret_cast<const uint4*>(&v);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+}
+template <class T>
+__device__ __forceinline__ T load_vec(const T* src) {
+  T r;
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+  return r;
+}
 
-// pass 3: one thread per segment
-template <class F>
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(MsmPlan pl, const Affine<F>* __restrict__ points,
-                                                             const uint32_t* __restrict__ refs,
-                                                             const uint32_t* __restrict__ cnt,
-                                                             const uint32_t* __restrict__ start,
-                                                             const uint32_t* __restrict__ segstart,
-                                                             const uint32_t* __restrict__ seg_bucket,
-                                                             XYZZ<F>* __restrict__ seg_sum) {
-  unsigned long long s = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+// pass 3: persistent grid; a warp takes 32 consecutive runs at a time from `work`, lane l owns run 32*item + l, i.e. the
+// sorted references [t*K, t*K + K).  F may be the inline-multiplier twin of the stored field (same layout).
+template <class F, int MINB>
+__global__ void __launch_bounds__(128, MINB) msm_accumulate_kernel(MsmPlan pl, const Affine<F>* __restrict__ points,
+                                                                    const uint32_t* __restrict__ refs,
+                                                                    const uint32_t* __restrict__ start,
+                                                                    const uint32_t* __restrict__ pstart,
+                                                                    const uint32_t* __restrict__ run_bucket,
+                                                                    XYZZ<F>* __restrict__ pieces,
+                                                                    unsigned int* __restrict__ work) {
   const unsigned long long nb = (unsigned long long)pl.nwin * pl.nbuck;
-  uint32_t total = segstart[nb];
-  if (s >= total) return;
-  uint32_t b = seg_bucket[s];
-  uint32_t k = (uint32_t)s - segstart[b];
-  uint32_t lo = start[b] + k * pl.seg;
-  uint32_t hi = start[b] + cnt[b];
-  if (hi > lo + pl.seg) hi = lo + pl.seg;
-  XYZZ<F> acc = XYZZ<F>::inf();
-  for (uint32_t r = lo; r < hi; r++) {
-    uint32_t ref = refs[r];
-    Affine<F> p = load_affine(points + (ref & 0x7fffffffu));
-    madd(acc, p, (ref >> 31) != 0);
-  }
-  seg_sum[s] = acc;
-}
-
-// pass 4: hot buckets -- one CTA folds all segment sums of a bucket into its first segment slot and
-// rewrites nseg[b] = 1.  Tree in shared memory.
-template <class F>
-__global__ void __launch_bounds__(128) msm_hot_kernel(const uint32_t* __restrict__ hot_list,
-                                                      const uint32_t* __restrict__ hot_count,
-                                                      uint32_t* __restrict__ nseg, const uint32_t* __restrict__ segstart,
-                                                      XYZZ<F>* __restrict__ seg_sum) {
-  extern __shared__ uint4 hot_smem[];
-  XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(hot_smem);
-  const uint32_t t = threadIdx.x;
-  uint32_t nh = *hot_count;
-  for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
-    uint32_t b = hot_list[h];
-    uint32_t ns = nseg[b], st = segstart[b];
+  const uint32_t total = start[nb];
+  const uint32_t K = pl.krun;
+  const uint32_t nruns = (total + K - 1) / K;
+  const uint32_t nitems = (nruns + 31) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  for (;;) {
+    uint32_t item = 0;
+    if (lane == 0) item = atomicAdd(work, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= nitems) break;
+    uint32_t t = (item << 5) + lane;
+    if (t >= nruns) continue;
+    uint32_t pos = t * K;
+    uint32_t end = pos + K;
+    if (end > total) end = total;
+    uint32_t b = run_bucket[t];
+    uint32_t bend = start[b + 1];
+    uint32_t slot = pstart[b] + (t - start[b] / K);
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t k = t; k < ns; k += blockDim.x) acc = add(acc, seg_sum[st + k]);
-    sh[t] = acc;
-    __syncthreads();
-    for (uint32_t off = blockDim.x >> 1; off > 0; off >>= 1) {
-      if (t < off) sh[t] = add(sh[t], sh[t + off]);
-      __syncthreads();
+    // one-ahead software prefetch of the gathered point where the register file allows it (G1)
+    constexpr bool PREFETCH = sizeof(Affine<F>) <= 96;
+    uint32_t ref_next = refs[pos];
+    Affine<F> p_next;
+    if (PREFETCH) p_next = load_affine(points + (ref_next & 0x7fffffffu));
+    for (uint32_t p = pos; p < end; p++) {
+      uint32_t ref = ref_next;
+      Affine<F> pt;
+      if (PREFETCH) {
+        pt = p_next;
+        if (p + 1 < end) {
+          ref_next = refs[p + 1];
+          p_next = load_affine(points + (ref_next & 0x7fffffffu));
+        }
+      } else {
+        pt = load_affine(points + (ref & 0x7fffffffu));
+        if (p + 1 < end) ref_next = refs[p + 1];
+      }
+      if (p == bend) {   // the run crosses into the next non-empty bucket: emit the finished piece
+        store_vec(pieces + slot, acc);
+        acc = XYZZ<F>::inf();
+        do {
+          b++;
+          bend = start[b + 1];
+        } while (bend == p);
+        slot = pstart[b];
+      }
+      madd(acc, pt, (ref >> 31) != 0);
     }
-    if (t == 0) {
-      seg_sum[st] = sh[0];
-      nseg[b] = 1;
-    }
-    __syncthreads();
+    store_vec(pieces + slot, acc);
   }
 }
 
-// pass 5a: per chunk of K buckets: sum_b (b+1) * B_b  restricted to the chunk  ->  contrib[chunk]
-template <class F>
-__global__ void __launch_bounds__(128) msm_bucket_reduce_kernel(MsmPlan pl, const uint32_t* __restrict__ nseg,
-                                                                const uint32_t* __restrict__ segstart,
-                                                                const XYZZ<F>* __restrict__ seg_sum,
-                                                                XYZZ<F>* __restrict__ contrib) {
-  unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-  const uint32_t chunks_per_win = pl.nbuck / pl.kchunk;
-  if (t >= (unsigned long long)pl.nwin * chunks_per_win) return;
-  uint32_t w = (uint32_t)(t / chunks_per_win), j = (uint32_t)(t % chunks_per_win);
-  uint32_t b0 = j * pl.kchunk;
-  XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
-  for (int idx = (int)pl.kchunk - 1; idx >= 0; idx--) {
-    unsigned long long b = (unsigned long long)w * pl.nbuck + b0 + idx;
-    uint32_t ns = nseg[b], st = segstart[b];
-    for (uint32_t k = 0; k < ns; k++) run = add(run, seg_sum[st + k]);
-    acc = add(acc, run);
-  }
-  // acc = sum (idx+1) B ; chunk offset adds b0 * run
-  if (b0) acc = add(acc, mul_small(run, b0));
-  contrib[t] = acc;
+// warp-shuffle of a whole struct (sizeof multiple of 4)
+template <class T>
+__device__ __forceinline__ T shfl_down_struct(const T& v, uint32_t delta) {
+  T r;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 4); i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], delta);
+  return r;
 }
 
-// pass 5b: one CTA per window: sum of its chunk contributions
+// CTA-wide sum of one XYZZ per thread through shared memory (blockDim.x a power of two); result valid in thread 0
 template <class F>
-__global__ void __launch_bounds__(128) msm_window_sum_kernel(uint32_t chunks_per_win, const XYZZ<F>* __restrict__ contrib,
-                                                             XYZZ<F>* __restrict__ win_sum) {
-  extern __shared__ uint4 ws_smem[];
-  XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(ws_smem);
-  const uint32_t t = threadIdx.x, w = blockIdx.x;
-  XYZZ<F> acc = XYZZ<F>::inf();
-  for (uint32_t k = t; k < chunks_per_win; k += blockDim.x) acc = add(acc, contrib[(unsigned long long)w * chunks_per_win + k]);
-  sh[t] = acc;
+__device__ __forceinline__ XYZZ<F> block_sum(XYZZ<F> acc, XYZZ<F>* sh) {
+  const uint32_t t = threadIdx.x;
+  store_vec(sh + t, acc);
   __syncthreads();
   for (uint32_t off = blockDim.x >> 1; off > 0; off >>= 1) {
-    if (t < off) sh[t] = add(sh[t], sh[t + off]);
+    if (t < off) {
+      acc = add(acc, load_vec(sh + t + off));
+      store_vec(sh + t, acc);
+    }
     __syncthreads();
   }
-  if (t == 0) win_sum[w] = sh[0];
+  return acc;
+}
+
+// pass 4a: one warp per hot bucket: lane-strided sums, shuffle tree, result into the bucket's first piece slot
+template <class F>
+__global__ void __launch_bounds__(128) msm_fold_warp_kernel(const uint32_t* __restrict__ hot_list,
+                                                            const uint32_t* __restrict__ counters,
+                                                            uint32_t* __restrict__ np_eff, const uint32_t* __restrict__ pstart,
+                                                            XYZZ<F>* __restrict__ pieces) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t nh = counters[0];
+  for (uint32_t h = warp; h < nh; h += nwarps) {
+    uint32_t b = hot_list[h];
+    uint32_t ns = np_eff[b], st = pstart[b];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t k = lane; k < ns; k += 32) acc = add(acc, load_vec(pieces + st + k));
+#pragma unroll 1
+    for (uint32_t off = 16; off > 0; off >>= 1) {
+      XYZZ<F> other = shfl_down_struct(acc, off);
+      if (lane < off) acc = add(acc, other);
+    }
+    if (lane == 0) {
+      store_vec(pieces + st, acc);
+      np_eff[b] = 1;
+    }
+  }
+}
+
+// pass 4b: very hot buckets: CTA (j, .) sums the j-th of ZKB_MSM_VHOT_SPLIT slices of the bucket's pieces into side[h][j]
+template <class F>
+__global__ void __launch_bounds__(128) msm_fold_cta1_kernel(const uint32_t* __restrict__ vhot_list,
+                                                            const uint32_t* __restrict__ counters,
+                                                            const uint32_t* __restrict__ np_eff,
+                                                            const uint32_t* __restrict__ pstart,
+                                                            const XYZZ<F>* __restrict__ pieces, XYZZ<F>* __restrict__ side) {
+  extern __shared__ uint4 fold_smem[];
+  XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(fold_smem);
+  const uint32_t nv = counters[2];
+  for (uint32_t h = blockIdx.y; h < nv; h += gridDim.y) {
+    uint32_t b = vhot_list[h];
+    uint32_t ns = np_eff[b], st = pstart[b];
+    uint32_t per = (ns + ZKB_MSM_VHOT_SPLIT - 1) / ZKB_MSM_VHOT_SPLIT;
+    uint32_t lo = blockIdx.x * per, hi = lo + per;
+    if (hi > ns) hi = ns;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t k = lo + threadIdx.x; k < hi; k += blockDim.x) acc = add(acc, load_vec(pieces + st + k));
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) store_vec(side + (size_t)h * ZKB_MSM_VHOT_SPLIT + blockIdx.x, acc);
+    __syncthreads();
+  }
+}
+// pass 4c: one CTA of ZKB_MSM_VHOT_SPLIT threads per very hot bucket adds the slice sums
+template <class F>
+__global__ void __launch_bounds__(ZKB_MSM_VHOT_SPLIT) msm_fold_cta2_kernel(const uint32_t* __restrict__ vhot_list,
+                                                                           const uint32_t* __restrict__ counters,
+                                                                           uint32_t* __restrict__ np_eff,
+                                                                           const uint32_t* __restrict__ pstart,
+                                                                           XYZZ<F>* __restrict__ pieces,
+                                                                           const XYZZ<F>* __restrict__ side) {
+  extern __shared__ uint4 fold_smem[];
+  XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(fold_smem);
+  const uint32_t nv = counters[2];
+  for (uint32_t h = blockIdx.x; h < nv; h += gridDim.x) {
+    uint32_t b = vhot_list[h];
+    XYZZ<F> acc = load_vec(side + (size_t)h * ZKB_MSM_VHOT_SPLIT + threadIdx.x);
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) {
+      store_vec(pieces + pstart[b], acc);
+      np_eff[b] = 1;
+    }
+    __syncthreads();
+  }
+}
+
+// pass 5, level 0: thread (w, j) folds the buckets [j*k, (j+1)*k) of window w:  R = sum_i S_i,  T = sum_i i * S_i
+// (S_i = the bucket's <= ZKB_MSM_HOT pieces added up).  Outputs at [w * (nbuck/k) + j].
+template <class F>
+__global__ void __launch_bounds__(128) msm_level0_kernel(MsmPlan pl, const uint32_t* __restrict__ np_eff,
+                                                         const uint32_t* __restrict__ pstart,
+                                                         const XYZZ<F>* __restrict__ pieces, XYZZ<F>* __restrict__ t_out,
+                                                         XYZZ<F>* __restrict__ r_out) {
+  unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  const uint32_t logk = pl.logk[0];
+  const uint32_t per_win = pl.nbuck >> logk;
+  if (t >= (unsigned long long)pl.nwin * per_win) return;
+  uint32_t w = (uint32_t)(t / per_win), j = (uint32_t)(t % per_win);
+  unsigned long long b0 = (unsigned long long)w * pl.nbuck + ((unsigned long long)j << logk);
+  XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
+  for (int i = (1 << logk) - 1; i >= 0; i--) {
+    uint32_t ns = np_eff[b0 + i], st = pstart[b0 + i];
+    for (uint32_t k = 0; k < ns; k++) run = add(run, load_vec(pieces + st + k));
+    if (i > 0) acc = add(acc, run);
+  }
+  store_vec(t_out + t, acc);
+  store_vec(r_out + t, run);
+}
+
+// pass 5, level l > 0: the same fold over the previous level's totals
+template <class F>
+__global__ void __launch_bounds__(128) msm_level_kernel(uint32_t nwin, uint32_t in_per_win, uint32_t logk,
+                                                        const XYZZ<F>* __restrict__ r_in, XYZZ<F>* __restrict__ t_out,
+                                                        XYZZ<F>* __restrict__ r_out) {
+  unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  const uint32_t per_win = in_per_win >> logk;
+  if (t >= (unsigned long long)nwin * per_win) return;
+  uint32_t w = (uint32_t)(t / per_win), j = (uint32_t)(t % per_win);
+  const XYZZ<F>* src = r_in + (unsigned long long)w * in_per_win + ((unsigned long long)j << logk);
+  XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
+  for (int i = (1 << logk) - 1; i >= 0; i--) {
+    run = add(run, load_vec(src + i));
+    if (i > 0) acc = add(acc, run);
+  }
+  store_vec(t_out + t, acc);
+  store_vec(r_out + t, run);
+}
+
+// pass 5b: plain sums.  Job q of window w adds base[w * count + j] over the j < count with bit `bit` of j set
+// (bit < 0: all j) -> out[w * njobs + q].  grid (njobs, nwin).
+template <class F>
+struct SumJobs {
+  const XYZZ<F>* base[ZKB_MSM_MAXJOBS];
+  uint32_t count[ZKB_MSM_MAXJOBS];
+  int bit[ZKB_MSM_MAXJOBS];
+};
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS) msm_sums_kernel(SumJobs<F> jobs, uint32_t njobs, XYZZ<F>* __restrict__ out) {
+  extern __shared__ uint4 ws_smem[];
+  XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(ws_smem);
+  const uint32_t t = threadIdx.x, q = blockIdx.x, w = blockIdx.y;
+  const uint32_t cntq = jobs.count[q];
+  const int bit = jobs.bit[q];
+  const XYZZ<F>* src = jobs.base[q] + (unsigned long long)w * cntq;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  if (bit < 0) {
+    for (uint32_t k = t; k < cntq; k += blockDim.x) acc = add(acc, load_vec(src + k));
+  } else {
+    // the indices with the bit set, enumerated densely: insert a 1 at position `bit` of m < count/2
+    const uint32_t lowmask = (1u << bit) - 1;
+    for (uint32_t m = t; m < (cntq >> 1); m += blockDim.x) {
+      uint32_t k = ((m & ~lowmask) << 1) | (1u << bit) | (m & lowmask);
+      acc = add(acc, load_vec(src + k));
+    }
+  }
+  acc = block_sum(acc, sh);
+  if (t == 0) store_vec(out + w * njobs + q, acc);
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -1,5 +1,6 @@
 // msm_common.cu -- (curve, group) dispatch for the MSM and point-vector entry points.
 #include <cuda_runtime.h>
+#include <string.h>
 #include "zkb_internal.h"
 
 namespace zkb {
@@ -12,7 +13,7 @@ void msm_set_tuning(int c, int seg, int kchunk) {
 }
 
 #define DECL(SUFFIX)                                                                      \
-  int msm_run_##SUFFIX(const void* p, const void* s, size_t n, uint64_t* o, int* inf);  \
+  int msm_enqueue_##SUFFIX(const void* p, const void* s, size_t n, MsmTicket* tk);      \
   int points_conv_##SUFFIX(int to, size_t n, void* p);                                   \
   int batch_mul_##SUFFIX(const void* b, int single, const void* s, size_t n, void* o);
 DECL(g1bn) DECL(g2bn) DECL(g1bls) DECL(g2bls)
@@ -24,9 +25,49 @@ DECL(g1bn) DECL(g2bn) DECL(g1bls) DECL(g2bls)
   if (curve == ZKB_BLS12_381 && group == 2) return CALL_BL2;              \
   return set_error(ZKB_ERR_ARG, "unknown (curve, group)");
 
+int ticket_reserve(MsmTicket* tk, size_t bytes) {
+  if (!tk->event) {
+    cudaEvent_t e;
+    ZKB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    tk->event = (void*)e;
+  }
+  if (bytes > tk->host_cap) {
+    if (tk->host) ZKB_CUDA(cudaFreeHost(tk->host));
+    tk->host = nullptr;
+    tk->host_cap = 0;
+    size_t cap = bytes + 4096;
+    ZKB_CUDA(cudaHostAlloc((void**)&tk->host, cap, cudaHostAllocDefault));
+    tk->host_cap = cap;
+  }
+  return ZKB_OK;
+}
+void ticket_release(MsmTicket* tk) {
+  if (tk->host) cudaFreeHost(tk->host);
+  if (tk->event) cudaEventDestroy((cudaEvent_t)tk->event);
+  tk->host = nullptr;
+  tk->host_cap = 0;
+  tk->event = nullptr;
+}
+int msm_enqueue(int curve, int group, const void* p, const void* s, size_t n, MsmTicket* tk) {
+  DISPATCH(msm_enqueue_g1bn(p, s, n, tk), msm_enqueue_g2bn(p, s, n, tk), msm_enqueue_g1bls(p, s, n, tk),
+           msm_enqueue_g2bls(p, s, n, tk))
+}
+int msm_finish(MsmTicket* tk, uint64_t* out_xy, int* out_inf) {
+  if (tk->empty) {
+    memset(out_xy, 0, affine_bytes(tk->curve, tk->group));
+    *out_inf = 1;
+    return ZKB_OK;
+  }
+  ZKB_CUDA(cudaEventSynchronize((cudaEvent_t)tk->event));
+  host_msm_finish(tk->curve, tk->group, tk->host, tk->nwin, tk->c, tk->nlev, tk->logk, tk->nbits, out_xy, out_inf);
+  tk->empty = true;
+  return ZKB_OK;
+}
 int msm_dev(int curve, int group, const void* p, const void* s, size_t n, uint64_t* o, int* inf) {
-  DISPATCH(msm_run_g1bn(p, s, n, o, inf), msm_run_g2bn(p, s, n, o, inf), msm_run_g1bls(p, s, n, o, inf),
-           msm_run_g2bls(p, s, n, o, inf))
+  static MsmTicket tk;
+  int rc = msm_enqueue(curve, group, p, s, n, &tk);
+  if (rc) return rc;
+  return msm_finish(&tk, o, inf);
 }
 int points_to_mont_dev(int curve, int group, size_t n, void* p) {
   DISPATCH(points_conv_g1bn(1, n, p), points_conv_g2bn(1, n, p), points_conv_g1bls(1, n, p), points_conv_g2bls(1, n, p))

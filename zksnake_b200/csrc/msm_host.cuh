@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdlib.h>
+#include <string.h>
 #include <vector>
 #include "msm.cuh"
 #include "zkb_internal.h"
@@ -12,103 +13,175 @@ extern int g_msm_c, g_msm_seg, g_msm_kchunk;   // tuning overrides (0 = heuristi
 
 static inline cudaStream_t MS() { return (cudaStream_t)ctx_stream(); }
 
+// the inline-multiplier twin of a stored field (identical layout; only the device code generation differs)
+template <class P> struct InlineMul : P { static constexpr bool NOINLINE_MUL = false; };
+template <class F> struct AccumField { typedef F type; static constexpr int MINB = 2; };
+// G1: the fully inlined XYZZ addition is ~9-15 % faster than calling the multiplier out of line (tools/ffbench.cu);
+// G2 (Fp2 Karatsuba, ~30 multiplier bodies per addition) is faster out of line.
+template <> struct AccumField<Fp<FqBN254>> { typedef Fp<InlineMul<FqBN254>> type; static constexpr int MINB = 4; };
+template <> struct AccumField<Fp<FqBLS381>> { typedef Fp<InlineMul<FqBLS381>> type; static constexpr int MINB = 3; };
+
 inline MsmPlan msm_make_plan(size_t n, uint32_t scalar_bits) {
   MsmPlan pl;
+  memset(&pl, 0, sizeof(pl));
   uint32_t logn = 0;
   while (((size_t)1 << logn) < n) logn++;
   int c = g_msm_c ? g_msm_c : (int)logn - 4;
   if (c < 3) c = 3;
-  if (c > 16) c = 16;
+  if (c > 22) c = 22;
   pl.c = (uint32_t)c;
   pl.nwin = (scalar_bits + 1 + pl.c - 1) / pl.c;
   pl.nbuck = 1u << (pl.c - 1);
-  pl.seg = g_msm_seg ? (uint32_t)g_msm_seg : 32u;
-  uint32_t k = g_msm_kchunk ? (uint32_t)g_msm_kchunk : 16u;
-  while (k > pl.nbuck) k >>= 1;
-  // keep at least ~16k threads in the bucket reduction when the bucket count allows it
-  while (k > 2 && (size_t)pl.nwin * pl.nbuck / k < 16384) k >>= 1;
-  pl.kchunk = k;
+  pl.krun = g_msm_seg ? (uint32_t)g_msm_seg : 32u;
+  uint32_t maxlog = g_msm_kchunk ? (uint32_t)g_msm_kchunk : 3u;   // log2 of the reduction radix
+  if (maxlog < 1) maxlog = 1;
+  if (maxlog > 5) maxlog = 5;
+  // level 0 always runs (it is what reads the pieces); further levels while a window has more than 512 inputs
+  pl.lsize[0] = pl.nbuck;
+  uint32_t l = 0;
+  do {
+    uint32_t lg = 0;
+    while ((2u << lg) <= pl.lsize[l] && lg + 1 <= maxlog) lg++;
+    pl.logk[l] = lg;
+    pl.lsize[l + 1] = pl.lsize[l] >> lg;
+    l++;
+  } while (pl.lsize[l] > 512 && l < ZKB_MSM_MAXLEV);
+  pl.nlev = l;
   pl.n = n;
-  pl.max_segs = (unsigned long long)pl.nwin * pl.nbuck + ((unsigned long long)n * pl.nwin) / pl.seg + 1;
+  pl.max_runs = ((unsigned long long)n * pl.nwin + pl.krun - 1) / pl.krun;
   return pl;
 }
 
+// exclusive scan of n u32 -> out[0..n]; `part` holds ceil(n / SCAN_TILE) + 1 words
+static inline void scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* part, cudaStream_t st) {
+  uint32_t nparts = (uint32_t)((n + ZKB_SCAN_TILE - 1) / ZKB_SCAN_TILE);
+  scan_partial_kernel<<<nparts, ZKB_SCAN_THREADS, 0, st>>>(in, part, n);
+  scan_spine_kernel<<<1, ZKB_SCAN_THREADS, 0, st>>>(part, nparts);
+  scan_final_kernel<<<nparts, ZKB_SCAN_THREADS, 0, st>>>(in, out, part, n, nparts);
+}
+
+// Enqueues every kernel of one MSM on the library stream plus the device->host copy of the per-window sums into the
+// ticket's pinned buffer; returns without synchronising.  msm_finish_ticket() waits for the copy and recombines on the host.
 template <class F, int SCALAR_BITS>
-int msm_run(int curve, int group, const void* d_points, const void* d_scalars, size_t n, uint64_t* out_xy, int* out_inf) {
-  typedef XYZZ<F> X;
-  size_t abytes = sizeof(Affine<F>);
-  if (n == 0) {
-    memset(out_xy, 0, abytes);
-    *out_inf = 1;
-    return ZKB_OK;
-  }
+int msm_enqueue_t(int curve, int group, const void* d_points, const void* d_scalars, size_t n, MsmTicket* tk) {
+  typedef typename AccumField<F>::type FA;   // G1: inline-multiplier twin (same layout); G2: F itself
+  typedef XYZZ<FA> X;
+  static_assert(sizeof(FA) == sizeof(F), "inline twin must share the layout");
+  tk->curve = curve;
+  tk->group = group;
+  tk->empty = (n == 0);
+  if (n == 0) return ZKB_OK;
   if (n >= ((size_t)1 << 31)) return set_error(ZKB_ERR_ARG, "msm: more than 2^31-1 points");
+  constexpr int SUM_THREADS = sizeof(X) <= 192 ? 256 : 128;
   static bool attr_set = false;
   if (!attr_set) {
-    ZKB_CUDA(cudaFuncSetAttribute(msm_hot_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (int)sizeof(X)));
-    ZKB_CUDA(cudaFuncSetAttribute(msm_window_sum_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (int)sizeof(X)));
+    ZKB_CUDA(cudaFuncSetAttribute(msm_fold_cta1_kernel<FA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (int)sizeof(X)));
+    ZKB_CUDA(cudaFuncSetAttribute(msm_fold_cta2_kernel<FA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)ZKB_MSM_VHOT_SPLIT * (int)sizeof(X)));
+    ZKB_CUDA(cudaFuncSetAttribute(msm_sums_kernel<FA, SUM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SUM_THREADS * (int)sizeof(X)));
     attr_set = true;
   }
   MsmPlan pl = msm_make_plan(n, SCALAR_BITS);
   const size_t nb = (size_t)pl.nwin * pl.nbuck;
   const size_t nrefs = n * pl.nwin;
   if (nrefs >= ((size_t)1 << 32)) return set_error(ZKB_ERR_ARG, "msm: n * windows exceeds 2^32 references");
-  const uint32_t chunks_per_win = pl.nbuck / pl.kchunk;
-  const size_t nchunks = (size_t)pl.nwin * chunks_per_win;
+  const size_t max_pieces = pl.max_runs + nb + 1;
+  const size_t nparts = (nb + ZKB_SCAN_TILE - 1) / ZKB_SCAN_TILE + 2;
+  const size_t max_vhot = pl.max_runs / ZKB_MSM_VHOT + 1;
+  size_t lev_elems = 0;   // T and R arrays of all levels
+  for (uint32_t l = 0; l < pl.nlev; l++) lev_elems += (size_t)pl.nwin * pl.lsize[l + 1];
+  const uint32_t m = pl.lsize[pl.nlev];
+  uint32_t nbits = 0;
+  while ((1u << nbits) < m) nbits++;
+  const uint32_t njobs = pl.nlev + nbits + 1;
+  if (njobs > ZKB_MSM_MAXJOBS) return set_error(ZKB_ERR_ARG, "msm: too many reduction jobs");
+  const size_t out_bytes = (size_t)pl.nwin * njobs * sizeof(X);
 
-  size_t need = (nb + 1) * 4 * 5 + nrefs * 4 + pl.max_segs * 4 + nb * 4 + pl.max_segs * sizeof(X) + nchunks * sizeof(X) +
-                pl.nwin * sizeof(X) + 64 * 256;
+  size_t need = (nb + 1) * 4 * 6 + nrefs * 4 + (pl.max_runs + 1) * 4 + nb * 4 + max_vhot * 4 + nparts * 4 +
+                max_pieces * sizeof(X) + 2 * lev_elems * sizeof(X) + max_vhot * ZKB_MSM_VHOT_SPLIT * sizeof(X) + out_bytes +
+                64 * 256;
   int rc;
   if ((rc = scratch_reserve(need))) return rc;
+  if ((rc = ticket_reserve(tk, out_bytes))) return rc;
   scratch_reset();
   uint32_t* cnt = (uint32_t*)scratch_take((nb + 1) * 4);
   uint32_t* start = (uint32_t*)scratch_take((nb + 1) * 4);
   uint32_t* cursor = (uint32_t*)scratch_take((nb + 1) * 4);
-  uint32_t* nseg = (uint32_t*)scratch_take((nb + 1) * 4);
-  uint32_t* segstart = (uint32_t*)scratch_take((nb + 1) * 4);
+  uint32_t* npieces = (uint32_t*)scratch_take((nb + 1) * 4);
+  uint32_t* np_eff = (uint32_t*)scratch_take((nb + 1) * 4);
+  uint32_t* pstart = (uint32_t*)scratch_take((nb + 1) * 4);
   uint32_t* refs = (uint32_t*)scratch_take(nrefs * 4);
-  uint32_t* seg_bucket = (uint32_t*)scratch_take(pl.max_segs * 4);
+  uint32_t* run_bucket = (uint32_t*)scratch_take((pl.max_runs + 1) * 4);
   uint32_t* hot_list = (uint32_t*)scratch_take(nb * 4);
-  uint32_t* hot_count = (uint32_t*)scratch_take(256);
-  X* seg_sum = (X*)scratch_take(pl.max_segs * sizeof(X));
-  X* contrib = (X*)scratch_take(nchunks * sizeof(X));
-  X* win_sum = (X*)scratch_take(pl.nwin * sizeof(X));
-  if (!cnt || !start || !cursor || !nseg || !segstart || !refs || !seg_bucket || !hot_list || !hot_count || !seg_sum ||
-      !contrib || !win_sum)
+  uint32_t* vhot_list = (uint32_t*)scratch_take(max_vhot * 4);
+  uint32_t* part = (uint32_t*)scratch_take(nparts * 4);
+  uint32_t* counters = (uint32_t*)scratch_take(256);   // [0] hot count, [1] accumulate work counter, [2] very hot count
+  X* pieces = (X*)scratch_take(max_pieces * sizeof(X));
+  X* lev_t = (X*)scratch_take(lev_elems * sizeof(X));
+  X* lev_r = (X*)scratch_take(lev_elems * sizeof(X));
+  X* side = (X*)scratch_take(max_vhot * ZKB_MSM_VHOT_SPLIT * sizeof(X));
+  X* sums = (X*)scratch_take(out_bytes);
+  if (!cnt || !start || !cursor || !npieces || !np_eff || !pstart || !refs || !run_bucket || !hot_list || !vhot_list || !part ||
+      !counters || !pieces || !lev_t || !lev_r || !side || !sums)
     return set_error(ZKB_ERR_CUDA, "msm: scratch exhausted");
 
   cudaStream_t st = MS();
   const uint32_t* sc = (const uint32_t*)d_scalars;
   ZKB_CUDA(cudaMemsetAsync(cnt, 0, (nb + 1) * 4, st));
-  ZKB_CUDA(cudaMemsetAsync(hot_count, 0, 4, st));
+  ZKB_CUDA(cudaMemsetAsync(counters, 0, 256, st));
   unsigned pblocks = (unsigned)((n + 255) / 256);
+  unsigned bblocks = (unsigned)((nb + 255) / 256);
   prof_begin(PROF_MSM_SORT);
   msm_count_kernel<<<pblocks, 256, 0, st>>>(pl, sc, cnt);
-  scan_kernel<<<1, 1024, 0, st>>>(cnt, start, nb);
+  scan_u32(cnt, start, nb, part, st);
   ZKB_CUDA(cudaMemcpyAsync(cursor, start, (nb + 1) * 4, cudaMemcpyDeviceToDevice, st));
   msm_scatter_kernel<<<pblocks, 256, 0, st>>>(pl, sc, cursor, refs);
-  unsigned bblocks = (unsigned)((nb + 255) / 256);
-  msm_nseg_kernel<<<bblocks, 256, 0, st>>>(pl, cnt, nseg);
-  scan_kernel<<<1, 1024, 0, st>>>(nseg, segstart, nb);
-  msm_segfill_kernel<<<bblocks, 256, 0, st>>>(pl, nseg, segstart, seg_bucket, hot_list, hot_count);
+  msm_piece_plan_kernel<<<bblocks, 256, 0, st>>>(pl, cnt, start, npieces, np_eff, run_bucket, hot_list, vhot_list, counters);
+  scan_u32(npieces, pstart, nb, part, st);
   prof_end(PROF_MSM_SORT);
-  unsigned ablocks = (unsigned)((pl.max_segs + 127) / 128);
   const int acc_tag = group == 2 ? PROF_MSM_ACCUM_G2 : PROF_MSM_ACCUM_G1;
   prof_begin(acc_tag);
-  msm_accumulate_kernel<F><<<ablocks, 128, 0, st>>>(pl, (const Affine<F>*)d_points, refs, cnt, start, segstart, seg_bucket,
-                                                    seg_sum);
+  constexpr int MINB = AccumField<F>::MINB;
+  msm_accumulate_kernel<FA, MINB><<<148 * MINB, 128, 0, st>>>(pl, (const Affine<FA>*)d_points, refs, start, pstart, run_bucket,
+                                                              pieces, counters + 1);
   prof_end(acc_tag);
   prof_begin(PROF_MSM_REDUCE);
-  msm_hot_kernel<F><<<296, 128, 128 * sizeof(X), st>>>(hot_list, hot_count, nseg, segstart, seg_sum);
-  msm_bucket_reduce_kernel<F><<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(pl, nseg, segstart, seg_sum, contrib);
-  msm_window_sum_kernel<F><<<pl.nwin, 128, 128 * sizeof(X), st>>>(chunks_per_win, contrib, win_sum);
+  msm_fold_cta1_kernel<FA><<<dim3(ZKB_MSM_VHOT_SPLIT, 8), 128, 128 * sizeof(X), st>>>(vhot_list, counters, np_eff, pstart, pieces,
+                                                                                      side);
+  msm_fold_cta2_kernel<FA><<<8, ZKB_MSM_VHOT_SPLIT, ZKB_MSM_VHOT_SPLIT * sizeof(X), st>>>(vhot_list, counters, np_eff, pstart,
+                                                                                         pieces, side);
+  msm_fold_warp_kernel<FA><<<148 * 4, 128, 0, st>>>(hot_list, counters, np_eff, pstart, pieces);
+  SumJobs<FA> jobs;
+  memset(&jobs, 0, sizeof(jobs));
+  size_t off = 0;
+  const X* r_prev = nullptr;
+  for (uint32_t l = 0; l < pl.nlev; l++) {
+    size_t outs = (size_t)pl.nwin * pl.lsize[l + 1];
+    unsigned blocks = (unsigned)((outs + 127) / 128);
+    if (l == 0) msm_level0_kernel<FA><<<blocks, 128, 0, st>>>(pl, np_eff, pstart, pieces, lev_t + off, lev_r + off);
+    else msm_level_kernel<FA><<<blocks, 128, 0, st>>>(pl.nwin, pl.lsize[l], pl.logk[l], r_prev, lev_t + off, lev_r + off);
+    jobs.base[l] = lev_t + off;
+    jobs.count[l] = pl.lsize[l + 1];
+    jobs.bit[l] = -1;
+    r_prev = lev_r + off;
+    off += outs;
+  }
+  for (uint32_t q = pl.nlev; q < njobs; q++) {
+    jobs.base[q] = r_prev;
+    jobs.count[q] = m;
+    jobs.bit[q] = (q + 1 == njobs) ? -1 : (int)(q - pl.nlev);
+  }
+  msm_sums_kernel<FA, SUM_THREADS><<<dim3(njobs, pl.nwin), SUM_THREADS, SUM_THREADS * sizeof(X), st>>>(jobs, njobs, sums);
   prof_end(PROF_MSM_REDUCE);
-  count_launch(9);
+  count_launch(14 + (int)pl.nlev);
   ZKB_CUDA(cudaGetLastError());
-  std::vector<unsigned char> host(pl.nwin * sizeof(X));
-  ZKB_CUDA(cudaMemcpyAsync(host.data(), win_sum, pl.nwin * sizeof(X), cudaMemcpyDeviceToHost, st));
-  ZKB_CUDA(cudaStreamSynchronize(st));
-  host_msm_finish(curve, group, host.data(), pl.nwin, pl.c, out_xy, out_inf);
+  ZKB_CUDA(cudaMemcpyAsync(tk->host, sums, out_bytes, cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(cudaEventRecord((cudaEvent_t)tk->event, st));
+  tk->nwin = pl.nwin;
+  tk->c = pl.c;
+  tk->nlev = pl.nlev;
+  tk->nbits = nbits;
+  for (uint32_t l = 0; l < ZKB_MSM_MAXLEV; l++) tk->logk[l] = pl.logk[l];
   return ZKB_OK;
 }
 
@@ -135,8 +208,8 @@ int batch_mul_run(const void* d_bases, int single_base, const void* d_scalars, s
 
 // every (curve, group) translation unit exports these three with a unique suffix
 #define ZKB_MSM_INSTANTIATE(SUFFIX, FIELD, BITS, CURVE, GROUP)                                                           \
-  int msm_run_##SUFFIX(const void* p, const void* s, size_t n, uint64_t* o, int* inf) {                                 \
-    return msm_run<FIELD, BITS>(CURVE, GROUP, p, s, n, o, inf);                                                         \
+  int msm_enqueue_##SUFFIX(const void* p, const void* s, size_t n, MsmTicket* tk) {                                     \
+    return msm_enqueue_t<FIELD, BITS>(CURVE, GROUP, p, s, n, tk);                                                       \
   }                                                                                                                      \
   int points_conv_##SUFFIX(int to, size_t n, void* p) { return points_conv_run<FIELD>(to != 0, n, p); }                 \
   int batch_mul_##SUFFIX(const void* b, int single, const void* s, size_t n, void* o) {                                 \

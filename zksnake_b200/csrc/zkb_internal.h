@@ -60,6 +60,21 @@ int spmv_dev(int curve, size_t n_out, size_t n_rows, const void* row_ptr, const 
 
 // ---- MSM (msm_host.cuh instantiations) ----
 // d_points: affine, Montgomery form; d_scalars: canonical 4 x u64.  Result: affine canonical coordinates on the host.
+// An MSM is enqueued on the library stream (no synchronisation) against a ticket that owns a pinned result buffer and an
+// event; msm_finish waits for that event and recombines the per-window sums on the host -- so the host part of MSM i
+// overlaps the kernels of MSM i+1.  A ticket can be reused after msm_finish.
+struct MsmTicket {
+  int curve = 0, group = 1;
+  bool empty = true;
+  uint32_t nwin = 0, c = 0, nlev = 0, nbits = 0, logk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned char* host = nullptr;   // pinned
+  size_t host_cap = 0;
+  void* event = nullptr;           // cudaEvent_t
+};
+int ticket_reserve(MsmTicket* tk, size_t bytes);
+void ticket_release(MsmTicket* tk);
+int msm_enqueue(int curve, int group, const void* d_points, const void* d_scalars, size_t n, MsmTicket* tk);
+int msm_finish(MsmTicket* tk, uint64_t* out_xy, int* out_inf);
 int msm_dev(int curve, int group, const void* d_points, const void* d_scalars, size_t n, uint64_t* out_xy, int* out_inf);
 int points_to_mont_dev(int curve, int group, size_t n, void* d_points);
 int points_from_mont_dev(int curve, int group, size_t n, void* d_points);
@@ -67,8 +82,12 @@ int batch_mul_dev(int curve, int group, const void* d_bases, int single_base, co
 void msm_set_tuning(int c, int seg, int kchunk);
 
 // ---- host math (host_math.cpp, plain g++) ----
-// recombine W window sums (XYZZ, Montgomery) into one affine canonical point
-void host_msm_finish(int curve, int group, const void* win_sums, uint32_t nwin, uint32_t c, uint64_t* out_xy, int* out_inf);
+// recombine the per-window sums of the bucket reduction (XYZZ, Montgomery; njobs = nlev + nbits + 1 per window:
+// U_0..U_{nlev-1}, A_0..A_{nbits-1}, R_top):
+//   window sum = R_top + U_0 + 2^logk[0] (U_1 + ... + 2^logk[nlev-1] (sum_beta 2^beta A_beta)),
+// then Horner over the windows with c doublings each
+void host_msm_finish(int curve, int group, const void* sums, uint32_t nwin, uint32_t c, uint32_t nlev, const uint32_t* logk,
+                     uint32_t nbits, uint64_t* out_xy, int* out_inf);
 // out = sum_i k_i * P_i + sum_j Q_j over a handful of canonical affine points (proof assembly)
 void host_lincomb(int curve, int group, int n_terms, const uint64_t* const* points, const int* infs,
                   const uint64_t* const* scalars, uint64_t* out_xy, int* out_inf);

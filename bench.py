@@ -323,6 +323,8 @@ def main_own(args):
 
     # ---- timed: end to end from pinned host memory through the public API ----
     barrier()
+    h2d0, d2h0 = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+    nat.lib.zkb_transfer_count(ctypes.byref(h2d0), ctypes.byref(d2h0))
     t2 = time.perf_counter()
     for _ in range(args.steps):
         p2 = prover.prove_packed(w_pinned, r_rand, s_rand)
@@ -330,6 +332,10 @@ def main_own(args):
     barrier()
     t3 = time.perf_counter()
     e2e_ms = (t3 - t2) * 1e3 / args.steps
+    h2d1, d2h1 = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+    nat.lib.zkb_transfer_count(ctypes.byref(h2d1), ctypes.byref(d2h1))
+    h2d_step = (h2d1.value - h2d0.value) // args.steps   # counted by the library around every cudaMemcpy it issues
+    d2h_step = (d2h1.value - d2h0.value) // args.steps
     clocks = sampler.stop(t0, t3) if rank == 0 else None
 
     if td is not None:
@@ -362,7 +368,9 @@ def main_own(args):
     lo, hi = prover._slice
     pts_per_launch = hi - lo
     # canonical algorithmic work of a G1 MSM = W*10 Fq products per point with c = 16 (W = 16), one
-    # product = 2L^2+L 32-bit multiply-adds (L = 8 limbs BN254, 12 BLS12-381)  => 21760 / 48000 per point
+    # product = 2L^2+L 32x32->64 multiply-adds (L = 8 limbs BN254, 12 BLS12-381)  => 21760 / 48000 per point.  In this
+    # library every one of them is one IMAD.WIDE.U32, whose issue rate (32 lanes/clk/SM, HALF the IMAD.LO rate; measured by
+    # zkb_imad_peak(1) with loop-variant operands, tools/ffbench.cu) is therefore the roofline denominator.
     L = 8 if curve == 0 else 12
     ops_per_pt = 16 * 10 * (2 * L * L + L)
     acc_ms, acc_cnt = prof["msm_accum_g1"]
@@ -370,13 +378,19 @@ def main_own(args):
     if acc_cnt:
         per_launch_ms = acc_ms / acc_cnt
         achieved = pts_per_launch * ops_per_pt / (per_launch_ms * 1e-3) / 1e12
-        roofline = {"kernel": "msm_accumulate_kernel<G1>", "bound": "int32-pipe", "achieved": achieved, "peak": imad.value / 1e12,
-                    "unit": "T int32 multiply-add lane-ops/s", "frac": achieved / (imad.value / 1e12),
-                    "peak_source": "zkb_imad_peak microbenchmark run inside this bench (mad.lo.u32, 8 chains/thread)",
-                    "imad_wide_peak": imad_wide.value / 1e12,
+        roofline = {"kernel": "msm_accumulate_kernel<G1>", "bound": "int32-pipe", "achieved": achieved,
+                    "peak": imad_wide.value / 1e12, "unit": "T 32x32->64 multiply-add lane-ops/s (IMAD.WIDE)",
+                    "frac": achieved / (imad_wide.value / 1e12),
+                    "peak_source": "zkb_imad_peak(1) microbenchmark run inside this bench (mad.wide.u32, loop-variant "
+                                   "multiplicand, 8 chains/thread)",
+                    "imad_lo_peak": imad.value / 1e12,
                     "algorithmic_ops_per_point": ops_per_pt, "points_per_launch": pts_per_launch,
                     "launch_ms": per_launch_ms, "launches": acc_cnt,
                     "traffic": traffic.get("msm_accumulate_g1"), "share_of_step": acc_ms / args.steps / dev_ms}
+        msm_all_ms = sum(prof[k][0] for k in ("msm_sort", "msm_accum_g1", "msm_accum_g2", "msm_reduce")) / args.steps
+        # the same algorithmic count over ALL FIVE MSMs of the proof (G2 = 3 Fq products per Fq2 product) and all MSM kernels
+        ops_step = pts_per_launch * ops_per_pt * (4 + 3)
+        roofline["whole_msm_frac"] = ops_step / (msm_all_ms * 1e-3) / imad_wide.value if msm_all_ms else None
     ntt_ms, ntt_cnt = prof["ntt"]
     roofline_ntt = None
     if ntt_cnt:
@@ -405,8 +419,7 @@ def main_own(args):
         "config": dict(workload_config(args), parallelism=f"msm-shard{world}", l2="working set 450 MiB (key 320 + scalars 130) exceeds L2; no flush"),
         "timing": "CUDA events on the library stream around the K steps (value); wall clock between barriers (ms_per_step, e2e)",
         "clocks": clocks,
-        "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": m * 32,
-                "d2h_bytes_per_step": 2 * g1b + g2b + 4 + 5 * 20 * 4 * (g2b // 2),
+        "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
                 "api": "zksnake_b200.groth16.Groth16.prove_packed(pinned witness) -> Proof.to_bytes()"},
         "gpu_launches": int(launches),
         "roofline": roofline, "roofline_ntt": roofline_ntt, "cpu_baseline": cpu_base,

@@ -61,6 +61,8 @@ const char* zkb_last_error(void);
 void* zkb_stream(void);                   /* the cudaStream_t all work is issued on */
 int zkb_sync(void);
 unsigned long long zkb_launch_count(void); /* kernels launched by this library so far */
+/* bytes the library has copied host->device / device->host so far (bench.py's e2e accounting) */
+void zkb_transfer_count(unsigned long long* h2d_bytes, unsigned long long* d2h_bytes);
 int zkb_timer_start(void);                /* CUDA events on the library stream */
 int zkb_timer_stop(float* ms);
 /* Per-kernel-family device time (CUDA events on the library stream around every launch of the family), for bench.py's

@@ -36,6 +36,7 @@ def _load():
         "zkb_stream": (c_vp, []),
         "zkb_sync": (c_int, []),
         "zkb_launch_count": (ctypes.c_ulonglong, []),
+        "zkb_transfer_count": (None, [ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]),
         "zkb_timer_start": (c_int, []),
         "zkb_timer_stop": (c_int, [ctypes.POINTER(ctypes.c_float)]),
         "zkb_prof_enable": (c_int, [c_int]),

@@ -59,10 +59,10 @@ int zkb_ntt(int curve, int inverse, int coset, uint32_t log_n, const uint64_t* i
   int rc;
   if ((rc = stage(0, (in_len ? in_len : 1) * 32, &d_in))) return rc;
   if ((rc = stage(1, n * 32, &d_out))) return rc;
-  if (in_len) ZKB_CUDA(cudaMemcpyAsync(d_in, in, in_len * 32, cudaMemcpyHostToDevice, S()));
+  if (in_len) ZKB_CUDA(ZKB_H2D(d_in, in, in_len * 32));
   if ((rc = fr_reduce_dev(curve, in_len, d_in))) return rc;
   if ((rc = ntt_dev(curve, inverse, coset, log_n, d_in, in_len, d_out))) return rc;
-  ZKB_CUDA(cudaMemcpyAsync(out, d_out, n * 32, cudaMemcpyDeviceToHost, S()));
+  ZKB_CUDA(ZKB_D2H(out, d_out, n * 32));
   ZKB_CUDA(cudaStreamSynchronize(S()));
   return ZKB_OK;
 }
@@ -86,12 +86,12 @@ int zkb_vec_op(int curve, int op, size_t n, const uint64_t* a, size_t na, const 
   if ((rc = stage(0, (na ? na : 1) * 32, &d_a))) return rc;
   if ((rc = stage(1, (nb ? nb : 1) * 32, &d_b))) return rc;
   if ((rc = stage(2, n * 32, &d_o))) return rc;
-  if (na) ZKB_CUDA(cudaMemcpyAsync(d_a, a, na * 32, cudaMemcpyHostToDevice, S()));
-  if (nb) ZKB_CUDA(cudaMemcpyAsync(d_b, b, nb * 32, cudaMemcpyHostToDevice, S()));
+  if (na) ZKB_CUDA(ZKB_H2D(d_a, a, na * 32));
+  if (nb) ZKB_CUDA(ZKB_H2D(d_b, b, nb * 32));
   if ((rc = fr_reduce_dev(curve, na, d_a))) return rc;
   if ((rc = fr_reduce_dev(curve, nb, d_b))) return rc;
   if ((rc = vec_op_dev(curve, op, n, d_a, na, d_b, nb, nullptr, d_o))) return rc;
-  ZKB_CUDA(cudaMemcpyAsync(out, d_o, n * 32, cudaMemcpyDeviceToHost, S()));
+  ZKB_CUDA(ZKB_D2H(out, d_o, n * 32));
   ZKB_CUDA(cudaStreamSynchronize(S()));
   return ZKB_OK;
 }
@@ -108,9 +108,9 @@ int zkb_fr_reduce(int curve, size_t n, uint64_t* inout) {
   void* d;
   int rc;
   if ((rc = stage(0, n * 32, &d))) return rc;
-  ZKB_CUDA(cudaMemcpyAsync(d, inout, n * 32, cudaMemcpyHostToDevice, S()));
+  ZKB_CUDA(ZKB_H2D(d, inout, n * 32));
   if ((rc = fr_reduce_dev(curve, n, d))) return rc;
-  ZKB_CUDA(cudaMemcpyAsync(inout, d, n * 32, cudaMemcpyDeviceToHost, S()));
+  ZKB_CUDA(ZKB_D2H(inout, d, n * 32));
   ZKB_CUDA(cudaStreamSynchronize(S()));
   return ZKB_OK;
 }
@@ -128,7 +128,7 @@ int zkb_points_upload(int curve, int group, const uint64_t* pts, size_t n, void*
   CHECK_CURVE(curve);
   CHECK_GROUP(group);
   if (n == 0) return ZKB_OK;
-  ZKB_CUDA(cudaMemcpyAsync(d_out, pts, n * affine_bytes(curve, group), cudaMemcpyHostToDevice, S()));
+  ZKB_CUDA(ZKB_H2D(d_out, pts, n * affine_bytes(curve, group)));
   return points_to_mont_dev(curve, group, n, d_out);
 }
 int zkb_points_download(int curve, int group, const void* d_pts, size_t n, uint64_t* out) {
@@ -142,7 +142,7 @@ int zkb_points_download(int curve, int group, const void* d_pts, size_t n, uint6
   if ((rc = stage(3, bytes, &d_tmp))) return rc;
   ZKB_CUDA(cudaMemcpyAsync(d_tmp, d_pts, bytes, cudaMemcpyDeviceToDevice, S()));
   if ((rc = points_from_mont_dev(curve, group, n, d_tmp))) return rc;
-  ZKB_CUDA(cudaMemcpyAsync(out, d_tmp, bytes, cudaMemcpyDeviceToHost, S()));
+  ZKB_CUDA(ZKB_D2H(out, d_tmp, bytes));
   ZKB_CUDA(cudaStreamSynchronize(S()));
   return ZKB_OK;
 }
@@ -170,8 +170,8 @@ int zkb_msm(int curve, int group, const uint64_t* pts, size_t n_points, const ui
   int rc;
   if ((rc = stage(3, n * affine_bytes(curve, group), &d_p))) return rc;
   if ((rc = stage(4, n * 32, &d_s))) return rc;
-  ZKB_CUDA(cudaMemcpyAsync(d_p, pts, n * affine_bytes(curve, group), cudaMemcpyHostToDevice, S()));
-  ZKB_CUDA(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, S()));
+  ZKB_CUDA(ZKB_H2D(d_p, pts, n * affine_bytes(curve, group)));
+  ZKB_CUDA(ZKB_H2D(d_s, scalars, n * 32));
   if ((rc = points_to_mont_dev(curve, group, n, d_p))) return rc;
   if ((rc = fr_reduce_dev(curve, n, d_s))) return rc;
   return msm_dev(curve, group, d_p, d_s, n, out_xy, out_inf);
@@ -206,7 +206,7 @@ int zkb_groth16_h(int curve, uint32_t log_n, const uint64_t* a, const uint64_t* 
   char* p = (char*)d;
   const uint64_t* src[3] = {a, b, c};
   for (int i = 0; i < 3; i++) {
-    ZKB_CUDA(cudaMemcpyAsync(p + i * bytes, src[i], bytes, cudaMemcpyHostToDevice, S()));
+    ZKB_CUDA(ZKB_H2D(p + i * bytes, src[i], bytes));
     if ((rc = fr_reduce_dev(curve, n, p + i * bytes))) return rc;
   }
   if ((rc = groth16_h_dev(curve, log_n, p, p + bytes, p + 2 * bytes, p + 3 * bytes, p + 4 * bytes, p + 5 * bytes,
@@ -214,7 +214,7 @@ int zkb_groth16_h(int curve, uint32_t log_n, const uint64_t* a, const uint64_t* 
     return rc;
   uint64_t* dst[4] = {u, v, w, h};
   for (int i = 0; i < 4; i++)
-    if (dst[i]) ZKB_CUDA(cudaMemcpyAsync(dst[i], p + (3 + i) * bytes, bytes, cudaMemcpyDeviceToHost, S()));
+    if (dst[i]) ZKB_CUDA(ZKB_D2H(dst[i], p + (3 + i) * bytes, bytes));
   ZKB_CUDA(cudaStreamSynchronize(S()));
   return ZKB_OK;
 }
@@ -395,10 +395,10 @@ int zkb_groth16_prove(zkb_groth16_pk* pk, const uint64_t* a, const uint64_t* b, 
   const size_t bytes = pk->n * 32;
   char* w = pk->work;
   char* d_priv = w + 7 * bytes;
-  ZKB_CUDA(cudaMemcpyAsync(w, a, bytes, cudaMemcpyHostToDevice, S()));
-  ZKB_CUDA(cudaMemcpyAsync(w + bytes, b, bytes, cudaMemcpyHostToDevice, S()));
-  ZKB_CUDA(cudaMemcpyAsync(w + 2 * bytes, c, bytes, cudaMemcpyHostToDevice, S()));
-  if (pk->n_kdelta) ZKB_CUDA(cudaMemcpyAsync(d_priv, priv, pk->n_kdelta * 32, cudaMemcpyHostToDevice, S()));
+  ZKB_CUDA(ZKB_H2D(w, a, bytes));
+  ZKB_CUDA(ZKB_H2D(w + bytes, b, bytes));
+  ZKB_CUDA(ZKB_H2D(w + 2 * bytes, c, bytes));
+  if (pk->n_kdelta) ZKB_CUDA(ZKB_H2D(d_priv, priv, pk->n_kdelta * 32));
   return zkb_groth16_prove_dev(pk, w, w + bytes, w + 2 * bytes, d_priv, r, s, out_a, out_b, out_c, out_inf);
 }
 
@@ -445,9 +445,9 @@ int zkb_r1cs_create(int curve, size_t n_rows, size_t n_cols, const uint64_t* con
     if ((e = cudaMalloc((void**)&r->row_ptr[i], (n_rows + 1) * 8)) != cudaSuccess ||
         (e = cudaMalloc((void**)&r->col[i], (nnz ? nnz : 1) * 4)) != cudaSuccess ||
         (e = cudaMalloc((void**)&r->val[i], (nnz ? nnz : 1) * 32)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(r->row_ptr[i], row_ptr[i], (n_rows + 1) * 8, cudaMemcpyHostToDevice, S())) != cudaSuccess ||
-        (nnz && (e = cudaMemcpyAsync(r->col[i], col[i], nnz * 4, cudaMemcpyHostToDevice, S())) != cudaSuccess) ||
-        (nnz && (e = cudaMemcpyAsync(r->val[i], val[i], nnz * 32, cudaMemcpyHostToDevice, S())) != cudaSuccess)) {
+        (e = ZKB_H2D(r->row_ptr[i], row_ptr[i], (n_rows + 1) * 8)) != cudaSuccess ||
+        (nnz && (e = ZKB_H2D(r->col[i], col[i], nnz * 4)) != cudaSuccess) ||
+        (nnz && (e = ZKB_H2D(r->val[i], val[i], nnz * 32)) != cudaSuccess)) {
       rc = cuda_fail((int)e, "r1cs upload", __FILE__, __LINE__);
       break;
     }
@@ -471,6 +471,7 @@ int zkb_r1cs_create(int curve, size_t n_rows, size_t n_cols, const uint64_t* con
 
 // witness (n_cols canonical-or-not 256-bit values, host or device) -> r->w, reduced mod r
 static int r1cs_load_witness(zkb_r1cs* r, const void* witness, int on_device) {
+  if (!on_device) count_h2d(r->n_cols * 32);
   ZKB_CUDA(cudaMemcpyAsync(r->w, witness, r->n_cols * 32, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, S()));
   return fr_reduce_dev(r->curve, r->n_cols, r->w);
 }
@@ -497,7 +498,7 @@ int zkb_r1cs_eval(zkb_r1cs* r, const uint64_t* witness, size_t n_out, uint64_t* 
   char* p = (char*)d;
   if ((rc = r1cs_eval_dev(r, witness, n_out, p, p + n_out * 32, p + 2 * n_out * 32))) return rc;
   uint64_t* dst[3] = {a, b, c};
-  for (int i = 0; i < 3; i++) ZKB_CUDA(cudaMemcpyAsync(dst[i], p + i * n_out * 32, n_out * 32, cudaMemcpyDeviceToHost, S()));
+  for (int i = 0; i < 3; i++) ZKB_CUDA(ZKB_D2H(dst[i], p + i * n_out * 32, n_out * 32));
   ZKB_CUDA(cudaStreamSynchronize(S()));
   return ZKB_OK;
 }
@@ -565,7 +566,7 @@ int zkb_groth16_last_poly(zkb_groth16_pk* pk, int which, uint64_t* out) {
   if (!pk || which < 0 || which > 2) return set_error(ZKB_ERR_ARG, "bad argument");
   const size_t bytes = pk->n * 32;
   static const int slot[3] = {3, 4, 6};
-  ZKB_CUDA(cudaMemcpyAsync(out, pk->work + slot[which] * bytes, bytes, cudaMemcpyDeviceToHost, S()));
+  ZKB_CUDA(ZKB_D2H(out, pk->work + slot[which] * bytes, bytes));
   ZKB_CUDA(cudaStreamSynchronize(S()));
   return ZKB_OK;
 }
@@ -610,12 +611,12 @@ int field_op_dev_t(int op, size_t n, const uint32_t* a, const uint32_t* b, uint3
   ZKB_CUDA(cudaMalloc((void**)&da, bytes));
   ZKB_CUDA(cudaMalloc((void**)&db, bytes));
   ZKB_CUDA(cudaMalloc((void**)&dout, bytes));
-  ZKB_CUDA(cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, S()));
-  ZKB_CUDA(cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, S()));
+  ZKB_CUDA(ZKB_H2D(da, a, bytes));
+  ZKB_CUDA(ZKB_H2D(db, b, bytes));
   field_op_kernel<F><<<(unsigned)((n + 127) / 128), 128, 0, S()>>>(op, n, da, db, dout);
   count_launch();
   ZKB_CUDA(cudaGetLastError());
-  ZKB_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, S()));
+  ZKB_CUDA(ZKB_D2H(out, dout, bytes));
   ZKB_CUDA(cudaStreamSynchronize(S()));
   cudaFree(da);
   cudaFree(db);

@@ -34,6 +34,9 @@ int cuda_fail(int cuda_err, const char* what, const char* file, int line) {
 void* ctx_stream() { return (void*)g_ctx.stream; }
 bool ctx_ready() { return g_ctx.ready; }
 void count_launch(int n) { g_ctx.launches += n; }
+static unsigned long long g_h2d_bytes = 0, g_d2h_bytes = 0;
+void count_h2d(size_t bytes) { g_h2d_bytes += bytes; }
+void count_d2h(size_t bytes) { g_d2h_bytes += bytes; }
 unsigned long long launches() { return g_ctx.launches; }
 
 // ---- per-kernel-family device timing (CUDA events on the library stream), off by default ----------------------------
@@ -107,14 +110,16 @@ __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, uint32_t 
 #pragma unroll
     for (int u = 0; u < 8; u++) {
       if (WIDE) {
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y0) : "r"(a), "r"(b));
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y1) : "r"(a), "r"(b));
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y2) : "r"(a), "r"(b));
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y3) : "r"(a), "r"(b));
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y4) : "r"(a), "r"(b));
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y5) : "r"(a), "r"(b));
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y6) : "r"(a), "r"(b));
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y7) : "r"(a), "r"(b));
+        // the multiplicand is the running low word, so ptxas cannot hoist the product out of the loop (with loop-invariant
+        // operands it does, and the "IMAD.WIDE rate" measured is that of a 64-bit add)
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y0) : "r"((uint32_t)y0), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y1) : "r"((uint32_t)y1), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y2) : "r"((uint32_t)y2), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y3) : "r"((uint32_t)y3), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y4) : "r"((uint32_t)y4), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y5) : "r"((uint32_t)y5), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y6) : "r"((uint32_t)y6), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y7) : "r"((uint32_t)y7), "r"(b));
       } else {
         asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x0) : "r"(a), "r"(b));
         asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x1) : "r"(a), "r"(b));
@@ -184,6 +189,10 @@ void zkb_shutdown(void) {
 const char* zkb_last_error(void) { return g_err.c_str(); }
 void* zkb_stream(void) { return (void*)g_ctx.stream; }
 unsigned long long zkb_launch_count(void) { return g_ctx.launches; }
+void zkb_transfer_count(unsigned long long* h2d_bytes, unsigned long long* d2h_bytes) {
+  if (h2d_bytes) *h2d_bytes = g_h2d_bytes;
+  if (d2h_bytes) *d2h_bytes = g_d2h_bytes;
+}
 
 #define NEED_INIT() \
   if (!g_ctx.ready) return set_error(ZKB_ERR_NOINIT, "zkb_init has not been called (no CUDA context; no CPU fallback)")
@@ -216,12 +225,14 @@ int zkb_host_free(void* p) {
 }
 int zkb_h2d(void* dst, const void* src, size_t bytes) {
   NEED_INIT();
+  count_h2d(bytes);
   ZKB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_ctx.stream));
   ZKB_CUDA(cudaStreamSynchronize(g_ctx.stream));
   return ZKB_OK;
 }
 int zkb_d2h(void* dst, const void* src, size_t bytes) {
   NEED_INIT();
+  count_d2h(bytes);
   ZKB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
   ZKB_CUDA(cudaStreamSynchronize(g_ctx.stream));
   return ZKB_OK;

@@ -9,10 +9,15 @@
 namespace zkb {
 
 template <class F>
-static void finish_t(const void* sums_, uint32_t nwin, uint32_t c, uint32_t nlev, const uint32_t* logk, uint32_t nbits,
-                     uint64_t* out_xy, int* out_inf) {
+static void finish_t(const void* sums_, uint32_t nwin, uint32_t c, uint32_t nlev, const uint32_t* logk, const uint32_t* parts,
+                     uint32_t nbits, uint64_t* out_xy, int* out_inf) {
   const XYZZ<F>* sums = (const XYZZ<F>*)sums_;
-  const uint32_t njobs = nlev + nbits + 1;
+  uint32_t first[8], nu = 0;   // first job of level l
+  for (uint32_t l = 0; l < nlev; l++) {
+    first[l] = nu;
+    nu += parts[l];
+  }
+  const uint32_t njobs = nu + nbits + 1;
   XYZZ<F> acc = XYZZ<F>::inf();
   for (int i = (int)nwin - 1; i >= 0; i--) {
     if (!acc.is_inf())
@@ -22,12 +27,12 @@ static void finish_t(const void* sums_, uint32_t nwin, uint32_t c, uint32_t nlev
     XYZZ<F> ws = XYZZ<F>::inf();
     for (int beta = (int)nbits - 1; beta >= 0; beta--) {
       if (!ws.is_inf()) ws = dbl(ws);
-      ws = add(ws, s[nlev + beta]);
+      ws = add(ws, s[nu + beta]);
     }
     for (int l = (int)nlev - 1; l >= 0; l--) {
       if (!ws.is_inf())
         for (uint32_t k = 0; k < logk[l]; k++) ws = dbl(ws);
-      ws = add(ws, s[l]);
+      for (uint32_t p = 0; p < parts[l]; p++) ws = add(ws, s[first[l] + p]);
     }
     ws = add(ws, s[njobs - 1]);
     acc = add(acc, ws);
@@ -40,11 +45,11 @@ static void finish_t(const void* sums_, uint32_t nwin, uint32_t c, uint32_t nlev
 }
 
 void host_msm_finish(int curve, int group, const void* sums, uint32_t nwin, uint32_t c, uint32_t nlev, const uint32_t* logk,
-                     uint32_t nbits, uint64_t* out_xy, int* out_inf) {
-  if (curve == ZKB_BN254 && group == 1) finish_t<Fh<FqBN254>>(sums, nwin, c, nlev, logk, nbits, out_xy, out_inf);
-  else if (curve == ZKB_BN254) finish_t<Fh2<FqBN254>>(sums, nwin, c, nlev, logk, nbits, out_xy, out_inf);
-  else if (group == 1) finish_t<Fh<FqBLS381>>(sums, nwin, c, nlev, logk, nbits, out_xy, out_inf);
-  else finish_t<Fh2<FqBLS381>>(sums, nwin, c, nlev, logk, nbits, out_xy, out_inf);
+                     const uint32_t* parts, uint32_t nbits, uint64_t* out_xy, int* out_inf) {
+  if (curve == ZKB_BN254 && group == 1) finish_t<Fh<FqBN254>>(sums, nwin, c, nlev, logk, parts, nbits, out_xy, out_inf);
+  else if (curve == ZKB_BN254) finish_t<Fh2<FqBN254>>(sums, nwin, c, nlev, logk, parts, nbits, out_xy, out_inf);
+  else if (group == 1) finish_t<Fh<FqBLS381>>(sums, nwin, c, nlev, logk, parts, nbits, out_xy, out_inf);
+  else finish_t<Fh2<FqBLS381>>(sums, nwin, c, nlev, logk, parts, nbits, out_xy, out_inf);
 }
 
 // sum_i k_i * P_i ; scalars[i] == nullptr means k_i = 1.  Interleaved (Straus) double-and-add over all terms.

@@ -27,7 +27,8 @@
 namespace zkb {
 
 #define ZKB_MSM_MAXLEV 8
-#define ZKB_MSM_MAXJOBS 32     // plain-sum jobs per window: <= MAXLEV U sums + <= 16 bit sums + R_top
+#define ZKB_MSM_MAXJOBS 96     // plain-sum jobs per window: <= 8 parts per level of U sums + <= 16 bit sums + R_top
+#define ZKB_MSM_MAXPARTS 8
 #define ZKB_MSM_HOT 4u         // buckets with more pieces are folded by a warp
 #define ZKB_MSM_VHOT 2048u     // ... by 64 CTAs
 #define ZKB_MSM_VHOT_SPLIT 64u
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(128, MINB) msm_accumulate_kernel(MsmPlan pl, c
     uint32_t slot = pstart[b] + (t - start[b] / K);
     XYZZ<F> acc = XYZZ<F>::inf();
     // one-ahead software prefetch of the gathered point where the register file allows it (G1)
-    constexpr bool PREFETCH = sizeof(Affine<F>) <= 96;
+    constexpr bool PREFETCH = true;
     uint32_t ref_next = refs[pos];
     Affine<F> p_next;
     if (PREFETCH) p_next = load_affine(points + (ref_next & 0x7fffffffu));
@@ -414,7 +415,7 @@ __global__ void __launch_bounds__(ZKB_MSM_VHOT_SPLIT) msm_fold_cta2_kernel(const
 // pass 5, level 0: thread (w, j) folds the buckets [j*k, (j+1)*k) of window w:  R = sum_i S_i,  T = sum_i i * S_i
 // (S_i = the bucket's <= ZKB_MSM_HOT pieces added up).  Outputs at [w * (nbuck/k) + j].
 template <class F>
-__global__ void __launch_bounds__(128) msm_level0_kernel(MsmPlan pl, const uint32_t* __restrict__ np_eff,
+__global__ void __launch_bounds__(128, 3) msm_level0_kernel(MsmPlan pl, const uint32_t* __restrict__ np_eff,
                                                          const uint32_t* __restrict__ pstart,
                                                          const XYZZ<F>* __restrict__ pieces, XYZZ<F>* __restrict__ t_out,
                                                          XYZZ<F>* __restrict__ r_out) {
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(128) msm_level0_kernel(MsmPlan pl, const uint3
 
 // pass 5, level l > 0: the same fold over the previous level's totals
 template <class F>
-__global__ void __launch_bounds__(128) msm_level_kernel(uint32_t nwin, uint32_t in_per_win, uint32_t logk,
+__global__ void __launch_bounds__(128, 3) msm_level_kernel(uint32_t nwin, uint32_t in_per_win, uint32_t logk,
                                                         const XYZZ<F>* __restrict__ r_in, XYZZ<F>* __restrict__ t_out,
                                                         XYZZ<F>* __restrict__ r_out) {
   unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
@@ -453,11 +454,14 @@ __global__ void __launch_bounds__(128) msm_level_kernel(uint32_t nwin, uint32_t 
   store_vec(r_out + t, run);
 }
 
-// pass 5b: plain sums.  Job q of window w adds base[w * count + j] over the j < count with bit `bit` of j set
-// (bit < 0: all j) -> out[w * njobs + q].  grid (njobs, nwin).
+// pass 5b: plain sums.  Job q of window w adds base[w * stride + offset + j] over the j < count with bit `bit` of j set
+// (bit < 0: all j) -> out[w * njobs + q].  grid (njobs, nwin).  Long U sums are cut into <= ZKB_MSM_MAXPARTS jobs (the host
+// adds the parts) because the cost of a job is its DEPTH: count/THREADS serial additions plus log2(THREADS) tree levels.
 template <class F>
 struct SumJobs {
   const XYZZ<F>* base[ZKB_MSM_MAXJOBS];
+  uint32_t stride[ZKB_MSM_MAXJOBS];
+  uint32_t offset[ZKB_MSM_MAXJOBS];
   uint32_t count[ZKB_MSM_MAXJOBS];
   int bit[ZKB_MSM_MAXJOBS];
 };
@@ -468,7 +472,7 @@ __global__ void __launch_bounds__(THREADS) msm_sums_kernel(SumJobs<F> jobs, uint
   const uint32_t t = threadIdx.x, q = blockIdx.x, w = blockIdx.y;
   const uint32_t cntq = jobs.count[q];
   const int bit = jobs.bit[q];
-  const XYZZ<F>* src = jobs.base[q] + (unsigned long long)w * cntq;
+  const XYZZ<F>* src = jobs.base[q] + (unsigned long long)w * jobs.stride[q] + jobs.offset[q];
   XYZZ<F> acc = XYZZ<F>::inf();
   if (bit < 0) {
     for (uint32_t k = t; k < cntq; k += blockDim.x) acc = add(acc, load_vec(src + k));

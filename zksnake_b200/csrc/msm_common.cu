@@ -59,7 +59,7 @@ int msm_finish(MsmTicket* tk, uint64_t* out_xy, int* out_inf) {
     return ZKB_OK;
   }
   ZKB_CUDA(cudaEventSynchronize((cudaEvent_t)tk->event));
-  host_msm_finish(tk->curve, tk->group, tk->host, tk->nwin, tk->c, tk->nlev, tk->logk, tk->nbits, out_xy, out_inf);
+  host_msm_finish(tk->curve, tk->group, tk->host, tk->nwin, tk->c, tk->nlev, tk->logk, tk->parts, tk->nbits, out_xy, out_inf);
   tk->empty = true;
   return ZKB_OK;
 }

@@ -26,7 +26,9 @@ inline MsmPlan msm_make_plan(size_t n, uint32_t scalar_bits) {
   memset(&pl, 0, sizeof(pl));
   uint32_t logn = 0;
   while (((size_t)1 << logn) < n) logn++;
-  int c = g_msm_c ? g_msm_c : (int)logn - 4;
+  // window: the bucket reduction costs ~2.3 full additions per bucket, so fewer, fuller buckets (~64 references each)
+  // beat the classical c = log2(n) - 4
+  int c = g_msm_c ? g_msm_c : (int)logn - 5;
   if (c < 3) c = 3;
   if (c > 22) c = 22;
   pl.c = (uint32_t)c;
@@ -93,7 +95,13 @@ int msm_enqueue_t(int curve, int group, const void* d_points, const void* d_scal
   const uint32_t m = pl.lsize[pl.nlev];
   uint32_t nbits = 0;
   while ((1u << nbits) < m) nbits++;
-  const uint32_t njobs = pl.nlev + nbits + 1;
+  uint32_t parts[ZKB_MSM_MAXLEV];   // U_l is summed in parts of ~512 elements (at most ZKB_MSM_MAXPARTS)
+  uint32_t njobs = nbits + 1;
+  for (uint32_t l = 0; l < pl.nlev; l++) {
+    uint32_t p = (pl.lsize[l + 1] + 511) / 512;
+    parts[l] = p > ZKB_MSM_MAXPARTS ? ZKB_MSM_MAXPARTS : p;
+    njobs += parts[l];
+  }
   if (njobs > ZKB_MSM_MAXJOBS) return set_error(ZKB_ERR_ARG, "msm: too many reduction jobs");
   const size_t out_bytes = (size_t)pl.nwin * njobs * sizeof(X);
 
@@ -154,34 +162,46 @@ int msm_enqueue_t(int curve, int group, const void* d_points, const void* d_scal
   SumJobs<FA> jobs;
   memset(&jobs, 0, sizeof(jobs));
   size_t off = 0;
+  uint32_t q = 0;
   const X* r_prev = nullptr;
   for (uint32_t l = 0; l < pl.nlev; l++) {
     size_t outs = (size_t)pl.nwin * pl.lsize[l + 1];
     unsigned blocks = (unsigned)((outs + 127) / 128);
     if (l == 0) msm_level0_kernel<FA><<<blocks, 128, 0, st>>>(pl, np_eff, pstart, pieces, lev_t + off, lev_r + off);
     else msm_level_kernel<FA><<<blocks, 128, 0, st>>>(pl.nwin, pl.lsize[l], pl.logk[l], r_prev, lev_t + off, lev_r + off);
-    jobs.base[l] = lev_t + off;
-    jobs.count[l] = pl.lsize[l + 1];
-    jobs.bit[l] = -1;
+    uint32_t per = (pl.lsize[l + 1] + parts[l] - 1) / parts[l];
+    for (uint32_t p = 0; p < parts[l]; p++, q++) {
+      jobs.base[q] = lev_t + off;
+      jobs.stride[q] = pl.lsize[l + 1];
+      jobs.offset[q] = p * per;
+      jobs.count[q] = (p + 1) * per <= pl.lsize[l + 1] ? per : pl.lsize[l + 1] - p * per;
+      jobs.bit[q] = -1;
+    }
     r_prev = lev_r + off;
     off += outs;
   }
-  for (uint32_t q = pl.nlev; q < njobs; q++) {
+  for (uint32_t k = 0; k <= nbits; k++, q++) {
     jobs.base[q] = r_prev;
+    jobs.stride[q] = m;
+    jobs.offset[q] = 0;
     jobs.count[q] = m;
-    jobs.bit[q] = (q + 1 == njobs) ? -1 : (int)(q - pl.nlev);
+    jobs.bit[q] = (k == nbits) ? -1 : (int)k;
   }
   msm_sums_kernel<FA, SUM_THREADS><<<dim3(njobs, pl.nwin), SUM_THREADS, SUM_THREADS * sizeof(X), st>>>(jobs, njobs, sums);
   prof_end(PROF_MSM_REDUCE);
   count_launch(14 + (int)pl.nlev);
   ZKB_CUDA(cudaGetLastError());
   ZKB_CUDA(cudaMemcpyAsync(tk->host, sums, out_bytes, cudaMemcpyDeviceToHost, st));
+  count_d2h(out_bytes);
   ZKB_CUDA(cudaEventRecord((cudaEvent_t)tk->event, st));
   tk->nwin = pl.nwin;
   tk->c = pl.c;
   tk->nlev = pl.nlev;
   tk->nbits = nbits;
-  for (uint32_t l = 0; l < ZKB_MSM_MAXLEV; l++) tk->logk[l] = pl.logk[l];
+  for (uint32_t l = 0; l < ZKB_MSM_MAXLEV; l++) {
+    tk->logk[l] = pl.logk[l];
+    tk->parts[l] = l < pl.nlev ? parts[l] : 0;
+  }
   return ZKB_OK;
 }
 

@@ -348,7 +348,7 @@ static int groth16_h_t(uint32_t log_n, const void* d_a, const void* d_b, const v
   if ((rc = ntt_exec<F>(ea, n, H, log_n, inv_t, nullptr, &gpost, nullptr, tmp))) return rc;
   if (check) {
     int hflag = 0;
-    ZKB_CUDA(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, S()));
+    ZKB_CUDA(ZKB_D2H(&hflag, flag, sizeof(int)));
     ZKB_CUDA(cudaStreamSynchronize(S()));
     if (hflag) return set_error(ZKB_ERR_NOT_DIVISIBLE, "(U * V - W) did not divided by Z to zero");
   }

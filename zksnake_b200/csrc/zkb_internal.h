@@ -37,6 +37,11 @@ int scratch_reserve(size_t bytes);  // make sure the arena holds at least `bytes
 void scratch_reset();
 void* scratch_take(size_t bytes);   // 256-byte aligned bump allocation; nullptr when exhausted
 void count_launch(int n = 1);
+void count_h2d(size_t bytes);   // host<->device traffic issued by the library (zkb_transfer_count)
+void count_d2h(size_t bytes);
+// counted copies on the library stream (the translation unit provides S())
+#define ZKB_H2D(dst, src, bytes) (zkb::count_h2d(bytes), cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, S()))
+#define ZKB_D2H(dst, src, bytes) (zkb::count_d2h(bytes), cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, S()))
 // device-time accounting per kernel family (zkb_prof_enable / zkb_prof_read); no-ops unless enabled
 enum { PROF_NTT = 0, PROF_MSM_SORT = 1, PROF_MSM_ACCUM_G1 = 2, PROF_MSM_ACCUM_G2 = 3, PROF_MSM_REDUCE = 4, PROF_SPMV = 5,
        PROF_VEC = 6, PROF_MISC = 7, PROF_NTAGS = 8 };
@@ -66,7 +71,7 @@ int spmv_dev(int curve, size_t n_out, size_t n_rows, const void* row_ptr, const 
 struct MsmTicket {
   int curve = 0, group = 1;
   bool empty = true;
-  uint32_t nwin = 0, c = 0, nlev = 0, nbits = 0, logk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t nwin = 0, c = 0, nlev = 0, nbits = 0, logk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, parts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   unsigned char* host = nullptr;   // pinned
   size_t host_cap = 0;
   void* event = nullptr;           // cudaEvent_t
@@ -82,12 +87,12 @@ int batch_mul_dev(int curve, int group, const void* d_bases, int single_base, co
 void msm_set_tuning(int c, int seg, int kchunk);
 
 // ---- host math (host_math.cpp, plain g++) ----
-// recombine the per-window sums of the bucket reduction (XYZZ, Montgomery; njobs = nlev + nbits + 1 per window:
-// U_0..U_{nlev-1}, A_0..A_{nbits-1}, R_top):
+// recombine the per-window sums of the bucket reduction (XYZZ, Montgomery; per window: parts[0] partial sums of U_0, ...,
+// parts[nlev-1] of U_{nlev-1}, then A_0..A_{nbits-1}, R_top):
 //   window sum = R_top + U_0 + 2^logk[0] (U_1 + ... + 2^logk[nlev-1] (sum_beta 2^beta A_beta)),
 // then Horner over the windows with c doublings each
 void host_msm_finish(int curve, int group, const void* sums, uint32_t nwin, uint32_t c, uint32_t nlev, const uint32_t* logk,
-                     uint32_t nbits, uint64_t* out_xy, int* out_inf);
+                     const uint32_t* parts, uint32_t nbits, uint64_t* out_xy, int* out_inf);
 // out = sum_i k_i * P_i + sum_j Q_j over a handful of canonical affine points (proof assembly)
 void host_lincomb(int curve, int group, int n_terms, const uint64_t* const* points, const int* infs,
                   const uint64_t* const* scalars, uint64_t* out_xy, int* out_inf);

@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--curve", default="BN254", choices=sorted(CURVE_IDS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-mode", default="windows", choices=["windows", "points"],
+                    help="multi-GPU split of every MSM: scalar windows (whole key per GPU) or point ranges (1/N of the key per GPU)")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="CPU seconds (wall) the cpu_baseline sample may take")
     return ap.parse_args()
 
@@ -280,7 +282,7 @@ def main_own(args):
     toxic = [rnd.randint(1, r1cs.p - 1) for _ in range(5)]
     seq = iter(toxic)
     zg.get_random_int = lambda n_max: next(seq)
-    prover = zg.Groth16(r1cs, args.curve, shard=(rank, world))
+    prover = zg.Groth16(r1cs, args.curve, shard=(rank, world), shard_mode=args.shard_mode)
     prover.setup()
     rs = random.Random(2)
     r_rand, s_rand = rs.randint(1, r1cs.p - 1), rs.randint(1, r1cs.p - 1)
@@ -366,7 +368,7 @@ def main_own(args):
     nat.check(nat.lib.zkb_imad_peak(1, ctypes.byref(imad_wide)))
     traffic = load_traffic()
     lo, hi = prover._slice
-    pts_per_launch = hi - lo
+    pts_per_launch = (hi - lo) / (world if args.shard_mode == "windows" else 1)   # point-equivalents of this rank's share
     # canonical algorithmic work of a G1 MSM = W*10 Fq products per point with c = 16 (W = 16), one
     # product = 2L^2+L 32x32->64 multiply-adds (L = 8 limbs BN254, 12 BLS12-381)  => 21760 / 48000 per point.  In this
     # library every one of them is one IMAD.WIDE.U32, whose issue rate (32 lanes/clk/SM, HALF the IMAD.LO rate; measured by
@@ -416,7 +418,7 @@ def main_own(args):
         "metric": METRIC, "value": dev_ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": wall_ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32 limbs (int32 pipe)", "data": "synthetic",
-        "config": dict(workload_config(args), parallelism=f"msm-shard{world}", l2="working set 450 MiB (key 320 + scalars 130) exceeds L2; no flush"),
+        "config": dict(workload_config(args), parallelism=f"msm-{args.shard_mode}-shard{world}", l2="working set 450 MiB (key 320 + scalars 130) exceeds L2; no flush"),
         "timing": "CUDA events on the library stream around the K steps (value); wall clock between barriers (ms_per_step, e2e)",
         "clocks": clocks,
         "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),

@@ -104,6 +104,11 @@ int zkb_points_download(int curve, int group, const void* d_pts, size_t n, uint6
 int zkb_msm(int curve, int group, const uint64_t* pts, size_t n_points, const uint64_t* scalars, size_t n_scalars,
             uint64_t* out_xy, int* out_inf);
 int zkb_msm_dev(int curve, int group, const void* d_pts, const void* d_scalars, size_t n, uint64_t* out_xy, int* out_inf);
+/* Window shard wrank of wworld (multi-GPU): the partial sum over the scalar windows
+ * [W*wrank/wworld, W*(wrank+1)/wworld) of ALL n points, already scaled by 2^(c*first window); the wworld partial results add
+ * up to zkb_msm_dev's result.  Every phase of the MSM (sort, accumulate, bucket reduction) shrinks by 1/wworld. */
+int zkb_msm_dev_windows(int curve, int group, const void* d_pts, const void* d_scalars, size_t n, uint32_t wrank,
+                        uint32_t wworld, uint64_t* out_xy, int* out_inf);
 /* d_out[i] = scalars[i] * bases[single_base ? 0 : i]  (device Montgomery points in and out) */
 int zkb_batch_mul_dev(int curve, int group, const void* d_bases, int single_base, const void* d_scalars, size_t n,
                       void* d_out);
@@ -131,6 +136,10 @@ int zkb_groth16_pk_create_sharded(int curve, uint32_t log_n, const void* d_tau1,
                                   const uint64_t* alpha1, const uint64_t* beta1, const uint64_t* beta2, const uint64_t* delta1,
                                   const uint64_t* delta2, zkb_groth16_pk** out);
 void zkb_groth16_pk_free(zkb_groth16_pk* pk);
+/* Window sharding for multi-GPU proving: the key holds the FULL vectors (create with zkb_groth16_pk_create) and every MSM of
+ * zkb_groth16_partial covers only window shard `rank` of `world`.  Scales better than point slices (the digit sort and the
+ * bucket reduction shrink too); costs the whole key per GPU (320 MiB at 2^20 BN254). */
+int zkb_groth16_pk_set_window_shard(zkb_groth16_pk* pk, uint32_t rank, uint32_t world);
 /* Groth16.prove from host buffers: a, b, c = A.w, B.w, C.w (n each), priv = private witness (n_kdelta scalars), r, s = the
  * prover's randomness.  Outputs canonical affine A (G1), B (G2), C (G1) and their infinity flags.  The timed e2e region of
  * bench.py is exactly one call of this function. */

@@ -140,3 +140,55 @@ def test_algebra_module_surface(gpu, curve_name):
     assert ec.batch_multi_scalar_g1(g1, [1, 2, 3]) == [g1, g1 * 2, g1 * 3]
     with pytest.raises(ValueError, match="mismatch"):
         ec.multiscalar_mul_g1(pts, [1])
+
+
+@pytest.mark.parametrize("mode", ["windows", "points"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_partials_assemble_to_the_same_proof(gpu, mode, world):
+    """Multi-GPU split emulated on one GPU: every "rank" runs zkb_groth16_partial over its shard (scalar
+    windows or point ranges), the partial points are added and assembled -- the proof bytes must not depend on the split."""
+    import ctypes
+
+    import numpy as np
+
+    from zksnake_b200 import _native as nat
+    from zksnake_b200 import dist
+    from zksnake_b200 import groth16 as gm
+    from zksnake_b200 import r1cs as rm
+    curve_name, n = "BN254", 1 << 11
+    cid = curve_id(curve_name)
+    r = PARAMS[cid].r
+    rr, ss = random.Random(5).randint(1, r - 1), random.Random(6).randint(1, r - 1)
+    g1, st, pub, priv = make(gm, rm, rm.chain_circuit(n, curve_name), curve_name)
+    want = prove_seeded(gm, g1, pub, priv, rr, ss).to_bytes()
+    A, B, C = og.prove_closed_form(st, pub + priv, rr, ss)
+    assert want == og.proof_bytes(cid, A, B, C)
+    toxic = list(g1.toxic)
+    w = nat.ints_to_limbs([x % r for x in pub + priv])
+    parts_xy, parts_inf, provers = [], [], []
+    for rank in range(world):
+        g = gm.Groth16(rm.chain_circuit(n, curve_name)[0], curve_name, shard=(rank, world), shard_mode=mode)
+        seq = iter(toxic)
+        old = gm.get_random_int
+        gm.get_random_int = lambda n_max: next(seq)
+        try:
+            g.setup()
+        finally:
+            gm.get_random_int = old
+        xy = np.zeros((dist.MSM_SLOTS, dist.SLOT_LIMBS), dtype=np.uint64)
+        flags = np.zeros(dist.MSM_SLOTS, dtype=np.int32)
+        nat.check(nat.lib.zkb_groth16_partial(g._pk_handle, g._r1cs_handle, nat.ptr(w), 0, g.n_public, nat.ptr(xy), nat.ptr(flags)))
+        parts_xy.append(xy)
+        parts_inf.append(flags)
+        provers.append(g)
+    sxy, sinf = dist.add_partials(cid, np.stack(parts_xy), np.stack(parts_inf))
+    g = provers[0]
+    g1b = nat.lib.zkb_affine_bytes(cid, 1) // 8
+    g2b = nat.lib.zkb_affine_bytes(cid, 2) // 8
+    oa, ob, oc = np.zeros(g1b, np.uint64), np.zeros(g2b, np.uint64), np.zeros(g1b, np.uint64)
+    inf = (ctypes.c_int * 3)()
+    nat.check(nat.lib.zkb_groth16_assemble(g._pk_handle, nat.ptr(sxy), nat.ptr(sinf), nat.ptr(nat.ints_to_limbs([rr])),
+                                           nat.ptr(nat.ints_to_limbs([ss])), nat.ptr(oa), nat.ptr(ob), nat.ptr(oc), inf))
+    ec = g.ec
+    got = gm.Proof(ec.PointG1._from_flat(oa, inf[0]), ec.PointG2._from_flat(ob, inf[1]), ec.PointG1._from_flat(oc, inf[2]))
+    assert got.to_bytes() == want

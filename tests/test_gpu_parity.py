@@ -295,3 +295,36 @@ def test_groth16_quotient(gpu, curve):
     with pytest.raises(ValueError, match="did not divided"):
         gpu.check(gpu.lib.zkb_groth16_h(curve, 1, gpu.ptr(fr_pack(gpu, a)), gpu.ptr(fr_pack(gpu, b)),
                                         gpu.ptr(fr_pack(gpu, c)), *[gpu.ptr(x) for x in bufs]))
+
+
+@pytest.mark.parametrize("curve", CURVES)
+@pytest.mark.parametrize("world", [2, 5, 40])
+def test_msm_window_shards_add_up(gpu, curve, world):
+    """zkb_msm_dev_windows: the partial sums over disjoint scalar-window ranges add up to the full MSM (also when there are
+    more ranks than windows: the surplus ranks return the identity)."""
+    nat = gpu
+    G = group(curve, False)
+    n = 3000
+    rng = np.random.Generator(np.random.PCG64(77 + world))
+    k = rng.integers(0, 2 ** 63, size=(n, 4), dtype=np.uint64)
+    k[:, 3] &= np.uint64((1 << 59) - 1)
+    s = rng.integers(0, 2 ** 64, size=(n, 4), dtype=np.uint64)
+    s[:, 3] &= np.uint64((1 << 60) - 1)   # the _dev entry takes canonical scalars: keep them below r
+    ab = nat.lib.zkb_affine_bytes(curve, 1)
+    d_k = nat.DeviceBuffer(n * 32).upload(k)
+    d_s = nat.DeviceBuffer(n * 32).upload(s)
+    d_gen = nat.DeviceBuffer(ab)
+    gen = pts_pack(G, [G.gen])
+    nat.check(nat.lib.zkb_points_upload(curve, 1, nat.ptr(gen), 1, d_gen.ptr))
+    d_pts = nat.DeviceBuffer(n * ab)
+    nat.check(nat.lib.zkb_batch_mul_dev(curve, 1, d_gen.ptr, 1, d_k.ptr, n, d_pts.ptr))
+    acc = None
+    for rank in range(world):
+        out = np.zeros(ab // 8, dtype=np.uint64)
+        inf = ctypes.c_int(0)
+        nat.check(nat.lib.zkb_msm_dev_windows(curve, 1, d_pts.ptr, d_s.ptr, n, rank, world, nat.ptr(out), ctypes.byref(inf)))
+        acc = G.add(acc, pt_unpack(G, out, inf.value))
+    e = sum(a * b for a, b in zip(nat.limbs_to_ints(k), nat.limbs_to_ints(s))) % G.r
+    assert acc == G.mul(G.gen, e)
+    for b in (d_k, d_s, d_gen, d_pts):
+        b.free()

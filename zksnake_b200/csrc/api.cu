@@ -147,6 +147,17 @@ int zkb_points_download(int curve, int group, const void* d_pts, size_t n, uint6
   return ZKB_OK;
 }
 
+int zkb_msm_dev_windows(int curve, int group, const void* d_pts, const void* d_scalars, size_t n, uint32_t wrank,
+                        uint32_t wworld, uint64_t* out_xy, int* out_inf) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  CHECK_GROUP(group);
+  static MsmTicket tk;
+  int rc = msm_enqueue(curve, group, d_pts, d_scalars, n, wrank, wworld, &tk);
+  if (rc) return rc;
+  return msm_finish(&tk, out_xy, out_inf);
+}
+
 int zkb_msm_dev(int curve, int group, const void* d_pts, const void* d_scalars, size_t n, uint64_t* out_xy, int* out_inf) {
   NEED_INIT();
   CHECK_CURVE(curve);
@@ -224,6 +235,7 @@ struct zkb_groth16_pk {
   uint32_t log_n;
   size_t n, n_kdelta;
   size_t off, len, koff, klen;  // this rank's slice of the n-point vectors / of the n_kdelta-point vector
+  uint32_t wrank, wworld;       // window shard of every MSM (0/1 = all windows)
   const void *tau1, *tau2, *target1, *kdelta1;
   uint64_t alpha1[12], beta1[12], beta2[24], delta1[12], delta2[24];
   char* work;  // a, b, c, u, v, w, h (n each) + priv (n_kdelta)
@@ -242,6 +254,8 @@ int zkb_groth16_pk_create_sharded(int curve, uint32_t log_n, const void* d_tau1,
   zkb_groth16_pk* pk = new zkb_groth16_pk();
   memset(pk, 0, sizeof(*pk));
   pk->curve = curve;
+  pk->wrank = 0;
+  pk->wworld = 1;
   pk->log_n = log_n;
   pk->n = (size_t)1 << log_n;
   pk->n_kdelta = n_kdelta;
@@ -286,6 +300,13 @@ void zkb_groth16_pk_free(zkb_groth16_pk* pk) {
   delete pk;
 }
 
+int zkb_groth16_pk_set_window_shard(zkb_groth16_pk* pk, uint32_t rank, uint32_t world) {
+  if (!pk || world == 0 || rank >= world) return set_error(ZKB_ERR_ARG, "bad window shard");
+  pk->wrank = rank;
+  pk->wworld = world;
+  return ZKB_OK;
+}
+
 static bool is_zero_pt(const uint64_t* p, size_t bytes) {
   for (size_t i = 0; i < bytes / 8; i++)
     if (p[i]) return false;
@@ -308,7 +329,7 @@ static int groth16_msms(zkb_groth16_pk* pk, const void* d_priv) {
       {1, pk->kdelta1, (const char*)d_priv + pk->koff * 32, pk->klen}};
   int rc;
   for (int i = 0; i < 5; i++) {
-    if ((rc = msm_enqueue(curve, job[i].group, job[i].pts, job[i].sc, job[i].n, &tk[i]))) return rc;
+    if ((rc = msm_enqueue(curve, job[i].group, job[i].pts, job[i].sc, job[i].n, pk->wrank, pk->wworld, &tk[i]))) return rc;
     if (i > 0 && (rc = msm_finish(&tk[i - 1], pk->msm_xy[i - 1], &pk->msm_inf[i - 1]))) return rc;
   }
   return msm_finish(&tk[4], pk->msm_xy[4], &pk->msm_inf[4]);
@@ -376,7 +397,7 @@ int zkb_groth16_prove_dev(zkb_groth16_pk* pk, const void* d_a, const void* d_b, 
                           int out_inf[3]) {
   NEED_INIT();
   if (!pk) return set_error(ZKB_ERR_ARG, "null proving key");
-  if (pk->len != pk->n || pk->klen != pk->n_kdelta)
+  if (pk->len != pk->n || pk->klen != pk->n_kdelta || pk->wworld != 1)
     return set_error(ZKB_ERR_ARG, "this proving key holds one slice only: use zkb_groth16_partial + zkb_groth16_assemble");
   const size_t bytes = pk->n * 32;
   char* w = pk->work;
@@ -541,7 +562,7 @@ int zkb_groth16_prove_witness(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const uint64_t
   NEED_INIT();
   int rc;
   if ((rc = prove_witness_checks(pk, r1cs, n_public))) return rc;
-  if (pk->len != pk->n || pk->klen != pk->n_kdelta)
+  if (pk->len != pk->n || pk->klen != pk->n_kdelta || pk->wworld != 1)
     return set_error(ZKB_ERR_ARG, "this proving key holds one slice only: use zkb_groth16_partial + zkb_groth16_assemble");
   if ((rc = r1cs_load_witness(r1cs, witness, 0))) return rc;
   if ((rc = partial_from_resident_witness(pk, r1cs, n_public))) return rc;
@@ -554,7 +575,7 @@ int zkb_groth16_prove_witness_dev(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const void
   NEED_INIT();
   int rc;
   if ((rc = prove_witness_checks(pk, r1cs, n_public))) return rc;
-  if (pk->len != pk->n || pk->klen != pk->n_kdelta)
+  if (pk->len != pk->n || pk->klen != pk->n_kdelta || pk->wworld != 1)
     return set_error(ZKB_ERR_ARG, "this proving key holds one slice only: use zkb_groth16_partial + zkb_groth16_assemble");
   if ((rc = r1cs_load_witness(r1cs, d_witness, 1))) return rc;
   if ((rc = partial_from_resident_witness(pk, r1cs, n_public))) return rc;

@@ -9,7 +9,7 @@
 namespace zkb {
 
 template <class F>
-static void finish_t(const void* sums_, uint32_t nwin, uint32_t c, uint32_t nlev, const uint32_t* logk, const uint32_t* parts,
+static void finish_t(const void* sums_, uint32_t nwin, uint32_t win0, uint32_t c, uint32_t nlev, const uint32_t* logk, const uint32_t* parts,
                      uint32_t nbits, uint64_t* out_xy, int* out_inf) {
   const XYZZ<F>* sums = (const XYZZ<F>*)sums_;
   uint32_t first[8], nu = 0;   // first job of level l
@@ -37,6 +37,8 @@ static void finish_t(const void* sums_, uint32_t nwin, uint32_t c, uint32_t nlev
     ws = add(ws, s[njobs - 1]);
     acc = add(acc, ws);
   }
+  if (!acc.is_inf())
+    for (uint32_t k = 0; k < c * win0; k++) acc = dbl(acc);   // window shard: the lowest window here is win0
   Affine<F> a = to_affine(acc);
   *out_inf = a.is_inf() ? 1 : 0;
   a.x = from_mont(a.x);
@@ -44,12 +46,12 @@ static void finish_t(const void* sums_, uint32_t nwin, uint32_t c, uint32_t nlev
   memcpy(out_xy, &a, sizeof(a));
 }
 
-void host_msm_finish(int curve, int group, const void* sums, uint32_t nwin, uint32_t c, uint32_t nlev, const uint32_t* logk,
-                     const uint32_t* parts, uint32_t nbits, uint64_t* out_xy, int* out_inf) {
-  if (curve == ZKB_BN254 && group == 1) finish_t<Fh<FqBN254>>(sums, nwin, c, nlev, logk, parts, nbits, out_xy, out_inf);
-  else if (curve == ZKB_BN254) finish_t<Fh2<FqBN254>>(sums, nwin, c, nlev, logk, parts, nbits, out_xy, out_inf);
-  else if (group == 1) finish_t<Fh<FqBLS381>>(sums, nwin, c, nlev, logk, parts, nbits, out_xy, out_inf);
-  else finish_t<Fh2<FqBLS381>>(sums, nwin, c, nlev, logk, parts, nbits, out_xy, out_inf);
+void host_msm_finish(int curve, int group, const void* sums, uint32_t nwin, uint32_t win0, uint32_t c, uint32_t nlev,
+                     const uint32_t* logk, const uint32_t* parts, uint32_t nbits, uint64_t* out_xy, int* out_inf) {
+  if (curve == ZKB_BN254 && group == 1) finish_t<Fh<FqBN254>>(sums, nwin, win0, c, nlev, logk, parts, nbits, out_xy, out_inf);
+  else if (curve == ZKB_BN254) finish_t<Fh2<FqBN254>>(sums, nwin, win0, c, nlev, logk, parts, nbits, out_xy, out_inf);
+  else if (group == 1) finish_t<Fh<FqBLS381>>(sums, nwin, win0, c, nlev, logk, parts, nbits, out_xy, out_inf);
+  else finish_t<Fh2<FqBLS381>>(sums, nwin, win0, c, nlev, logk, parts, nbits, out_xy, out_inf);
 }
 
 // sum_i k_i * P_i ; scalars[i] == nullptr means k_i = 1.  Interleaved (Straus) double-and-add over all terms.

@@ -34,7 +34,9 @@ namespace zkb {
 #define ZKB_MSM_VHOT_SPLIT 64u
 struct MsmPlan {
   uint32_t c;        // window bits
-  uint32_t nwin;     // W
+  uint32_t nwin;     // windows handled by THIS launch: [win0, win0 + nwin) of the scalar's nwin_total windows
+  uint32_t win0;
+  uint32_t nwin_total;
   uint32_t nbuck;    // buckets per window = 2^(c-1)
   uint32_t krun;     // K: references per accumulation run
   uint32_t nlev;     // levels of the bucket reduction
@@ -68,11 +70,12 @@ static __global__ void msm_count_kernel(MsmPlan pl, const uint32_t* __restrict__
   load_scalar(scalars + i * 8, s);
   uint32_t carry = 0;
   const uint32_t half = 1u << (pl.c - 1);
-  for (uint32_t w = 0; w < pl.nwin; w++) {
+  const uint32_t wend = pl.win0 + pl.nwin;
+  for (uint32_t w = 0; w < wend; w++) {   // the carry has to be walked up from window 0 even when win0 > 0
     uint32_t d = scalar_bits(s, w * pl.c, pl.c) + carry;
     carry = d > half;
     uint32_t mag = carry ? ((1u << pl.c) - d) : d;
-    if (mag) atomicAdd(&cnt[w * pl.nbuck + mag - 1], 1u);
+    if (mag && w >= pl.win0) atomicAdd(&cnt[(w - pl.win0) * pl.nbuck + mag - 1], 1u);
   }
 }
 
@@ -87,13 +90,15 @@ static __global__ void msm_scatter_kernel(MsmPlan pl, const uint32_t* __restrict
   uint32_t carry = 0;
   const uint32_t half = 1u << (pl.c - 1);
   const uint32_t lane = threadIdx.x & 31;
-  for (uint32_t w = 0; w < pl.nwin; w++) {
+  const uint32_t wend = pl.win0 + pl.nwin;
+  for (uint32_t w = 0; w < wend; w++) {
     uint32_t d = scalar_bits(s, w * pl.c, pl.c) + carry;
     carry = d > half;
     uint32_t mag = carry ? ((1u << pl.c) - d) : d;
+    if (w < pl.win0) continue;   // warp-uniform
     bool have = live && mag != 0;
     // warp-aggregated atomics: lanes with the same bucket take consecutive slots from one atomicAdd
-    uint32_t key = have ? (w * pl.nbuck + mag - 1) : 0xffffffffu;
+    uint32_t key = have ? ((w - pl.win0) * pl.nbuck + mag - 1) : 0xffffffffu;
     uint32_t peers = __match_any_sync(0xffffffffu, key);
     if (have) {
       uint32_t leader = __ffs(peers) - 1;

@@ -13,7 +13,7 @@ void msm_set_tuning(int c, int seg, int kchunk) {
 }
 
 #define DECL(SUFFIX)                                                                      \
-  int msm_enqueue_##SUFFIX(const void* p, const void* s, size_t n, MsmTicket* tk);      \
+  int msm_enqueue_##SUFFIX(const void* p, const void* s, size_t n, uint32_t wr, uint32_t ww, MsmTicket* tk); \
   int points_conv_##SUFFIX(int to, size_t n, void* p);                                   \
   int batch_mul_##SUFFIX(const void* b, int single, const void* s, size_t n, void* o);
 DECL(g1bn) DECL(g2bn) DECL(g1bls) DECL(g2bls)
@@ -48,9 +48,9 @@ void ticket_release(MsmTicket* tk) {
   tk->host_cap = 0;
   tk->event = nullptr;
 }
-int msm_enqueue(int curve, int group, const void* p, const void* s, size_t n, MsmTicket* tk) {
-  DISPATCH(msm_enqueue_g1bn(p, s, n, tk), msm_enqueue_g2bn(p, s, n, tk), msm_enqueue_g1bls(p, s, n, tk),
-           msm_enqueue_g2bls(p, s, n, tk))
+int msm_enqueue(int curve, int group, const void* p, const void* s, size_t n, uint32_t wr, uint32_t ww, MsmTicket* tk) {
+  DISPATCH(msm_enqueue_g1bn(p, s, n, wr, ww, tk), msm_enqueue_g2bn(p, s, n, wr, ww, tk), msm_enqueue_g1bls(p, s, n, wr, ww, tk),
+           msm_enqueue_g2bls(p, s, n, wr, ww, tk))
 }
 int msm_finish(MsmTicket* tk, uint64_t* out_xy, int* out_inf) {
   if (tk->empty) {
@@ -59,13 +59,13 @@ int msm_finish(MsmTicket* tk, uint64_t* out_xy, int* out_inf) {
     return ZKB_OK;
   }
   ZKB_CUDA(cudaEventSynchronize((cudaEvent_t)tk->event));
-  host_msm_finish(tk->curve, tk->group, tk->host, tk->nwin, tk->c, tk->nlev, tk->logk, tk->parts, tk->nbits, out_xy, out_inf);
+  host_msm_finish(tk->curve, tk->group, tk->host, tk->nwin, tk->win0, tk->c, tk->nlev, tk->logk, tk->parts, tk->nbits, out_xy, out_inf);
   tk->empty = true;
   return ZKB_OK;
 }
 int msm_dev(int curve, int group, const void* p, const void* s, size_t n, uint64_t* o, int* inf) {
   static MsmTicket tk;
-  int rc = msm_enqueue(curve, group, p, s, n, &tk);
+  int rc = msm_enqueue(curve, group, p, s, n, 0, 1, &tk);
   if (rc) return rc;
   return msm_finish(&tk, o, inf);
 }

@@ -21,18 +21,38 @@ template <class F> struct AccumField { typedef F type; static constexpr int MINB
 template <> struct AccumField<Fp<FqBN254>> { typedef Fp<InlineMul<FqBN254>> type; static constexpr int MINB = 4; };
 template <> struct AccumField<Fp<FqBLS381>> { typedef Fp<InlineMul<FqBLS381>> type; static constexpr int MINB = 3; };
 
-inline MsmPlan msm_make_plan(size_t n, uint32_t scalar_bits) {
+// wrank/wworld: this launch handles the windows [W*wrank/wworld, W*(wrank+1)/wworld) of every scalar (multi-GPU window
+// sharding); 0/1 = all windows.
+inline MsmPlan msm_make_plan(size_t n, uint32_t scalar_bits, uint32_t wrank, uint32_t wworld) {
   MsmPlan pl;
   memset(&pl, 0, sizeof(pl));
   uint32_t logn = 0;
   while (((size_t)1 << logn) < n) logn++;
-  // window: the bucket reduction costs ~2.3 full additions per bucket, so fewer, fuller buckets (~64 references each)
-  // beat the classical c = log2(n) - 4
-  int c = g_msm_c ? g_msm_c : (int)logn - 5;
+  // Window choice by a cost model in units of one mixed addition: every window costs n additions plus ~5 per bucket (the
+  // bucket reduction is ~2.3 full additions per bucket plus the piece folds); with window sharding the slowest rank has
+  // ceil(W / world) windows, which favours a W that divides evenly.
+  int c = g_msm_c;
+  if (!c) {
+    double best = 0;
+    int lo = (int)logn - 7 < 3 ? 3 : (int)logn - 7, hi = (int)logn - 3 < 3 ? 3 : (int)logn - 3;
+    if (hi > 22) hi = 22;
+    if (lo > hi) lo = hi;
+    for (int cc = lo; cc <= hi; cc++) {
+      uint32_t W = (scalar_bits + 1 + cc - 1) / cc;
+      uint32_t per_rank = (W + wworld - 1) / wworld;
+      double cost = (double)per_rank * ((double)n + 5.0 * (double)(1u << (cc - 1)));
+      if (c == 0 || cost < best) {
+        best = cost;
+        c = cc;
+      }
+    }
+  }
   if (c < 3) c = 3;
   if (c > 22) c = 22;
   pl.c = (uint32_t)c;
-  pl.nwin = (scalar_bits + 1 + pl.c - 1) / pl.c;
+  pl.nwin_total = (scalar_bits + 1 + pl.c - 1) / pl.c;
+  pl.win0 = pl.nwin_total * wrank / wworld;
+  pl.nwin = pl.nwin_total * (wrank + 1) / wworld - pl.win0;
   pl.nbuck = 1u << (pl.c - 1);
   pl.krun = g_msm_seg ? (uint32_t)g_msm_seg : 32u;
   uint32_t maxlog = g_msm_kchunk ? (uint32_t)g_msm_kchunk : 3u;   // log2 of the reduction radix
@@ -65,7 +85,8 @@ static inline void scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_
 // Enqueues every kernel of one MSM on the library stream plus the device->host copy of the per-window sums into the
 // ticket's pinned buffer; returns without synchronising.  msm_finish_ticket() waits for the copy and recombines on the host.
 template <class F, int SCALAR_BITS>
-int msm_enqueue_t(int curve, int group, const void* d_points, const void* d_scalars, size_t n, MsmTicket* tk) {
+int msm_enqueue_t(int curve, int group, const void* d_points, const void* d_scalars, size_t n, uint32_t wrank, uint32_t wworld,
+                  MsmTicket* tk) {
   typedef typename AccumField<F>::type FA;   // G1: inline-multiplier twin (same layout); G2: F itself
   typedef XYZZ<FA> X;
   static_assert(sizeof(FA) == sizeof(F), "inline twin must share the layout");
@@ -73,6 +94,7 @@ int msm_enqueue_t(int curve, int group, const void* d_points, const void* d_scal
   tk->group = group;
   tk->empty = (n == 0);
   if (n == 0) return ZKB_OK;
+  if (wworld == 0 || wrank >= wworld) return set_error(ZKB_ERR_ARG, "msm: bad window shard");
   if (n >= ((size_t)1 << 31)) return set_error(ZKB_ERR_ARG, "msm: more than 2^31-1 points");
   constexpr int SUM_THREADS = sizeof(X) <= 192 ? 256 : 128;
   static bool attr_set = false;
@@ -83,7 +105,11 @@ int msm_enqueue_t(int curve, int group, const void* d_points, const void* d_scal
     ZKB_CUDA(cudaFuncSetAttribute(msm_sums_kernel<FA, SUM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SUM_THREADS * (int)sizeof(X)));
     attr_set = true;
   }
-  MsmPlan pl = msm_make_plan(n, SCALAR_BITS);
+  MsmPlan pl = msm_make_plan(n, SCALAR_BITS, wrank, wworld);
+  if (pl.nwin == 0) {   // more ranks than windows: nothing to do here
+    tk->empty = true;
+    return ZKB_OK;
+  }
   const size_t nb = (size_t)pl.nwin * pl.nbuck;
   const size_t nrefs = n * pl.nwin;
   if (nrefs >= ((size_t)1 << 32)) return set_error(ZKB_ERR_ARG, "msm: n * windows exceeds 2^32 references");
@@ -195,6 +221,7 @@ int msm_enqueue_t(int curve, int group, const void* d_points, const void* d_scal
   count_d2h(out_bytes);
   ZKB_CUDA(cudaEventRecord((cudaEvent_t)tk->event, st));
   tk->nwin = pl.nwin;
+  tk->win0 = pl.win0;
   tk->c = pl.c;
   tk->nlev = pl.nlev;
   tk->nbits = nbits;
@@ -228,8 +255,8 @@ int batch_mul_run(const void* d_bases, int single_base, const void* d_scalars, s
 
 // every (curve, group) translation unit exports these three with a unique suffix
 #define ZKB_MSM_INSTANTIATE(SUFFIX, FIELD, BITS, CURVE, GROUP)                                                           \
-  int msm_enqueue_##SUFFIX(const void* p, const void* s, size_t n, MsmTicket* tk) {                                     \
-    return msm_enqueue_t<FIELD, BITS>(CURVE, GROUP, p, s, n, tk);                                                       \
+  int msm_enqueue_##SUFFIX(const void* p, const void* s, size_t n, uint32_t wr, uint32_t ww, MsmTicket* tk) {           \
+    return msm_enqueue_t<FIELD, BITS>(CURVE, GROUP, p, s, n, wr, ww, tk);                                               \
   }                                                                                                                      \
   int points_conv_##SUFFIX(int to, size_t n, void* p) { return points_conv_run<FIELD>(to != 0, n, p); }                 \
   int batch_mul_##SUFFIX(const void* b, int single, const void* s, size_t n, void* o) {                                 \

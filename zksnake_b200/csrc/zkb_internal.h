@@ -71,14 +71,16 @@ int spmv_dev(int curve, size_t n_out, size_t n_rows, const void* row_ptr, const 
 struct MsmTicket {
   int curve = 0, group = 1;
   bool empty = true;
-  uint32_t nwin = 0, c = 0, nlev = 0, nbits = 0, logk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, parts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t nwin = 0, win0 = 0, c = 0, nlev = 0, nbits = 0, logk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, parts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   unsigned char* host = nullptr;   // pinned
   size_t host_cap = 0;
   void* event = nullptr;           // cudaEvent_t
 };
 int ticket_reserve(MsmTicket* tk, size_t bytes);
 void ticket_release(MsmTicket* tk);
-int msm_enqueue(int curve, int group, const void* d_points, const void* d_scalars, size_t n, MsmTicket* tk);
+// wrank/wworld: window shard handled by this call (0/1 = the whole MSM); the result is then the partial sum over those windows
+int msm_enqueue(int curve, int group, const void* d_points, const void* d_scalars, size_t n, uint32_t wrank, uint32_t wworld,
+                MsmTicket* tk);
 int msm_finish(MsmTicket* tk, uint64_t* out_xy, int* out_inf);
 int msm_dev(int curve, int group, const void* d_points, const void* d_scalars, size_t n, uint64_t* out_xy, int* out_inf);
 int points_to_mont_dev(int curve, int group, size_t n, void* d_points);
@@ -91,8 +93,9 @@ void msm_set_tuning(int c, int seg, int kchunk);
 // parts[nlev-1] of U_{nlev-1}, then A_0..A_{nbits-1}, R_top):
 //   window sum = R_top + U_0 + 2^logk[0] (U_1 + ... + 2^logk[nlev-1] (sum_beta 2^beta A_beta)),
 // then Horner over the windows with c doublings each
-void host_msm_finish(int curve, int group, const void* sums, uint32_t nwin, uint32_t c, uint32_t nlev, const uint32_t* logk,
-                     const uint32_t* parts, uint32_t nbits, uint64_t* out_xy, int* out_inf);
+// (the windows are win0 .. win0+nwin-1 of the scalar: the result is multiplied by 2^(c*win0))
+void host_msm_finish(int curve, int group, const void* sums, uint32_t nwin, uint32_t win0, uint32_t c, uint32_t nlev,
+                     const uint32_t* logk, const uint32_t* parts, uint32_t nbits, uint64_t* out_xy, int* out_inf);
 // out = sum_i k_i * P_i + sum_j Q_j over a handful of canonical affine points (proof assembly)
 void host_lincomb(int curve, int group, int n_terms, const uint64_t* const* points, const int* infs,
                   const uint64_t* const* scalars, uint64_t* out_xy, int* out_inf);

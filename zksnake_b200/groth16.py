@@ -71,10 +71,15 @@ class VerifyingKey:
 
 
 class Groth16:
-    def __init__(self, r1cs: R1CS, curve: str = "BN254", shard=None):
-        """shard = (rank, world): this process keeps only its contiguous slice of the four proving-key vectors and proves
-        cooperatively with the other ranks (zksnake_b200/dist.py).  Default: the torch.distributed world, else (0, 1)."""
+    def __init__(self, r1cs: R1CS, curve: str = "BN254", shard=None, shard_mode="windows"):
+        """shard = (rank, world): this process proves cooperatively with the other ranks (zksnake_b200/dist.py).  Default: the
+        torch.distributed world, else (0, 1).  shard_mode "windows" (default): every rank holds the whole key and runs the
+        scalar windows [W*rank/world, W*(rank+1)/world) of every MSM -- sort, accumulation and bucket reduction all shrink by
+        1/world.  "points": every rank keeps only its contiguous 1/world slice of the four key vectors (1/world of the memory;
+        only the accumulation shrinks)."""
         self.rank, self.world = shard if shard is not None else dist.world()
+        assert shard_mode in ("windows", "points")
+        self.shard_mode = shard_mode
         self.curve_name = curve
         self.curve = _CURVES[curve]
         self.ec = _EC[self.curve]
@@ -114,7 +119,8 @@ class Groth16:
         K = [(L[i] * beta + R[i] * alpha + O[i]) % o for i in range(m)]
         t = self.poly.evaluate_vanishing_polynomial(n, tau)
 
-        lo, hi = dist.shard_range(n, self.rank, self.world)
+        by_points = self.shard_mode == "points"
+        lo, hi = dist.shard_range(n, self.rank, self.world) if by_points else (0, n)
         self._slice = (lo, hi)
 
         def powers(scale):  # scale * tau^i for i in this rank's slice
@@ -137,7 +143,7 @@ class Groth16:
         d_tgt = powers(t * inv_delta % o)
         target_G1 = batch(G1, 1, d_tgt, hi - lo)
         n_priv = m - self.n_public
-        klo, khi = dist.shard_range(n_priv, self.rank, self.world)
+        klo, khi = dist.shard_range(n_priv, self.rank, self.world) if by_points else (0, n_priv)
         self._kslice = (klo, khi)
         d_k = nat.DeviceBuffer(max(khi - klo, 1) * 32)
         if khi > klo:
@@ -164,6 +170,8 @@ class Groth16:
                                                         *[nat.ptr(s) for s in singles], ctypes.byref(h)))
         self._pk_handle = h
         self._singles = singles
+        if self.shard_mode == "windows" and self.world > 1:
+            nat.check(nat.lib.zkb_groth16_pk_set_window_shard(h, self.rank, self.world))
         n_rows = max((t[0] for arr in (self.r1cs.A, self.r1cs.B, self.r1cs.C) for t in arr.triplets), default=-1) + 1
         csr = [arr.to_csr(n_rows) for arr in (self.r1cs.A, self.r1cs.B, self.r1cs.C)]
         self._csr = csr

@@ -319,20 +319,21 @@ static int groth16_msms(zkb_groth16_pk* pk, const void* d_priv) {
   const size_t bytes = pk->n * 32;
   char* w = pk->work;
   const char *d_u = w + 3 * bytes + pk->off * 32, *d_v = w + 4 * bytes + pk->off * 32, *d_h = w + 6 * bytes + pk->off * 32;
-  // enqueue MSM i+1 before recombining MSM i on the host: the host Horner steps (~0.2 ms each) hide behind GPU work
+  // The five MSMs as one batch: sort + accumulate back to back on the library stream, every reduction (latency-bound) on a
+  // side stream as soon as its accumulation is done.  The G2 MSM goes first: its reduction chain is the longest (an Fp2
+  // addition is ~40 dependent Fq products) and so hides behind the four G1 accumulations.
   static MsmTicket tk[5];
-  struct { int group; const void* pts; const void* sc; size_t n; } job[5] = {
-      {1, pk->tau1, d_u, pk->len},
-      {1, pk->tau1, d_v, pk->len},
-      {2, pk->tau2, d_v, pk->len},
-      {1, pk->target1, d_h, pk->len},
-      {1, pk->kdelta1, (const char*)d_priv + pk->koff * 32, pk->klen}};
+  static const int slot[5] = {2, 0, 1, 3, 4};   // batch position -> index in msm_xy (A, B1, B2, HZ, KW)
+  MsmJob job[5] = {{2, pk->tau2, d_v, pk->len},
+                   {1, pk->tau1, d_u, pk->len},
+                   {1, pk->tau1, d_v, pk->len},
+                   {1, pk->target1, d_h, pk->len},
+                   {1, pk->kdelta1, (const char*)d_priv + pk->koff * 32, pk->klen}};
   int rc;
-  for (int i = 0; i < 5; i++) {
-    if ((rc = msm_enqueue(curve, job[i].group, job[i].pts, job[i].sc, job[i].n, pk->wrank, pk->wworld, &tk[i]))) return rc;
-    if (i > 0 && (rc = msm_finish(&tk[i - 1], pk->msm_xy[i - 1], &pk->msm_inf[i - 1]))) return rc;
-  }
-  return msm_finish(&tk[4], pk->msm_xy[4], &pk->msm_inf[4]);
+  if ((rc = msm_enqueue_batch(curve, job, 5, pk->wrank, pk->wworld, tk))) return rc;
+  for (int i = 0; i < 5; i++)
+    if ((rc = msm_finish(&tk[i], pk->msm_xy[slot[i]], &pk->msm_inf[slot[i]]))) return rc;
+  return ZKB_OK;
 }
 
 int zkb_groth16_assemble(zkb_groth16_pk* pk, const uint64_t* msm_xy, const int* msm_inf, const uint64_t r[4], const uint64_t s[4],

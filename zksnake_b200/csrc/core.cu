@@ -14,6 +14,7 @@ struct Ctx {
   int device = -1;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t side[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   char* arena = nullptr;
   size_t arena_cap = 0, arena_off = 0;
   unsigned long long launches = 0;
@@ -32,6 +33,11 @@ int cuda_fail(int cuda_err, const char* what, const char* file, int line) {
   return set_error(ZKB_ERR_CUDA, buf);
 }
 void* ctx_stream() { return (void*)g_ctx.stream; }
+void* ctx_side_stream(int i) {
+  if (i < 0 || i >= 8) return nullptr;
+  if (!g_ctx.side[i] && cudaStreamCreateWithFlags(&g_ctx.side[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  return (void*)g_ctx.side[i];
+}
 bool ctx_ready() { return g_ctx.ready; }
 void count_launch(int n) { g_ctx.launches += n; }
 static unsigned long long g_h2d_bytes = 0, g_d2h_bytes = 0;
@@ -181,6 +187,10 @@ void zkb_shutdown(void) {
   g_ctx.arena_cap = g_ctx.arena_off = 0;
   cudaEventDestroy(g_ctx.ev0);
   cudaEventDestroy(g_ctx.ev1);
+  for (int i = 0; i < 8; i++) {
+    if (g_ctx.side[i]) cudaStreamDestroy(g_ctx.side[i]);
+    g_ctx.side[i] = nullptr;
+  }
   cudaStreamDestroy(g_ctx.stream);
   g_ctx.stream = nullptr;
   g_ctx.ready = false;

@@ -13,7 +13,9 @@ void msm_set_tuning(int c, int seg, int kchunk) {
 }
 
 #define DECL(SUFFIX)                                                                      \
-  int msm_enqueue_##SUFFIX(const void* p, const void* s, size_t n, uint32_t wr, uint32_t ww, MsmTicket* tk); \
+  int msm_need_##SUFFIX(size_t n, uint32_t wr, uint32_t ww, size_t* need);                                \
+  int msm_phase1_##SUFFIX(const void* p, const void* s, size_t n, uint32_t wr, uint32_t ww, MsmTicket* tk); \
+  int msm_phase2_##SUFFIX(MsmTicket* tk, void* stream);                                                   \
   int points_conv_##SUFFIX(int to, size_t n, void* p);                                   \
   int batch_mul_##SUFFIX(const void* b, int single, const void* s, size_t n, void* o);
 DECL(g1bn) DECL(g2bn) DECL(g1bls) DECL(g2bls)
@@ -48,9 +50,61 @@ void ticket_release(MsmTicket* tk) {
   tk->host_cap = 0;
   tk->event = nullptr;
 }
+static int msm_need(int curve, int group, size_t n, uint32_t wr, uint32_t ww, size_t* need) {
+  DISPATCH(msm_need_g1bn(n, wr, ww, need), msm_need_g2bn(n, wr, ww, need), msm_need_g1bls(n, wr, ww, need),
+           msm_need_g2bls(n, wr, ww, need))
+}
+static int msm_phase1(int curve, int group, const void* p, const void* s, size_t n, uint32_t wr, uint32_t ww, MsmTicket* tk) {
+  DISPATCH(msm_phase1_g1bn(p, s, n, wr, ww, tk), msm_phase1_g2bn(p, s, n, wr, ww, tk), msm_phase1_g1bls(p, s, n, wr, ww, tk),
+           msm_phase1_g2bls(p, s, n, wr, ww, tk))
+}
+static int msm_phase2(MsmTicket* tk, void* stream) {
+  const int curve = tk->curve, group = tk->group;
+  DISPATCH(msm_phase2_g1bn(tk, stream), msm_phase2_g2bn(tk, stream), msm_phase2_g1bls(tk, stream), msm_phase2_g2bls(tk, stream))
+}
 int msm_enqueue(int curve, int group, const void* p, const void* s, size_t n, uint32_t wr, uint32_t ww, MsmTicket* tk) {
-  DISPATCH(msm_enqueue_g1bn(p, s, n, wr, ww, tk), msm_enqueue_g2bn(p, s, n, wr, ww, tk), msm_enqueue_g1bls(p, s, n, wr, ww, tk),
-           msm_enqueue_g2bls(p, s, n, wr, ww, tk))
+  size_t need = 0;
+  int rc;
+  if ((rc = msm_need(curve, group, n, wr, ww, &need))) return rc;
+  if ((rc = scratch_reserve(need))) return rc;
+  scratch_reset();
+  if ((rc = msm_phase1(curve, group, p, s, n, wr, ww, tk))) return rc;
+  prof_begin(PROF_MSM_REDUCE);
+  rc = msm_phase2(tk, ctx_stream());
+  prof_end(PROF_MSM_REDUCE);
+  return rc;
+}
+int msm_enqueue_batch(int curve, const MsmJob* jobs, int njobs, uint32_t wr, uint32_t ww, MsmTicket* tickets) {
+  if (njobs > 8) return set_error(ZKB_ERR_ARG, "msm batch: at most 8 jobs");
+  size_t total = 0;
+  int rc;
+  for (int i = 0; i < njobs; i++) {
+    size_t need = 0;
+    if ((rc = msm_need(curve, jobs[i].group, jobs[i].n, wr, ww, &need))) return rc;
+    total += need;
+  }
+  if ((rc = scratch_reserve(total))) return rc;
+  scratch_reset();
+  cudaStream_t main_st = (cudaStream_t)ctx_stream();
+  // fork after every phase 1: the job's reduction runs on its own side stream while the library stream goes on with the next
+  // job's sort and accumulation (the accumulation is a work-stealing persistent grid, so it tolerates the few CTAs slots the
+  // short reduction kernels borrow); join at the end so later library work is ordered after all of them
+  static cudaEvent_t fork_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int i = 0; i < njobs; i++) {
+    if ((rc = msm_phase1(curve, jobs[i].group, jobs[i].points, jobs[i].scalars, jobs[i].n, wr, ww, &tickets[i]))) return rc;
+    if (tickets[i].empty) continue;
+    if (!fork_ev[i]) ZKB_CUDA(cudaEventCreateWithFlags(&fork_ev[i], cudaEventDisableTiming));
+    cudaStream_t side = (cudaStream_t)ctx_side_stream(i);
+    if (!side) return set_error(ZKB_ERR_CUDA, "msm batch: cannot create a side stream");
+    ZKB_CUDA(cudaEventRecord(fork_ev[i], main_st));
+    ZKB_CUDA(cudaStreamWaitEvent(side, fork_ev[i], 0));
+    if ((rc = msm_phase2(&tickets[i], side))) return rc;
+  }
+  prof_begin(PROF_MSM_REDUCE);   // what is left of the reductions after the last accumulation
+  for (int i = 0; i < njobs; i++)
+    if (!tickets[i].empty) ZKB_CUDA(cudaStreamWaitEvent(main_st, (cudaEvent_t)tickets[i].event, 0));
+  prof_end(PROF_MSM_REDUCE);
+  return ZKB_OK;
 }
 int msm_finish(MsmTicket* tk, uint64_t* out_xy, int* out_inf) {
   if (tk->empty) {

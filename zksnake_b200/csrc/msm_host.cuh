@@ -82,87 +82,114 @@ static inline void scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_
   scan_final_kernel<<<nparts, ZKB_SCAN_THREADS, 0, st>>>(in, out, part, n, nparts);
 }
 
-// Enqueues every kernel of one MSM on the library stream plus the device->host copy of the per-window sums into the
-// ticket's pinned buffer; returns without synchronising.  msm_finish_ticket() waits for the copy and recombines on the host.
+// Sizes of one MSM launch, derived from the plan only (so the scratch of a whole batch can be reserved up front).
+template <class X>
+struct MsmGeom {
+  MsmPlan pl;
+  size_t nb, nrefs, max_pieces, nparts, max_vhot, lev_elems, out_bytes, need;
+  uint32_t m, nbits, njobs, parts[ZKB_MSM_MAXLEV];
+  bool skip;   // nothing to do (n == 0, or a window shard beyond the last window)
+};
+template <class X>
+inline int msm_geometry(size_t n, uint32_t scalar_bits, uint32_t wrank, uint32_t wworld, MsmGeom<X>* g) {
+  memset(g, 0, sizeof(*g));
+  if (wworld == 0 || wrank >= wworld) return set_error(ZKB_ERR_ARG, "msm: bad window shard");
+  if (n >= ((size_t)1 << 31)) return set_error(ZKB_ERR_ARG, "msm: more than 2^31-1 points");
+  if (n == 0) {
+    g->skip = true;
+    return ZKB_OK;
+  }
+  g->pl = msm_make_plan(n, scalar_bits, wrank, wworld);
+  const MsmPlan& pl = g->pl;
+  if (pl.nwin == 0) {   // more ranks than windows
+    g->skip = true;
+    return ZKB_OK;
+  }
+  g->nb = (size_t)pl.nwin * pl.nbuck;
+  g->nrefs = n * pl.nwin;
+  if (g->nrefs >= ((size_t)1 << 32)) return set_error(ZKB_ERR_ARG, "msm: n * windows exceeds 2^32 references");
+  g->max_pieces = pl.max_runs + g->nb + 1;
+  g->nparts = (g->nb + ZKB_SCAN_TILE - 1) / ZKB_SCAN_TILE + 2;
+  g->max_vhot = pl.max_runs / ZKB_MSM_VHOT + 1;
+  for (uint32_t l = 0; l < pl.nlev; l++) g->lev_elems += (size_t)pl.nwin * pl.lsize[l + 1];
+  g->m = pl.lsize[pl.nlev];
+  while ((1u << g->nbits) < g->m) g->nbits++;
+  g->njobs = g->nbits + 1;
+  for (uint32_t l = 0; l < pl.nlev; l++) {   // U_l is summed in parts of ~512 elements (at most ZKB_MSM_MAXPARTS)
+    uint32_t p = (pl.lsize[l + 1] + 511) / 512;
+    g->parts[l] = p > ZKB_MSM_MAXPARTS ? ZKB_MSM_MAXPARTS : p;
+    g->njobs += g->parts[l];
+  }
+  if (g->njobs > ZKB_MSM_MAXJOBS) return set_error(ZKB_ERR_ARG, "msm: too many reduction jobs");
+  g->out_bytes = (size_t)pl.nwin * g->njobs * sizeof(X);
+  g->need = (g->nb + 1) * 4 * 6 + g->nrefs * 4 + (pl.max_runs + 1) * 4 + g->nb * 4 + g->max_vhot * 4 + g->nparts * 4 +
+            g->max_pieces * sizeof(X) + 2 * g->lev_elems * sizeof(X) + g->max_vhot * ZKB_MSM_VHOT_SPLIT * sizeof(X) +
+            g->out_bytes + 32 * 256;
+  return ZKB_OK;
+}
+
+// device pointers an MSM keeps between its two phases (stored in the ticket)
+template <class X>
+struct MsmDev {
+  MsmGeom<X> g;
+  uint32_t *np_eff, *pstart, *hot_list, *vhot_list, *counters;
+  X *pieces, *lev_t, *lev_r, *side, *sums;
+};
+
 template <class F, int SCALAR_BITS>
-int msm_enqueue_t(int curve, int group, const void* d_points, const void* d_scalars, size_t n, uint32_t wrank, uint32_t wworld,
-                  MsmTicket* tk) {
+int msm_need_t(size_t n, uint32_t wrank, uint32_t wworld, size_t* need) {
+  typedef XYZZ<typename AccumField<F>::type> X;
+  MsmGeom<X> g;
+  int rc = msm_geometry<X>(n, SCALAR_BITS, wrank, wworld, &g);
+  *need = g.need + 4096;
+  return rc;
+}
+
+// Phase 1 on the library stream: digit sort and bucket accumulation.  Takes its scratch from the arena WITHOUT resetting it
+// (the caller reserved and reset once for the whole batch), so several MSMs can be between phase 1 and phase 2 at once.
+template <class F, int SCALAR_BITS>
+int msm_phase1_t(int curve, int group, const void* d_points, const void* d_scalars, size_t n, uint32_t wrank, uint32_t wworld,
+                 MsmTicket* tk) {
   typedef typename AccumField<F>::type FA;   // G1: inline-multiplier twin (same layout); G2: F itself
   typedef XYZZ<FA> X;
   static_assert(sizeof(FA) == sizeof(F), "inline twin must share the layout");
+  static_assert(sizeof(MsmDev<X>) <= sizeof(tk->dev), "ticket device-state storage too small");
   tk->curve = curve;
   tk->group = group;
-  tk->empty = (n == 0);
-  if (n == 0) return ZKB_OK;
-  if (wworld == 0 || wrank >= wworld) return set_error(ZKB_ERR_ARG, "msm: bad window shard");
-  if (n >= ((size_t)1 << 31)) return set_error(ZKB_ERR_ARG, "msm: more than 2^31-1 points");
-  constexpr int SUM_THREADS = sizeof(X) <= 192 ? 256 : 128;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ZKB_CUDA(cudaFuncSetAttribute(msm_fold_cta1_kernel<FA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (int)sizeof(X)));
-    ZKB_CUDA(cudaFuncSetAttribute(msm_fold_cta2_kernel<FA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)ZKB_MSM_VHOT_SPLIT * (int)sizeof(X)));
-    ZKB_CUDA(cudaFuncSetAttribute(msm_sums_kernel<FA, SUM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SUM_THREADS * (int)sizeof(X)));
-    attr_set = true;
-  }
-  MsmPlan pl = msm_make_plan(n, SCALAR_BITS, wrank, wworld);
-  if (pl.nwin == 0) {   // more ranks than windows: nothing to do here
-    tk->empty = true;
-    return ZKB_OK;
-  }
-  const size_t nb = (size_t)pl.nwin * pl.nbuck;
-  const size_t nrefs = n * pl.nwin;
-  if (nrefs >= ((size_t)1 << 32)) return set_error(ZKB_ERR_ARG, "msm: n * windows exceeds 2^32 references");
-  const size_t max_pieces = pl.max_runs + nb + 1;
-  const size_t nparts = (nb + ZKB_SCAN_TILE - 1) / ZKB_SCAN_TILE + 2;
-  const size_t max_vhot = pl.max_runs / ZKB_MSM_VHOT + 1;
-  size_t lev_elems = 0;   // T and R arrays of all levels
-  for (uint32_t l = 0; l < pl.nlev; l++) lev_elems += (size_t)pl.nwin * pl.lsize[l + 1];
-  const uint32_t m = pl.lsize[pl.nlev];
-  uint32_t nbits = 0;
-  while ((1u << nbits) < m) nbits++;
-  uint32_t parts[ZKB_MSM_MAXLEV];   // U_l is summed in parts of ~512 elements (at most ZKB_MSM_MAXPARTS)
-  uint32_t njobs = nbits + 1;
-  for (uint32_t l = 0; l < pl.nlev; l++) {
-    uint32_t p = (pl.lsize[l + 1] + 511) / 512;
-    parts[l] = p > ZKB_MSM_MAXPARTS ? ZKB_MSM_MAXPARTS : p;
-    njobs += parts[l];
-  }
-  if (njobs > ZKB_MSM_MAXJOBS) return set_error(ZKB_ERR_ARG, "msm: too many reduction jobs");
-  const size_t out_bytes = (size_t)pl.nwin * njobs * sizeof(X);
-
-  size_t need = (nb + 1) * 4 * 6 + nrefs * 4 + (pl.max_runs + 1) * 4 + nb * 4 + max_vhot * 4 + nparts * 4 +
-                max_pieces * sizeof(X) + 2 * lev_elems * sizeof(X) + max_vhot * ZKB_MSM_VHOT_SPLIT * sizeof(X) + out_bytes +
-                64 * 256;
+  MsmDev<X>* d = reinterpret_cast<MsmDev<X>*>(tk->dev);
   int rc;
-  if ((rc = scratch_reserve(need))) return rc;
-  if ((rc = ticket_reserve(tk, out_bytes))) return rc;
-  scratch_reset();
+  if ((rc = msm_geometry<X>(n, SCALAR_BITS, wrank, wworld, &d->g))) return rc;
+  tk->empty = d->g.skip;
+  if (d->g.skip) return ZKB_OK;
+  const MsmGeom<X>& g = d->g;
+  const MsmPlan& pl = g.pl;
+  if ((rc = ticket_reserve(tk, g.out_bytes))) return rc;
+  const size_t nb = g.nb;
   uint32_t* cnt = (uint32_t*)scratch_take((nb + 1) * 4);
   uint32_t* start = (uint32_t*)scratch_take((nb + 1) * 4);
   uint32_t* cursor = (uint32_t*)scratch_take((nb + 1) * 4);
   uint32_t* npieces = (uint32_t*)scratch_take((nb + 1) * 4);
-  uint32_t* np_eff = (uint32_t*)scratch_take((nb + 1) * 4);
-  uint32_t* pstart = (uint32_t*)scratch_take((nb + 1) * 4);
-  uint32_t* refs = (uint32_t*)scratch_take(nrefs * 4);
+  d->np_eff = (uint32_t*)scratch_take((nb + 1) * 4);
+  d->pstart = (uint32_t*)scratch_take((nb + 1) * 4);
+  uint32_t* refs = (uint32_t*)scratch_take(g.nrefs * 4);
   uint32_t* run_bucket = (uint32_t*)scratch_take((pl.max_runs + 1) * 4);
-  uint32_t* hot_list = (uint32_t*)scratch_take(nb * 4);
-  uint32_t* vhot_list = (uint32_t*)scratch_take(max_vhot * 4);
-  uint32_t* part = (uint32_t*)scratch_take(nparts * 4);
-  uint32_t* counters = (uint32_t*)scratch_take(256);   // [0] hot count, [1] accumulate work counter, [2] very hot count
-  X* pieces = (X*)scratch_take(max_pieces * sizeof(X));
-  X* lev_t = (X*)scratch_take(lev_elems * sizeof(X));
-  X* lev_r = (X*)scratch_take(lev_elems * sizeof(X));
-  X* side = (X*)scratch_take(max_vhot * ZKB_MSM_VHOT_SPLIT * sizeof(X));
-  X* sums = (X*)scratch_take(out_bytes);
-  if (!cnt || !start || !cursor || !npieces || !np_eff || !pstart || !refs || !run_bucket || !hot_list || !vhot_list || !part ||
-      !counters || !pieces || !lev_t || !lev_r || !side || !sums)
+  d->hot_list = (uint32_t*)scratch_take(nb * 4);
+  d->vhot_list = (uint32_t*)scratch_take(g.max_vhot * 4);
+  uint32_t* part = (uint32_t*)scratch_take(g.nparts * 4);
+  d->counters = (uint32_t*)scratch_take(256);   // [0] hot count, [1] accumulate work counter, [2] very hot count
+  d->pieces = (X*)scratch_take(g.max_pieces * sizeof(X));
+  d->lev_t = (X*)scratch_take(g.lev_elems * sizeof(X));
+  d->lev_r = (X*)scratch_take(g.lev_elems * sizeof(X));
+  d->side = (X*)scratch_take(g.max_vhot * ZKB_MSM_VHOT_SPLIT * sizeof(X));
+  d->sums = (X*)scratch_take(g.out_bytes);
+  if (!cnt || !start || !cursor || !npieces || !d->np_eff || !d->pstart || !refs || !run_bucket || !d->hot_list || !d->vhot_list ||
+      !part || !d->counters || !d->pieces || !d->lev_t || !d->lev_r || !d->side || !d->sums)
     return set_error(ZKB_ERR_CUDA, "msm: scratch exhausted");
 
   cudaStream_t st = MS();
   const uint32_t* sc = (const uint32_t*)d_scalars;
   ZKB_CUDA(cudaMemsetAsync(cnt, 0, (nb + 1) * 4, st));
-  ZKB_CUDA(cudaMemsetAsync(counters, 0, 256, st));
+  ZKB_CUDA(cudaMemsetAsync(d->counters, 0, 256, st));
   unsigned pblocks = (unsigned)((n + 255) / 256);
   unsigned bblocks = (unsigned)((nb + 255) / 256);
   prof_begin(PROF_MSM_SORT);
@@ -170,21 +197,46 @@ int msm_enqueue_t(int curve, int group, const void* d_points, const void* d_scal
   scan_u32(cnt, start, nb, part, st);
   ZKB_CUDA(cudaMemcpyAsync(cursor, start, (nb + 1) * 4, cudaMemcpyDeviceToDevice, st));
   msm_scatter_kernel<<<pblocks, 256, 0, st>>>(pl, sc, cursor, refs);
-  msm_piece_plan_kernel<<<bblocks, 256, 0, st>>>(pl, cnt, start, npieces, np_eff, run_bucket, hot_list, vhot_list, counters);
-  scan_u32(npieces, pstart, nb, part, st);
+  msm_piece_plan_kernel<<<bblocks, 256, 0, st>>>(pl, cnt, start, npieces, d->np_eff, run_bucket, d->hot_list, d->vhot_list,
+                                                 d->counters);
+  scan_u32(npieces, d->pstart, nb, part, st);
   prof_end(PROF_MSM_SORT);
   const int acc_tag = group == 2 ? PROF_MSM_ACCUM_G2 : PROF_MSM_ACCUM_G1;
   prof_begin(acc_tag);
   constexpr int MINB = AccumField<F>::MINB;
-  msm_accumulate_kernel<FA, MINB><<<148 * MINB, 128, 0, st>>>(pl, (const Affine<FA>*)d_points, refs, start, pstart, run_bucket,
-                                                              pieces, counters + 1);
+  msm_accumulate_kernel<FA, MINB><<<148 * MINB, 128, 0, st>>>(pl, (const Affine<FA>*)d_points, refs, start, d->pstart, run_bucket,
+                                                              d->pieces, d->counters + 1);
   prof_end(acc_tag);
-  prof_begin(PROF_MSM_REDUCE);
-  msm_fold_cta1_kernel<FA><<<dim3(ZKB_MSM_VHOT_SPLIT, 8), 128, 128 * sizeof(X), st>>>(vhot_list, counters, np_eff, pstart, pieces,
-                                                                                      side);
-  msm_fold_cta2_kernel<FA><<<8, ZKB_MSM_VHOT_SPLIT, ZKB_MSM_VHOT_SPLIT * sizeof(X), st>>>(vhot_list, counters, np_eff, pstart,
-                                                                                         pieces, side);
-  msm_fold_warp_kernel<FA><<<148 * 4, 128, 0, st>>>(hot_list, counters, np_eff, pstart, pieces);
+  count_launch(11);
+  ZKB_CUDA(cudaGetLastError());
+  return ZKB_OK;
+}
+
+// Phase 2 on stream `st` (the library stream, or a side stream so that the latency-bound reductions of several MSMs overlap):
+// folds, bucket reduction, plain sums, device->host copy of the per-window sums into the ticket's pinned buffer, event record.
+template <class F, int SCALAR_BITS>
+int msm_phase2_t(MsmTicket* tk, cudaStream_t st) {
+  typedef typename AccumField<F>::type FA;
+  typedef XYZZ<FA> X;
+  if (tk->empty) return ZKB_OK;
+  MsmDev<X>* d = reinterpret_cast<MsmDev<X>*>(tk->dev);
+  const MsmGeom<X>& g = d->g;
+  const MsmPlan& pl = g.pl;
+  constexpr int SUM_THREADS = sizeof(X) <= 192 ? 256 : 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ZKB_CUDA(cudaFuncSetAttribute(msm_fold_cta1_kernel<FA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (int)sizeof(X)));
+    ZKB_CUDA(cudaFuncSetAttribute(msm_fold_cta2_kernel<FA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)ZKB_MSM_VHOT_SPLIT * (int)sizeof(X)));
+    ZKB_CUDA(cudaFuncSetAttribute(msm_sums_kernel<FA, SUM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  SUM_THREADS * (int)sizeof(X)));
+    attr_set = true;
+  }
+  msm_fold_cta1_kernel<FA><<<dim3(ZKB_MSM_VHOT_SPLIT, 8), 128, 128 * sizeof(X), st>>>(d->vhot_list, d->counters, d->np_eff,
+                                                                                      d->pstart, d->pieces, d->side);
+  msm_fold_cta2_kernel<FA><<<8, ZKB_MSM_VHOT_SPLIT, ZKB_MSM_VHOT_SPLIT * sizeof(X), st>>>(d->vhot_list, d->counters, d->np_eff,
+                                                                                         d->pstart, d->pieces, d->side);
+  msm_fold_warp_kernel<FA><<<148 * 4, 128, 0, st>>>(d->hot_list, d->counters, d->np_eff, d->pstart, d->pieces);
   SumJobs<FA> jobs;
   memset(&jobs, 0, sizeof(jobs));
   size_t off = 0;
@@ -193,41 +245,40 @@ int msm_enqueue_t(int curve, int group, const void* d_points, const void* d_scal
   for (uint32_t l = 0; l < pl.nlev; l++) {
     size_t outs = (size_t)pl.nwin * pl.lsize[l + 1];
     unsigned blocks = (unsigned)((outs + 127) / 128);
-    if (l == 0) msm_level0_kernel<FA><<<blocks, 128, 0, st>>>(pl, np_eff, pstart, pieces, lev_t + off, lev_r + off);
-    else msm_level_kernel<FA><<<blocks, 128, 0, st>>>(pl.nwin, pl.lsize[l], pl.logk[l], r_prev, lev_t + off, lev_r + off);
-    uint32_t per = (pl.lsize[l + 1] + parts[l] - 1) / parts[l];
-    for (uint32_t p = 0; p < parts[l]; p++, q++) {
-      jobs.base[q] = lev_t + off;
+    if (l == 0) msm_level0_kernel<FA><<<blocks, 128, 0, st>>>(pl, d->np_eff, d->pstart, d->pieces, d->lev_t + off, d->lev_r + off);
+    else msm_level_kernel<FA><<<blocks, 128, 0, st>>>(pl.nwin, pl.lsize[l], pl.logk[l], r_prev, d->lev_t + off, d->lev_r + off);
+    uint32_t per = (pl.lsize[l + 1] + g.parts[l] - 1) / g.parts[l];
+    for (uint32_t p = 0; p < g.parts[l]; p++, q++) {
+      jobs.base[q] = d->lev_t + off;
       jobs.stride[q] = pl.lsize[l + 1];
       jobs.offset[q] = p * per;
       jobs.count[q] = (p + 1) * per <= pl.lsize[l + 1] ? per : pl.lsize[l + 1] - p * per;
       jobs.bit[q] = -1;
     }
-    r_prev = lev_r + off;
+    r_prev = d->lev_r + off;
     off += outs;
   }
-  for (uint32_t k = 0; k <= nbits; k++, q++) {
+  for (uint32_t k = 0; k <= g.nbits; k++, q++) {
     jobs.base[q] = r_prev;
-    jobs.stride[q] = m;
+    jobs.stride[q] = g.m;
     jobs.offset[q] = 0;
-    jobs.count[q] = m;
-    jobs.bit[q] = (k == nbits) ? -1 : (int)k;
+    jobs.count[q] = g.m;
+    jobs.bit[q] = (k == g.nbits) ? -1 : (int)k;
   }
-  msm_sums_kernel<FA, SUM_THREADS><<<dim3(njobs, pl.nwin), SUM_THREADS, SUM_THREADS * sizeof(X), st>>>(jobs, njobs, sums);
-  prof_end(PROF_MSM_REDUCE);
-  count_launch(14 + (int)pl.nlev);
+  msm_sums_kernel<FA, SUM_THREADS><<<dim3(g.njobs, pl.nwin), SUM_THREADS, SUM_THREADS * sizeof(X), st>>>(jobs, g.njobs, d->sums);
+  count_launch(4 + (int)pl.nlev);
   ZKB_CUDA(cudaGetLastError());
-  ZKB_CUDA(cudaMemcpyAsync(tk->host, sums, out_bytes, cudaMemcpyDeviceToHost, st));
-  count_d2h(out_bytes);
+  ZKB_CUDA(cudaMemcpyAsync(tk->host, d->sums, g.out_bytes, cudaMemcpyDeviceToHost, st));
+  count_d2h(g.out_bytes);
   ZKB_CUDA(cudaEventRecord((cudaEvent_t)tk->event, st));
   tk->nwin = pl.nwin;
   tk->win0 = pl.win0;
   tk->c = pl.c;
   tk->nlev = pl.nlev;
-  tk->nbits = nbits;
+  tk->nbits = g.nbits;
   for (uint32_t l = 0; l < ZKB_MSM_MAXLEV; l++) {
     tk->logk[l] = pl.logk[l];
-    tk->parts[l] = l < pl.nlev ? parts[l] : 0;
+    tk->parts[l] = l < pl.nlev ? g.parts[l] : 0;
   }
   return ZKB_OK;
 }
@@ -255,9 +306,11 @@ int batch_mul_run(const void* d_bases, int single_base, const void* d_scalars, s
 
 // every (curve, group) translation unit exports these three with a unique suffix
 #define ZKB_MSM_INSTANTIATE(SUFFIX, FIELD, BITS, CURVE, GROUP)                                                           \
-  int msm_enqueue_##SUFFIX(const void* p, const void* s, size_t n, uint32_t wr, uint32_t ww, MsmTicket* tk) {           \
-    return msm_enqueue_t<FIELD, BITS>(CURVE, GROUP, p, s, n, wr, ww, tk);                                               \
+  int msm_need_##SUFFIX(size_t n, uint32_t wr, uint32_t ww, size_t* need) { return msm_need_t<FIELD, BITS>(n, wr, ww, need); } \
+  int msm_phase1_##SUFFIX(const void* p, const void* s, size_t n, uint32_t wr, uint32_t ww, MsmTicket* tk) {            \
+    return msm_phase1_t<FIELD, BITS>(CURVE, GROUP, p, s, n, wr, ww, tk);                                                \
   }                                                                                                                      \
+  int msm_phase2_##SUFFIX(MsmTicket* tk, void* stream) { return msm_phase2_t<FIELD, BITS>(tk, (cudaStream_t)stream); }  \
   int points_conv_##SUFFIX(int to, size_t n, void* p) { return points_conv_run<FIELD>(to != 0, n, p); }                 \
   int batch_mul_##SUFFIX(const void* b, int single, const void* s, size_t n, void* o) {                                 \
     return batch_mul_run<FIELD>(b, single, s, n, o);                                                                    \

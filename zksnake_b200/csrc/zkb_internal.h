@@ -31,6 +31,7 @@ int cuda_fail(int cuda_err, const char* what, const char* file, int line);
   } while (0)
 
 void* ctx_stream();                 // cudaStream_t
+void* ctx_side_stream(int i);       // cudaStream_t, i < 8 (created on first use); nullptr on failure
 bool ctx_ready();
 // grow-only device scratch arena; `scratch_reset` starts a new allocation epoch (pointers from the previous epoch die)
 int scratch_reserve(size_t bytes);  // make sure the arena holds at least `bytes` (may reallocate; sync)
@@ -75,12 +76,23 @@ struct MsmTicket {
   unsigned char* host = nullptr;   // pinned
   size_t host_cap = 0;
   void* event = nullptr;           // cudaEvent_t
+  alignas(16) unsigned char dev[512];   // MsmDev<X>: plan + device pointers between phase 1 and phase 2
 };
 int ticket_reserve(MsmTicket* tk, size_t bytes);
 void ticket_release(MsmTicket* tk);
 // wrank/wworld: window shard handled by this call (0/1 = the whole MSM); the result is then the partial sum over those windows
+struct MsmJob {
+  int group;
+  const void* points;
+  const void* scalars;
+  size_t n;
+};
+// One MSM, both phases on the library stream.
 int msm_enqueue(int curve, int group, const void* d_points, const void* d_scalars, size_t n, uint32_t wrank, uint32_t wworld,
                 MsmTicket* tk);
+// A batch: phase 1 (sort + accumulate) of every job back to back on the library stream, then all phase 2s (the latency-bound
+// folds / bucket reductions) concurrently on side streams, joined back into the library stream.
+int msm_enqueue_batch(int curve, const MsmJob* jobs, int njobs, uint32_t wrank, uint32_t wworld, MsmTicket* tickets);
 int msm_finish(MsmTicket* tk, uint64_t* out_xy, int* out_inf);
 int msm_dev(int curve, int group, const void* d_points, const void* d_scalars, size_t n, uint64_t* out_xy, int* out_inf);
 int points_to_mont_dev(int curve, int group, size_t n, void* d_points);

@@ -98,6 +98,11 @@ class PointVector:
     def __len__(self):
         return self.n
 
+    def prefix(self, n):
+        """The first n points as a view sharing this vector's device buffer (no copy)."""
+        assert 0 <= n <= self.n
+        return PointVector(self.curve, self.group, n, buf=self.buf)
+
     def download(self):
         """-> uint64 array (n, affine_bytes/8), canonical coordinates (all-zero row = identity)."""
         out = np.zeros((self.n, self.affine_bytes // 8), dtype=np.uint64)

@@ -107,6 +107,13 @@ if __name__ == "__main__":
                 time_ntt(0, ln)
         os.environ["ZKB_NTT_MAXK"] = "10"
         time_ntt(1, 20)
+    if what == "msmx":
+        time_msm(1, 1, 20)
+        time_msm(1, 1, 22, tunings=((0, 0, 0), (15, 32, 3), (16, 32, 3), (17, 32, 3)))
+        time_msm(1, 2, 20)
+        time_msm(1, 2, 22, reps=2)
+        time_msm(0, 1, 24, reps=2, tunings=((0, 0, 0), (18, 32, 3), (19, 32, 3)))
+        time_msm(0, 1, 26, reps=2, tunings=((0, 0, 0), (20, 32, 3), (19, 32, 3)))
     if what == "msm1":
         time_msm(0, 1, 20, reps=1)
     if what in ("msm", "all"):

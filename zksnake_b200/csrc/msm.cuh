@@ -29,7 +29,7 @@ namespace zkb {
 #define ZKB_MSM_MAXLEV 8
 #define ZKB_MSM_MAXJOBS 96     // plain-sum jobs per window: <= 8 parts per level of U sums + <= 16 bit sums + R_top
 #define ZKB_MSM_MAXPARTS 8
-#define ZKB_MSM_HOT 4u         // buckets with more pieces are folded by a warp
+#define ZKB_MSM_HOT 6u         // buckets with more pieces are folded by a warp
 #define ZKB_MSM_VHOT 2048u     // ... by 64 CTAs
 #define ZKB_MSM_VHOT_SPLIT 64u
 struct MsmPlan {
@@ -63,19 +63,32 @@ __device__ __forceinline__ void load_scalar(const uint32_t* p, uint32_t* s) {
 }
 
 // pass 1: histogram of (window, bucket).  The signed digits are produced by walking the windows with a carry.
+// Window 0 and the top two windows are where skewed inputs pile up (0/1 or small witnesses live in window 0; when the top
+// window only holds the final carry, ~half of all scalars share its bucket 1 -- BLS12-381 with c = 15), so there the atomics
+// are warp-aggregated: one atomicAdd per distinct bucket per warp instead of up to 2^20 on one address.
 static __global__ void msm_count_kernel(MsmPlan pl, const uint32_t* __restrict__ scalars, uint32_t* __restrict__ cnt) {
   unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-  if (i >= pl.n) return;
+  const bool live = i < pl.n;
   uint32_t s[8];
-  load_scalar(scalars + i * 8, s);
+  if (live) load_scalar(scalars + i * 8, s);
+  else { for (int j = 0; j < 8; j++) s[j] = 0; }
   uint32_t carry = 0;
   const uint32_t half = 1u << (pl.c - 1);
+  const uint32_t lane = threadIdx.x & 31;
   const uint32_t wend = pl.win0 + pl.nwin;
   for (uint32_t w = 0; w < wend; w++) {   // the carry has to be walked up from window 0 even when win0 > 0
     uint32_t d = scalar_bits(s, w * pl.c, pl.c) + carry;
     carry = d > half;
     uint32_t mag = carry ? ((1u << pl.c) - d) : d;
-    if (mag && w >= pl.win0) atomicAdd(&cnt[(w - pl.win0) * pl.nbuck + mag - 1], 1u);
+    if (w < pl.win0) continue;   // warp-uniform
+    const bool have = live && mag != 0;
+    const uint32_t key = (w - pl.win0) * pl.nbuck + mag - 1;
+    if (w == 0 || w + 2 >= pl.nwin_total) {
+      uint32_t peers = __match_any_sync(0xffffffffu, have ? key : 0xffffffffu);
+      if (have && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&cnt[key], (uint32_t)__popc(peers));
+    } else if (have) {
+      atomicAdd(&cnt[key], 1u);
+    }
   }
 }
 

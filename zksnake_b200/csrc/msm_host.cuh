@@ -54,7 +54,11 @@ inline MsmPlan msm_make_plan(size_t n, uint32_t scalar_bits, uint32_t wrank, uin
   pl.win0 = pl.nwin_total * wrank / wworld;
   pl.nwin = pl.nwin_total * (wrank + 1) / wworld - pl.win0;
   pl.nbuck = 1u << (pl.c - 1);
-  pl.krun = g_msm_seg ? (uint32_t)g_msm_seg : 32u;
+  // run length: a bucket with r references is cut into ~r/K + 1 pieces, and more than ZKB_MSM_HOT pieces send it to the
+  // (lane-inefficient) warp fold -- keep the typical bucket at <= 3 pieces
+  pl.krun = 32u;
+  while (pl.krun < 256u && n / pl.nbuck > 2 * (size_t)pl.krun) pl.krun *= 2;
+  if (g_msm_seg) pl.krun = (uint32_t)g_msm_seg;
   uint32_t maxlog = g_msm_kchunk ? (uint32_t)g_msm_kchunk : 3u;   // log2 of the reduction radix
   if (maxlog < 1) maxlog = 1;
   if (maxlog > 5) maxlog = 5;

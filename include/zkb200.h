@@ -114,6 +114,20 @@ int zkb_batch_mul_dev(int curve, int group, const void* d_bases, int single_base
                       void* d_out);
 void zkb_msm_set_tuning(int window_bits, int segment, int reduce_chunk);  /* 0 = heuristic */
 
+/* Fixed-base tables: when the same points are used by many MSMs (a proving key, a KZG SRS -- the reference rebuilds nothing
+ * either: python/zksnake/groth16/protocol.py:133-155 and commitment/polynomial/kzg.py:32-37 pass the same key vectors to every
+ * multiexp), table[w * n + i] = 2^(c w) * P_i is computed once (W * n affine points in HBM; 0.9 GiB for 2^20 BN254 G1 points).
+ * Window w of scalar i then gathers its own pre-multiplied point, so ALL windows share ONE set of 2^(c-1) buckets: the bucket
+ * reduction shrinks W-fold and the window can be larger (fewer windows, fewer additions).  window_bits 0 = cost model for
+ * `world` window-sharding ranks.  zkb_msm_table_dev covers the first n_scalars <= n points (ZKB_ERR_MISMATCH beyond). */
+typedef struct zkb_msm_table zkb_msm_table;
+int zkb_msm_table_create(int curve, int group, const void* d_pts, size_t n, uint32_t window_bits, uint32_t world,
+                         zkb_msm_table** out);
+void zkb_msm_table_free(zkb_msm_table* t);
+int zkb_msm_table_info(const zkb_msm_table* t, uint32_t* window_bits, uint32_t* windows, size_t* bytes);
+int zkb_msm_table_dev(zkb_msm_table* t, const void* d_scalars, size_t n_scalars, uint32_t wrank, uint32_t wworld,
+                      uint64_t* out_xy, int* out_inf);
+
 /* ---- Groth16 ---------------------------------------------------------------------------------------------- */
 /* a, b, c: the vectors A.w, B.w, C.w (n = 2^log_n each).  u, v, w, h receive n coefficients each (h[n-1] = 0).
  * Returns ZKB_ERR_NOT_DIVISIBLE when a[i]*b[i] != c[i] somewhere (the reference's non-zero remainder). */
@@ -140,6 +154,8 @@ void zkb_groth16_pk_free(zkb_groth16_pk* pk);
  * zkb_groth16_partial covers only window shard `rank` of `world`.  Scales better than point slices (the digit sort and the
  * bucket reduction shrink too); costs the whole key per GPU (320 MiB at 2^20 BN254). */
 int zkb_groth16_pk_set_window_shard(zkb_groth16_pk* pk, uint32_t rank, uint32_t world);
+/* Build fixed-base tables for the key's four point vectors (see zkb_msm_table_create); every later prove uses them. */
+int zkb_groth16_pk_build_tables(zkb_groth16_pk* pk, uint32_t world);
 /* Groth16.prove from host buffers: a, b, c = A.w, B.w, C.w (n each), priv = private witness (n_kdelta scalars), r, s = the
  * prover's randomness.  Outputs canonical affine A (G1), B (G2), C (G1) and their infinity flags.  The timed e2e region of
  * bench.py is exactly one call of this function. */

@@ -328,3 +328,67 @@ def test_msm_window_shards_add_up(gpu, curve, world):
     assert acc == G.mul(G.gen, e)
     for b in (d_k, d_s, d_gen, d_pts):
         b.free()
+
+
+@pytest.mark.parametrize("curve", CURVES)
+@pytest.mark.parametrize("g2", [False, True])
+def test_msm_fixed_base_table(gpu, curve, g2):
+    """zkb_msm_table_*: table[w*n+i] = 2^(c w) P_i, one bucket set for all windows.  Must equal the discrete-log closed form for
+    the full vector, a prefix (n_scalars < n), window shards, skewed scalars (all equal -> one hot bucket; 0/1/2), and report a
+    mismatch beyond the table."""
+    nat = gpu
+    G = group(curve, g2)
+    grp = 2 if g2 else 1
+    n = 5000 if g2 else 20000
+    rng = np.random.Generator(np.random.PCG64(4242 + curve))
+    k = rng.integers(0, 2 ** 63, size=(n, 4), dtype=np.uint64)
+    k[:, 3] &= np.uint64((1 << 59) - 1)
+    ab = nat.lib.zkb_affine_bytes(curve, grp)
+    d_k = nat.DeviceBuffer(n * 32).upload(k)
+    d_gen = nat.DeviceBuffer(ab)
+    gen = pts_pack(G, [G.gen])
+    nat.check(nat.lib.zkb_points_upload(curve, grp, nat.ptr(gen), 1, d_gen.ptr))
+    d_pts = nat.DeviceBuffer(n * ab)
+    nat.check(nat.lib.zkb_batch_mul_dev(curve, grp, d_gen.ptr, 1, d_k.ptr, n, d_pts.ptr))
+    tab = ctypes.c_void_p()
+    nat.check(nat.lib.zkb_msm_table_create(curve, grp, d_pts.ptr, n, 0, 1, ctypes.byref(tab)))
+    cbits, W, nbytes = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_size_t()
+    nat.check(nat.lib.zkb_msm_table_info(tab, ctypes.byref(cbits), ctypes.byref(W), ctypes.byref(nbytes)))
+    assert nbytes.value == W.value * n * ab and 3 <= cbits.value <= 22
+    ks = nat.limbs_to_ints(k)
+
+    def run(s, count, rank=0, world=1):
+        d_s = nat.DeviceBuffer(max(count, 1) * 32).upload(s[:max(count, 1)])
+        out = np.zeros(ab // 8, dtype=np.uint64)
+        inf = ctypes.c_int(0)
+        nat.check(nat.lib.zkb_msm_table_dev(tab, d_s.ptr, count, rank, world, nat.ptr(out), ctypes.byref(inf)))
+        d_s.free()
+        return pt_unpack(G, out, inf.value)
+
+    def want(s, count):
+        ss = nat.limbs_to_ints(s[:count]) if count else []
+        return G.mul(G.gen, sum(a * b for a, b in zip(ks, ss)) % G.r)
+
+    uni = rng.integers(0, 2 ** 64, size=(n, 4), dtype=np.uint64)
+    uni[:, 3] &= np.uint64((1 << 60) - 1)
+    assert run(uni, n) == want(uni, n)
+    assert run(uni, n - 777) == want(uni, n - 777)          # prefix of the table
+    assert run(uni, 1) == want(uni, 1)
+    assert run(uni, 0) is None
+    acc = None
+    for rank in range(3):                                    # window shards add up
+        acc = G.add(acc, run(uni, n, rank, 3))
+    assert acc == want(uni, n)
+    same = np.tile(np.array([[0x123456789abcdef1, 0x0fedcba987654321, 0x1111111122222222, 0x0333333344444444]],
+                            dtype=np.uint64), (n, 1))
+    assert run(same, n) == want(same, n)
+    bits = np.zeros((n, 4), dtype=np.uint64)
+    bits[:, 0] = rng.integers(0, 3, size=n, dtype=np.uint64)
+    assert run(bits, n) == want(bits, n)
+    with pytest.raises(ValueError, match="mismatch"):
+        d_s = nat.DeviceBuffer((n + 1) * 32)
+        nat.check(nat.lib.zkb_msm_table_dev(tab, d_s.ptr, n + 1, 0, 1, nat.ptr(np.zeros(ab // 8, dtype=np.uint64)),
+                                            ctypes.byref(ctypes.c_int())))
+    nat.lib.zkb_msm_table_free(tab)
+    for b in (d_k, d_gen, d_pts):
+        b.free()

@@ -107,6 +107,34 @@ if __name__ == "__main__":
                 time_ntt(0, ln)
         os.environ["ZKB_NTT_MAXK"] = "10"
         time_ntt(1, 20)
+    if what == "table":
+        for curve, grp, ln in ((0, 1, 20), (0, 2, 20), (1, 1, 20)):
+            n = 1 << ln
+            ab = nat.lib.zkb_affine_bytes(curve, grp)
+            d_pts = make_points(curve, grp, n, 1)
+            d_s = nat.DeviceBuffer(n * 32).upload(rand_fr(n, 2, curve))
+            out = np.zeros(ab // 8, dtype=np.uint64)
+            inf = ctypes.c_int()
+            for cb in (0, 16, 17, 18, 19, 20):
+                tab = ctypes.c_void_p()
+                t0 = time.time()
+                nat.check(nat.lib.zkb_msm_table_create(curve, grp, d_pts.ptr, n, cb, 1, ctypes.byref(tab)))
+                nat.check(nat.lib.zkb_sync())
+                tb = time.time() - t0
+                c_, W_, by_ = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_size_t()
+                nat.lib.zkb_msm_table_info(tab, ctypes.byref(c_), ctypes.byref(W_), ctypes.byref(by_))
+                nat.check(nat.lib.zkb_msm_table_dev(tab, d_s.ptr, n, 0, 1, nat.ptr(out), ctypes.byref(inf)))
+                with nat.Timer() as t:
+                    for _ in range(3):
+                        nat.check(nat.lib.zkb_msm_table_dev(tab, d_s.ptr, n, 0, 1, nat.ptr(out), ctypes.byref(inf)))
+                nat.check(nat.lib.zkb_prof_enable(1))
+                nat.check(nat.lib.zkb_msm_table_dev(tab, d_s.ptr, n, 0, 1, nat.ptr(out), ctypes.byref(inf)))
+                pr = nat.prof_read()
+                nat.check(nat.lib.zkb_prof_enable(0))
+                print(f"table msm curve={curve} g{grp} 2^{ln} c={c_.value} W={W_.value} table={by_.value/2**20:.0f} MiB build={tb:.2f}s: "
+                      f"{t.ms/3:8.3f} ms {n/(t.ms/3)/1e3:8.1f} Mpts/s  " + " ".join(f"{k}={v[0]:.3f}" for k, v in pr.items() if v[1]), flush=True)
+                nat.lib.zkb_msm_table_free(tab)
+            d_pts.free(); d_s.free()
     if what == "msmx":
         time_msm(1, 1, 20)
         time_msm(1, 1, 22, tunings=((0, 0, 0), (15, 32, 3), (16, 32, 3), (17, 32, 3)))

@@ -2,6 +2,7 @@
 // prover object, self-test hooks).  Reference call sites are cited in the header.
 #include <cuda_runtime.h>
 #include <string.h>
+#include <thread>
 #include <vector>
 #include "../../include/zkb200.h"
 #include "ec.cuh"
@@ -153,7 +154,65 @@ int zkb_msm_dev_windows(int curve, int group, const void* d_pts, const void* d_s
   CHECK_CURVE(curve);
   CHECK_GROUP(group);
   static MsmTicket tk;
-  int rc = msm_enqueue(curve, group, d_pts, d_scalars, n, wrank, wworld, &tk);
+  MsmJob job = {group, d_pts, d_scalars, n, 0, 0};
+  int rc = msm_enqueue(curve, job, wrank, wworld, &tk);
+  if (rc) return rc;
+  return msm_finish(&tk, out_xy, out_inf);
+}
+
+// ---- fixed-base tables --------------------------------------------------------------------------------------------------
+struct zkb_msm_table {
+  int curve, group;
+  size_t n;
+  uint32_t c, W;
+  void* d_table;   // W * n affine points: table[w * n + i] = 2^(c w) * P_i
+};
+
+int zkb_msm_table_create(int curve, int group, const void* d_pts, size_t n, uint32_t window_bits, uint32_t world,
+                         zkb_msm_table** out) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  CHECK_GROUP(group);
+  uint32_t c = window_bits, W = 0;
+  int rc;
+  if ((rc = msm_table_build(curve, group, d_pts, n, world, &c, &W, nullptr))) return rc;
+  zkb_msm_table* t = new zkb_msm_table{curve, group, n, c, W, nullptr};
+  cudaError_t e = cudaMalloc(&t->d_table, (size_t)W * n * affine_bytes(curve, group));
+  if (e != cudaSuccess) {
+    delete t;
+    return cuda_fail((int)e, "msm table allocation", __FILE__, __LINE__);
+  }
+  if ((rc = msm_table_build(curve, group, d_pts, n, world, &c, &W, t->d_table))) {
+    cudaFree(t->d_table);
+    delete t;
+    return rc;
+  }
+  *out = t;
+  return ZKB_OK;
+}
+void zkb_msm_table_free(zkb_msm_table* t) {
+  if (!t) return;
+  if (ctx_ready()) {
+    cudaStreamSynchronize(S());
+    cudaFree(t->d_table);
+  }
+  delete t;
+}
+int zkb_msm_table_info(const zkb_msm_table* t, uint32_t* window_bits, uint32_t* windows, size_t* bytes) {
+  if (!t) return set_error(ZKB_ERR_ARG, "null table");
+  if (window_bits) *window_bits = t->c;
+  if (windows) *windows = t->W;
+  if (bytes) *bytes = (size_t)t->W * t->n * affine_bytes(t->curve, t->group);
+  return ZKB_OK;
+}
+int zkb_msm_table_dev(zkb_msm_table* t, const void* d_scalars, size_t n_scalars, uint32_t wrank, uint32_t wworld,
+                      uint64_t* out_xy, int* out_inf) {
+  NEED_INIT();
+  if (!t) return set_error(ZKB_ERR_ARG, "null table");
+  if (n_scalars > t->n) return set_error(ZKB_ERR_MISMATCH, "Number of points and scalars mismatch");
+  static MsmTicket tk;
+  MsmJob job = {t->group, t->d_table, d_scalars, n_scalars, t->c, t->n};
+  int rc = msm_enqueue(t->curve, job, wrank, wworld, &tk);
   if (rc) return rc;
   return msm_finish(&tk, out_xy, out_inf);
 }
@@ -236,6 +295,7 @@ struct zkb_groth16_pk {
   size_t n, n_kdelta;
   size_t off, len, koff, klen;  // this rank's slice of the n-point vectors / of the n_kdelta-point vector
   uint32_t wrank, wworld;       // window shard of every MSM (0/1 = all windows)
+  zkb_msm_table* tab[4];        // optional fixed-base tables of tau1, tau2, target1, kdelta1 (over this key's slices)
   const void *tau1, *tau2, *target1, *kdelta1;
   uint64_t alpha1[12], beta1[12], beta2[24], delta1[12], delta2[24];
   char* work;  // a, b, c, u, v, w, h (n each) + priv (n_kdelta)
@@ -293,11 +353,27 @@ int zkb_groth16_pk_create(int curve, uint32_t log_n, const void* d_tau1, const v
 
 void zkb_groth16_pk_free(zkb_groth16_pk* pk) {
   if (!pk) return;
+  for (int i = 0; i < 4; i++) zkb_msm_table_free(pk->tab[i]);
   if (ctx_ready()) {
     cudaStreamSynchronize(S());
     cudaFree(pk->work);
   }
   delete pk;
+}
+
+int zkb_groth16_pk_build_tables(zkb_groth16_pk* pk, uint32_t world) {
+  NEED_INIT();
+  if (!pk) return set_error(ZKB_ERR_ARG, "null proving key");
+  const void* vec[4] = {pk->tau1, pk->tau2, pk->target1, pk->kdelta1};
+  const size_t cnt[4] = {pk->len, pk->len, pk->len, pk->klen};
+  const int grp[4] = {1, 2, 1, 1};
+  for (int i = 0; i < 4; i++) {
+    if (pk->tab[i] || cnt[i] == 0) continue;
+    int rc = zkb_msm_table_create(pk->curve, grp[i], vec[i], cnt[i], 0, world ? world : 1, &pk->tab[i]);
+    if (rc) return rc;
+  }
+  ZKB_CUDA(cudaStreamSynchronize(S()));
+  return ZKB_OK;
 }
 
 int zkb_groth16_pk_set_window_shard(zkb_groth16_pk* pk, uint32_t rank, uint32_t world) {
@@ -324,15 +400,26 @@ static int groth16_msms(zkb_groth16_pk* pk, const void* d_priv) {
   // addition is ~40 dependent Fq products) and so hides behind the four G1 accumulations.
   static MsmTicket tk[5];
   static const int slot[5] = {2, 0, 1, 3, 4};   // batch position -> index in msm_xy (A, B1, B2, HZ, KW)
-  MsmJob job[5] = {{2, pk->tau2, d_v, pk->len},
-                   {1, pk->tau1, d_u, pk->len},
-                   {1, pk->tau1, d_v, pk->len},
-                   {1, pk->target1, d_h, pk->len},
-                   {1, pk->kdelta1, (const char*)d_priv + pk->koff * 32, pk->klen}};
+  auto mk = [&](int group, int which, const void* pts, const void* sc, size_t n) {
+    const zkb_msm_table* t = pk->tab[which];
+    if (t) return MsmJob{group, t->d_table, sc, n, t->c, t->n};
+    return MsmJob{group, pts, sc, n, 0, 0};
+  };
+  MsmJob job[5] = {mk(2, 1, pk->tau2, d_v, pk->len), mk(1, 0, pk->tau1, d_u, pk->len), mk(1, 0, pk->tau1, d_v, pk->len),
+                   mk(1, 2, pk->target1, d_h, pk->len),
+                   mk(1, 3, pk->kdelta1, (const char*)d_priv + pk->koff * 32, pk->klen)};
   int rc;
   if ((rc = msm_enqueue_batch(curve, job, 5, pk->wrank, pk->wworld, tk))) return rc;
+  // the five host recombinations (~0.1-0.2 ms of 64-bit Montgomery arithmetic each) run on five host threads; each waits
+  // for its own ticket's event, so they also overlap the reductions still running on the GPU
+  int rcs[5] = {0, 0, 0, 0, 0};
+  std::thread th[4];
+  for (int i = 1; i < 5; i++)
+    th[i - 1] = std::thread([&, i]() { rcs[i] = msm_finish(&tk[i], pk->msm_xy[slot[i]], &pk->msm_inf[slot[i]]); });
+  rcs[0] = msm_finish(&tk[0], pk->msm_xy[slot[0]], &pk->msm_inf[slot[0]]);
+  for (int i = 0; i < 4; i++) th[i].join();
   for (int i = 0; i < 5; i++)
-    if ((rc = msm_finish(&tk[i], pk->msm_xy[slot[i]], &pk->msm_inf[slot[i]]))) return rc;
+    if (rcs[i]) return set_error(rcs[i], "msm_finish failed in the Groth16 MSM batch");
   return ZKB_OK;
 }
 
@@ -360,12 +447,13 @@ int zkb_groth16_assemble(zkb_groth16_pk* pk, const uint64_t* msm_xy, const int* 
     const uint64_t* sc[3] = {nullptr, nullptr, s};
     host_lincomb(curve, 1, 3, pts, infs, sc, B1, &infB1);
   }
-  {
+  // B (G2, the slowest of the four linear combinations) on its own host thread while A, B1 and C are computed here
+  std::thread th_b2([&]() {
     const uint64_t* pts[3] = {mx[2], pk->beta2, pk->delta2};
     int infs[3] = {msm_inf[2], inf_beta2, inf_d2};
     const uint64_t* sc[3] = {nullptr, nullptr, s};
     host_lincomb(curve, 2, 3, pts, infs, sc, out_b, &infB2);
-  }
+  });
   {
     // C = HZ + KW + s*A + r*B1 - (r*s)*delta1 ; the last term as (order - r*s) * delta1
     uint64_t rs[4], neg_rs[4];
@@ -386,6 +474,7 @@ int zkb_groth16_assemble(zkb_groth16_pk* pk, const uint64_t* msm_xy, const int* 
     const uint64_t* sc[5] = {nullptr, nullptr, s, r, neg_rs};
     host_lincomb(curve, 1, 5, pts, infs, sc, out_c, &infC);
   }
+  th_b2.join();
   memcpy(out_a, A, g1);
   out_inf[0] = infA;
   out_inf[1] = infB2;

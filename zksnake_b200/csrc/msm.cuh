@@ -37,6 +37,8 @@ struct MsmPlan {
   uint32_t nwin;     // windows handled by THIS launch: [win0, win0 + nwin) of the scalar's nwin_total windows
   uint32_t win0;
   uint32_t nwin_total;
+  uint32_t bwin;     // bucket sets: nwin, or 1 with a fixed-base table (every window's digits share one set of buckets)
+  uint32_t table_n;  // 0, or the point count N of the fixed-base table: window w of point i gathers table[w * N + i] = 2^(c w) P_i
   uint32_t nbuck;    // buckets per window = 2^(c-1)
   uint32_t krun;     // K: references per accumulation run
   uint32_t nlev;     // levels of the bucket reduction
@@ -82,7 +84,7 @@ static __global__ void msm_count_kernel(MsmPlan pl, const uint32_t* __restrict__
     uint32_t mag = carry ? ((1u << pl.c) - d) : d;
     if (w < pl.win0) continue;   // warp-uniform
     const bool have = live && mag != 0;
-    const uint32_t key = (w - pl.win0) * pl.nbuck + mag - 1;
+    const uint32_t key = (pl.table_n ? 0u : (w - pl.win0) * pl.nbuck) + mag - 1;
     if (w == 0 || w + 2 >= pl.nwin_total) {
       uint32_t peers = __match_any_sync(0xffffffffu, have ? key : 0xffffffffu);
       if (have && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&cnt[key], (uint32_t)__popc(peers));
@@ -111,7 +113,7 @@ static __global__ void msm_scatter_kernel(MsmPlan pl, const uint32_t* __restrict
     if (w < pl.win0) continue;   // warp-uniform
     bool have = live && mag != 0;
     // warp-aggregated atomics: lanes with the same bucket take consecutive slots from one atomicAdd
-    uint32_t key = have ? ((w - pl.win0) * pl.nbuck + mag - 1) : 0xffffffffu;
+    uint32_t key = have ? ((pl.table_n ? 0u : (w - pl.win0) * pl.nbuck) + mag - 1) : 0xffffffffu;
     uint32_t peers = __match_any_sync(0xffffffffu, key);
     if (have) {
       uint32_t leader = __ffs(peers) - 1;
@@ -119,7 +121,7 @@ static __global__ void msm_scatter_kernel(MsmPlan pl, const uint32_t* __restrict
       uint32_t base = 0;
       if (lane == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
       base = __shfl_sync(peers, base, leader);
-      refs[base + rank] = (uint32_t)i | (carry << 31);
+      refs[base + rank] = ((uint32_t)i + w * pl.table_n) | (carry << 31);
     }
   }
 }
@@ -225,7 +227,7 @@ static __global__ void msm_piece_plan_kernel(MsmPlan pl, const uint32_t* __restr
                                       uint32_t* __restrict__ run_bucket, uint32_t* __restrict__ hot_list,
                                       uint32_t* __restrict__ vhot_list, uint32_t* __restrict__ counters) {
   unsigned long long b = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-  if (b >= (unsigned long long)pl.nwin * pl.nbuck) return;
+  if (b >= (unsigned long long)pl.bwin * pl.nbuck) return;
   uint32_t n = cnt[b], st = start[b];
   uint32_t np = 0;
   if (n) {
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(128, MINB) msm_accumulate_kernel(MsmPlan pl, c
                                                                     const uint32_t* __restrict__ run_bucket,
                                                                     XYZZ<F>* __restrict__ pieces,
                                                                     unsigned int* __restrict__ work) {
-  const unsigned long long nb = (unsigned long long)pl.nwin * pl.nbuck;
+  const unsigned long long nb = (unsigned long long)pl.bwin * pl.nbuck;
   const uint32_t total = start[nb];
   const uint32_t K = pl.krun;
   const uint32_t nruns = (total + K - 1) / K;
@@ -440,7 +442,7 @@ __global__ void __launch_bounds__(128, 3) msm_level0_kernel(MsmPlan pl, const ui
   unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   const uint32_t logk = pl.logk[0];
   const uint32_t per_win = pl.nbuck >> logk;
-  if (t >= (unsigned long long)pl.nwin * per_win) return;
+  if (t >= (unsigned long long)pl.bwin * per_win) return;
   uint32_t w = (uint32_t)(t / per_win), j = (uint32_t)(t % per_win);
   unsigned long long b0 = (unsigned long long)w * pl.nbuck + ((unsigned long long)j << logk);
   XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
@@ -527,6 +529,21 @@ __global__ void points_from_mont_kernel(unsigned long long n, Affine<F>* pts) {
   p.x = from_mont(p.x);
   p.y = from_mont(p.y);
   pts[i] = p;
+}
+
+// fixed-base table: table[w * n + i] = 2^(c w) * pts[i] for w < W (affine, Montgomery; infinity stays (0,0))
+template <class F>
+__global__ void __launch_bounds__(128) msm_table_kernel(unsigned long long n, uint32_t c, uint32_t W,
+                                                        const Affine<F>* __restrict__ pts, Affine<F>* __restrict__ table) {
+  unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<F> p = pts[i];
+  table[i] = p;
+  XYZZ<F> acc = XYZZ<F>::from_affine(p);
+  for (uint32_t w = 1; w < W; w++) {
+    for (uint32_t k = 0; k < c; k++) acc = dbl(acc);
+    table[(unsigned long long)w * n + i] = to_affine(acc);
+  }
 }
 
 // out[i] = scalars[i] * bases[i or 0]  as affine Montgomery points -- replaces the per-point `g.point * Fr` loop of

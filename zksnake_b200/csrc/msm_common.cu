@@ -13,9 +13,11 @@ void msm_set_tuning(int c, int seg, int kchunk) {
 }
 
 #define DECL(SUFFIX)                                                                      \
-  int msm_need_##SUFFIX(size_t n, uint32_t wr, uint32_t ww, size_t* need);                                \
-  int msm_phase1_##SUFFIX(const void* p, const void* s, size_t n, uint32_t wr, uint32_t ww, MsmTicket* tk); \
-  int msm_phase2_##SUFFIX(MsmTicket* tk, void* stream);                                                   \
+  int msm_need_##SUFFIX(size_t n, uint32_t wr, uint32_t ww, uint32_t tc, size_t tn, size_t* need);                     \
+  int msm_phase1_##SUFFIX(const void* p, const void* s, size_t n, uint32_t wr, uint32_t ww, uint32_t tc, size_t tn,     \
+                          MsmTicket* tk);                                                                                \
+  int msm_phase2_##SUFFIX(MsmTicket* tk, void* stream);                                                                 \
+  int msm_table_##SUFFIX(const void* pts, size_t n, uint32_t world, uint32_t* c, uint32_t* W, void* table);             \
   int points_conv_##SUFFIX(int to, size_t n, void* p);                                   \
   int batch_mul_##SUFFIX(const void* b, int single, const void* s, size_t n, void* o);
 DECL(g1bn) DECL(g2bn) DECL(g1bls) DECL(g2bls)
@@ -50,25 +52,33 @@ void ticket_release(MsmTicket* tk) {
   tk->host_cap = 0;
   tk->event = nullptr;
 }
-static int msm_need(int curve, int group, size_t n, uint32_t wr, uint32_t ww, size_t* need) {
-  DISPATCH(msm_need_g1bn(n, wr, ww, need), msm_need_g2bn(n, wr, ww, need), msm_need_g1bls(n, wr, ww, need),
-           msm_need_g2bls(n, wr, ww, need))
+static int msm_need(int curve, const MsmJob& j, uint32_t wr, uint32_t ww, size_t* need) {
+  const int group = j.group;
+  DISPATCH(msm_need_g1bn(j.n, wr, ww, j.table_c, j.table_n, need), msm_need_g2bn(j.n, wr, ww, j.table_c, j.table_n, need),
+           msm_need_g1bls(j.n, wr, ww, j.table_c, j.table_n, need), msm_need_g2bls(j.n, wr, ww, j.table_c, j.table_n, need))
 }
-static int msm_phase1(int curve, int group, const void* p, const void* s, size_t n, uint32_t wr, uint32_t ww, MsmTicket* tk) {
-  DISPATCH(msm_phase1_g1bn(p, s, n, wr, ww, tk), msm_phase1_g2bn(p, s, n, wr, ww, tk), msm_phase1_g1bls(p, s, n, wr, ww, tk),
-           msm_phase1_g2bls(p, s, n, wr, ww, tk))
+static int msm_phase1(int curve, const MsmJob& j, uint32_t wr, uint32_t ww, MsmTicket* tk) {
+  const int group = j.group;
+  DISPATCH(msm_phase1_g1bn(j.points, j.scalars, j.n, wr, ww, j.table_c, j.table_n, tk),
+           msm_phase1_g2bn(j.points, j.scalars, j.n, wr, ww, j.table_c, j.table_n, tk),
+           msm_phase1_g1bls(j.points, j.scalars, j.n, wr, ww, j.table_c, j.table_n, tk),
+           msm_phase1_g2bls(j.points, j.scalars, j.n, wr, ww, j.table_c, j.table_n, tk))
+}
+int msm_table_build(int curve, int group, const void* p, size_t n, uint32_t world, uint32_t* c, uint32_t* W, void* t) {
+  DISPATCH(msm_table_g1bn(p, n, world, c, W, t), msm_table_g2bn(p, n, world, c, W, t), msm_table_g1bls(p, n, world, c, W, t),
+           msm_table_g2bls(p, n, world, c, W, t))
 }
 static int msm_phase2(MsmTicket* tk, void* stream) {
   const int curve = tk->curve, group = tk->group;
   DISPATCH(msm_phase2_g1bn(tk, stream), msm_phase2_g2bn(tk, stream), msm_phase2_g1bls(tk, stream), msm_phase2_g2bls(tk, stream))
 }
-int msm_enqueue(int curve, int group, const void* p, const void* s, size_t n, uint32_t wr, uint32_t ww, MsmTicket* tk) {
+int msm_enqueue(int curve, const MsmJob& job, uint32_t wr, uint32_t ww, MsmTicket* tk) {
   size_t need = 0;
   int rc;
-  if ((rc = msm_need(curve, group, n, wr, ww, &need))) return rc;
+  if ((rc = msm_need(curve, job, wr, ww, &need))) return rc;
   if ((rc = scratch_reserve(need))) return rc;
   scratch_reset();
-  if ((rc = msm_phase1(curve, group, p, s, n, wr, ww, tk))) return rc;
+  if ((rc = msm_phase1(curve, job, wr, ww, tk))) return rc;
   prof_begin(PROF_MSM_REDUCE);
   rc = msm_phase2(tk, ctx_stream());
   prof_end(PROF_MSM_REDUCE);
@@ -80,7 +90,7 @@ int msm_enqueue_batch(int curve, const MsmJob* jobs, int njobs, uint32_t wr, uin
   int rc;
   for (int i = 0; i < njobs; i++) {
     size_t need = 0;
-    if ((rc = msm_need(curve, jobs[i].group, jobs[i].n, wr, ww, &need))) return rc;
+    if ((rc = msm_need(curve, jobs[i], wr, ww, &need))) return rc;
     total += need;
   }
   if ((rc = scratch_reserve(total))) return rc;
@@ -91,7 +101,7 @@ int msm_enqueue_batch(int curve, const MsmJob* jobs, int njobs, uint32_t wr, uin
   // short reduction kernels borrow); join at the end so later library work is ordered after all of them
   static cudaEvent_t fork_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int i = 0; i < njobs; i++) {
-    if ((rc = msm_phase1(curve, jobs[i].group, jobs[i].points, jobs[i].scalars, jobs[i].n, wr, ww, &tickets[i]))) return rc;
+    if ((rc = msm_phase1(curve, jobs[i], wr, ww, &tickets[i]))) return rc;
     if (tickets[i].empty) continue;
     if (!fork_ev[i]) ZKB_CUDA(cudaEventCreateWithFlags(&fork_ev[i], cudaEventDisableTiming));
     cudaStream_t side = (cudaStream_t)ctx_side_stream(i);
@@ -119,7 +129,8 @@ int msm_finish(MsmTicket* tk, uint64_t* out_xy, int* out_inf) {
 }
 int msm_dev(int curve, int group, const void* p, const void* s, size_t n, uint64_t* o, int* inf) {
   static MsmTicket tk;
-  int rc = msm_enqueue(curve, group, p, s, n, 0, 1, &tk);
+  MsmJob job = {group, p, s, n, 0, 0};
+  int rc = msm_enqueue(curve, job, 0, 1, &tk);
   if (rc) return rc;
   return msm_finish(&tk, o, inf);
 }

@@ -23,41 +23,51 @@ template <> struct AccumField<Fp<FqBLS381>> { typedef Fp<InlineMul<FqBLS381>> ty
 
 // wrank/wworld: this launch handles the windows [W*wrank/wworld, W*(wrank+1)/wworld) of every scalar (multi-GPU window
 // sharding); 0/1 = all windows.
-inline MsmPlan msm_make_plan(size_t n, uint32_t scalar_bits, uint32_t wrank, uint32_t wworld) {
+// table_c / table_n: non-zero when the points come from a fixed-base table built for window size table_c over table_n points.
+inline int msm_choose_window(size_t n, uint32_t scalar_bits, uint32_t wworld, bool table) {
+  uint32_t logn = 0;
+  while (((size_t)1 << logn) < n) logn++;
+  // cost model in units of one mixed addition: every window costs n additions; every bucket ~5 (the bucket reduction is ~2.3
+  // full additions per bucket plus the piece folds); with a table there is ONE set of buckets, otherwise one per window; with
+  // window sharding the slowest rank has ceil(W / world) windows, which favours a W that divides evenly.
+  double best = 0;
+  int c = 0;
+  int lo = (int)logn - 7 < 3 ? 3 : (int)logn - 7, hi = (int)logn - (table ? 1 : 3) < 3 ? 3 : (int)logn - (table ? 1 : 3);
+  if (hi > 22) hi = 22;
+  if (lo > hi) lo = hi;
+  for (int cc = lo; cc <= hi; cc++) {
+    uint32_t W = (scalar_bits + 1 + cc - 1) / cc;
+    uint32_t per_rank = (W + wworld - 1) / wworld;
+    double buckets = 5.0 * (double)(1u << (cc - 1));
+    double cost = table ? (double)per_rank * (double)n + buckets : (double)per_rank * ((double)n + buckets);
+    if (c == 0 || cost < best) {
+      best = cost;
+      c = cc;
+    }
+  }
+  return c;
+}
+
+inline MsmPlan msm_make_plan(size_t n, uint32_t scalar_bits, uint32_t wrank, uint32_t wworld, uint32_t table_c = 0,
+                             size_t table_n = 0) {
   MsmPlan pl;
   memset(&pl, 0, sizeof(pl));
   uint32_t logn = 0;
   while (((size_t)1 << logn) < n) logn++;
-  // Window choice by a cost model in units of one mixed addition: every window costs n additions plus ~5 per bucket (the
-  // bucket reduction is ~2.3 full additions per bucket plus the piece folds); with window sharding the slowest rank has
-  // ceil(W / world) windows, which favours a W that divides evenly.
-  int c = g_msm_c;
-  if (!c) {
-    double best = 0;
-    int lo = (int)logn - 7 < 3 ? 3 : (int)logn - 7, hi = (int)logn - 3 < 3 ? 3 : (int)logn - 3;
-    if (hi > 22) hi = 22;
-    if (lo > hi) lo = hi;
-    for (int cc = lo; cc <= hi; cc++) {
-      uint32_t W = (scalar_bits + 1 + cc - 1) / cc;
-      uint32_t per_rank = (W + wworld - 1) / wworld;
-      double cost = (double)per_rank * ((double)n + 5.0 * (double)(1u << (cc - 1)));
-      if (c == 0 || cost < best) {
-        best = cost;
-        c = cc;
-      }
-    }
-  }
+  int c = table_c ? (int)table_c : (g_msm_c ? g_msm_c : msm_choose_window(n, scalar_bits, wworld, false));
   if (c < 3) c = 3;
   if (c > 22) c = 22;
   pl.c = (uint32_t)c;
   pl.nwin_total = (scalar_bits + 1 + pl.c - 1) / pl.c;
   pl.win0 = pl.nwin_total * wrank / wworld;
   pl.nwin = pl.nwin_total * (wrank + 1) / wworld - pl.win0;
+  pl.table_n = (uint32_t)table_n;
+  pl.bwin = table_n ? (pl.nwin ? 1u : 0u) : pl.nwin;
   pl.nbuck = 1u << (pl.c - 1);
   // run length: a bucket with r references is cut into ~r/K + 1 pieces, and more than ZKB_MSM_HOT pieces send it to the
   // (lane-inefficient) warp fold -- keep the typical bucket at <= 3 pieces
   pl.krun = 32u;
-  while (pl.krun < 256u && n / pl.nbuck > 2 * (size_t)pl.krun) pl.krun *= 2;
+  while (pl.krun < 256u && (table_n ? n * pl.nwin : n) / pl.nbuck > 2 * (size_t)pl.krun) pl.krun *= 2;
   if (g_msm_seg) pl.krun = (uint32_t)g_msm_seg;
   uint32_t maxlog = g_msm_kchunk ? (uint32_t)g_msm_kchunk : 3u;   // log2 of the reduction radix
   if (maxlog < 1) maxlog = 1;
@@ -95,7 +105,8 @@ struct MsmGeom {
   bool skip;   // nothing to do (n == 0, or a window shard beyond the last window)
 };
 template <class X>
-inline int msm_geometry(size_t n, uint32_t scalar_bits, uint32_t wrank, uint32_t wworld, MsmGeom<X>* g) {
+inline int msm_geometry(size_t n, uint32_t scalar_bits, uint32_t wrank, uint32_t wworld, uint32_t table_c, size_t table_n,
+                        MsmGeom<X>* g) {
   memset(g, 0, sizeof(*g));
   if (wworld == 0 || wrank >= wworld) return set_error(ZKB_ERR_ARG, "msm: bad window shard");
   if (n >= ((size_t)1 << 31)) return set_error(ZKB_ERR_ARG, "msm: more than 2^31-1 points");
@@ -103,19 +114,22 @@ inline int msm_geometry(size_t n, uint32_t scalar_bits, uint32_t wrank, uint32_t
     g->skip = true;
     return ZKB_OK;
   }
-  g->pl = msm_make_plan(n, scalar_bits, wrank, wworld);
+  if (table_n && n > table_n) return set_error(ZKB_ERR_ARG, "msm: more scalars than table points");
+  g->pl = msm_make_plan(n, scalar_bits, wrank, wworld, table_c, table_n);
   const MsmPlan& pl = g->pl;
   if (pl.nwin == 0) {   // more ranks than windows
     g->skip = true;
     return ZKB_OK;
   }
-  g->nb = (size_t)pl.nwin * pl.nbuck;
+  g->nb = (size_t)pl.bwin * pl.nbuck;
   g->nrefs = n * pl.nwin;
   if (g->nrefs >= ((size_t)1 << 32)) return set_error(ZKB_ERR_ARG, "msm: n * windows exceeds 2^32 references");
+  if (table_n && (size_t)pl.nwin_total * table_n >= ((size_t)1 << 31))
+    return set_error(ZKB_ERR_ARG, "msm: table index exceeds 31 bits");
   g->max_pieces = pl.max_runs + g->nb + 1;
   g->nparts = (g->nb + ZKB_SCAN_TILE - 1) / ZKB_SCAN_TILE + 2;
   g->max_vhot = pl.max_runs / ZKB_MSM_VHOT + 1;
-  for (uint32_t l = 0; l < pl.nlev; l++) g->lev_elems += (size_t)pl.nwin * pl.lsize[l + 1];
+  for (uint32_t l = 0; l < pl.nlev; l++) g->lev_elems += (size_t)pl.bwin * pl.lsize[l + 1];
   g->m = pl.lsize[pl.nlev];
   while ((1u << g->nbits) < g->m) g->nbits++;
   g->njobs = g->nbits + 1;
@@ -125,7 +139,7 @@ inline int msm_geometry(size_t n, uint32_t scalar_bits, uint32_t wrank, uint32_t
     g->njobs += g->parts[l];
   }
   if (g->njobs > ZKB_MSM_MAXJOBS) return set_error(ZKB_ERR_ARG, "msm: too many reduction jobs");
-  g->out_bytes = (size_t)pl.nwin * g->njobs * sizeof(X);
+  g->out_bytes = (size_t)pl.bwin * g->njobs * sizeof(X);
   g->need = (g->nb + 1) * 4 * 6 + g->nrefs * 4 + (pl.max_runs + 1) * 4 + g->nb * 4 + g->max_vhot * 4 + g->nparts * 4 +
             g->max_pieces * sizeof(X) + 2 * g->lev_elems * sizeof(X) + g->max_vhot * ZKB_MSM_VHOT_SPLIT * sizeof(X) +
             g->out_bytes + 32 * 256;
@@ -141,10 +155,10 @@ struct MsmDev {
 };
 
 template <class F, int SCALAR_BITS>
-int msm_need_t(size_t n, uint32_t wrank, uint32_t wworld, size_t* need) {
+int msm_need_t(size_t n, uint32_t wrank, uint32_t wworld, uint32_t table_c, size_t table_n, size_t* need) {
   typedef XYZZ<typename AccumField<F>::type> X;
   MsmGeom<X> g;
-  int rc = msm_geometry<X>(n, SCALAR_BITS, wrank, wworld, &g);
+  int rc = msm_geometry<X>(n, SCALAR_BITS, wrank, wworld, table_c, table_n, &g);
   *need = g.need + 4096;
   return rc;
 }
@@ -153,7 +167,7 @@ int msm_need_t(size_t n, uint32_t wrank, uint32_t wworld, size_t* need) {
 // (the caller reserved and reset once for the whole batch), so several MSMs can be between phase 1 and phase 2 at once.
 template <class F, int SCALAR_BITS>
 int msm_phase1_t(int curve, int group, const void* d_points, const void* d_scalars, size_t n, uint32_t wrank, uint32_t wworld,
-                 MsmTicket* tk) {
+                 uint32_t table_c, size_t table_n, MsmTicket* tk) {
   typedef typename AccumField<F>::type FA;   // G1: inline-multiplier twin (same layout); G2: F itself
   typedef XYZZ<FA> X;
   static_assert(sizeof(FA) == sizeof(F), "inline twin must share the layout");
@@ -162,7 +176,7 @@ int msm_phase1_t(int curve, int group, const void* d_points, const void* d_scala
   tk->group = group;
   MsmDev<X>* d = reinterpret_cast<MsmDev<X>*>(tk->dev);
   int rc;
-  if ((rc = msm_geometry<X>(n, SCALAR_BITS, wrank, wworld, &d->g))) return rc;
+  if ((rc = msm_geometry<X>(n, SCALAR_BITS, wrank, wworld, table_c, table_n, &d->g))) return rc;
   tk->empty = d->g.skip;
   if (d->g.skip) return ZKB_OK;
   const MsmGeom<X>& g = d->g;
@@ -247,10 +261,10 @@ int msm_phase2_t(MsmTicket* tk, cudaStream_t st) {
   uint32_t q = 0;
   const X* r_prev = nullptr;
   for (uint32_t l = 0; l < pl.nlev; l++) {
-    size_t outs = (size_t)pl.nwin * pl.lsize[l + 1];
+    size_t outs = (size_t)pl.bwin * pl.lsize[l + 1];
     unsigned blocks = (unsigned)((outs + 127) / 128);
     if (l == 0) msm_level0_kernel<FA><<<blocks, 128, 0, st>>>(pl, d->np_eff, d->pstart, d->pieces, d->lev_t + off, d->lev_r + off);
-    else msm_level_kernel<FA><<<blocks, 128, 0, st>>>(pl.nwin, pl.lsize[l], pl.logk[l], r_prev, d->lev_t + off, d->lev_r + off);
+    else msm_level_kernel<FA><<<blocks, 128, 0, st>>>(pl.bwin, pl.lsize[l], pl.logk[l], r_prev, d->lev_t + off, d->lev_r + off);
     uint32_t per = (pl.lsize[l + 1] + g.parts[l] - 1) / g.parts[l];
     for (uint32_t p = 0; p < g.parts[l]; p++, q++) {
       jobs.base[q] = d->lev_t + off;
@@ -269,14 +283,14 @@ int msm_phase2_t(MsmTicket* tk, cudaStream_t st) {
     jobs.count[q] = g.m;
     jobs.bit[q] = (k == g.nbits) ? -1 : (int)k;
   }
-  msm_sums_kernel<FA, SUM_THREADS><<<dim3(g.njobs, pl.nwin), SUM_THREADS, SUM_THREADS * sizeof(X), st>>>(jobs, g.njobs, d->sums);
+  msm_sums_kernel<FA, SUM_THREADS><<<dim3(g.njobs, pl.bwin), SUM_THREADS, SUM_THREADS * sizeof(X), st>>>(jobs, g.njobs, d->sums);
   count_launch(4 + (int)pl.nlev);
   ZKB_CUDA(cudaGetLastError());
   ZKB_CUDA(cudaMemcpyAsync(tk->host, d->sums, g.out_bytes, cudaMemcpyDeviceToHost, st));
   count_d2h(g.out_bytes);
   ZKB_CUDA(cudaEventRecord((cudaEvent_t)tk->event, st));
-  tk->nwin = pl.nwin;
-  tk->win0 = pl.win0;
+  tk->nwin = pl.bwin;
+  tk->win0 = pl.table_n ? 0 : pl.win0;   // table entries already carry the factor 2^(c w)
   tk->c = pl.c;
   tk->nlev = pl.nlev;
   tk->nbits = g.nbits;
@@ -284,6 +298,23 @@ int msm_phase2_t(MsmTicket* tk, cudaStream_t st) {
     tk->logk[l] = pl.logk[l];
     tk->parts[l] = l < pl.nlev ? g.parts[l] : 0;
   }
+  return ZKB_OK;
+}
+
+// Fixed-base table of the n points: chooses the window size (cost model with ONE bucket set) when *c == 0, reports W, and --
+// when `table` is non-null -- fills table[w * n + i] = 2^(c w) * pts[i] (W * n affine points).  Call once with table == nullptr
+// to size the allocation.
+template <class F, int SCALAR_BITS>
+int msm_table_run(const void* d_pts, size_t n, uint32_t world, uint32_t* c, uint32_t* W, void* d_table) {
+  if (n == 0) return set_error(ZKB_ERR_ARG, "msm table: no points");
+  if (!*c) *c = (uint32_t)msm_choose_window(n, SCALAR_BITS, world ? world : 1, true);
+  if (*c < 3 || *c > 22) return set_error(ZKB_ERR_ARG, "msm table: window size out of range");
+  *W = (SCALAR_BITS + 1 + *c - 1) / *c;
+  if ((size_t)*W * n >= ((size_t)1 << 31)) return set_error(ZKB_ERR_ARG, "msm table: W * n exceeds 31 bits");
+  if (!d_table) return ZKB_OK;
+  msm_table_kernel<F><<<(unsigned)((n + 127) / 128), 128, 0, MS()>>>(n, *c, *W, (const Affine<F>*)d_pts, (Affine<F>*)d_table);
+  count_launch();
+  ZKB_CUDA(cudaGetLastError());
   return ZKB_OK;
 }
 
@@ -310,11 +341,17 @@ int batch_mul_run(const void* d_bases, int single_base, const void* d_scalars, s
 
 // every (curve, group) translation unit exports these three with a unique suffix
 #define ZKB_MSM_INSTANTIATE(SUFFIX, FIELD, BITS, CURVE, GROUP)                                                           \
-  int msm_need_##SUFFIX(size_t n, uint32_t wr, uint32_t ww, size_t* need) { return msm_need_t<FIELD, BITS>(n, wr, ww, need); } \
-  int msm_phase1_##SUFFIX(const void* p, const void* s, size_t n, uint32_t wr, uint32_t ww, MsmTicket* tk) {            \
-    return msm_phase1_t<FIELD, BITS>(CURVE, GROUP, p, s, n, wr, ww, tk);                                                \
+  int msm_need_##SUFFIX(size_t n, uint32_t wr, uint32_t ww, uint32_t tc, size_t tn, size_t* need) {                     \
+    return msm_need_t<FIELD, BITS>(n, wr, ww, tc, tn, need);                                                            \
+  }                                                                                                                      \
+  int msm_phase1_##SUFFIX(const void* p, const void* s, size_t n, uint32_t wr, uint32_t ww, uint32_t tc, size_t tn,     \
+                          MsmTicket* tk) {                                                                               \
+    return msm_phase1_t<FIELD, BITS>(CURVE, GROUP, p, s, n, wr, ww, tc, tn, tk);                                        \
   }                                                                                                                      \
   int msm_phase2_##SUFFIX(MsmTicket* tk, void* stream) { return msm_phase2_t<FIELD, BITS>(tk, (cudaStream_t)stream); }  \
+  int msm_table_##SUFFIX(const void* pts, size_t n, uint32_t world, uint32_t* c, uint32_t* W, void* table) {            \
+    return msm_table_run<FIELD, BITS>(pts, n, world, c, W, table);                                                      \
+  }                                                                                                                      \
   int points_conv_##SUFFIX(int to, size_t n, void* p) { return points_conv_run<FIELD>(to != 0, n, p); }                 \
   int batch_mul_##SUFFIX(const void* b, int single, const void* s, size_t n, void* o) {                                 \
     return batch_mul_run<FIELD>(b, single, s, n, o);                                                                    \

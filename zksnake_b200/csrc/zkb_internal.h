@@ -83,13 +83,16 @@ void ticket_release(MsmTicket* tk);
 // wrank/wworld: window shard handled by this call (0/1 = the whole MSM); the result is then the partial sum over those windows
 struct MsmJob {
   int group;
-  const void* points;
+  const void* points;     // n affine points, or a fixed-base table (table_n != 0)
   const void* scalars;
   size_t n;
+  uint32_t table_c;       // window size the table was built for (0 = plain points)
+  size_t table_n;         // points per window of the table
 };
 // One MSM, both phases on the library stream.
-int msm_enqueue(int curve, int group, const void* d_points, const void* d_scalars, size_t n, uint32_t wrank, uint32_t wworld,
-                MsmTicket* tk);
+int msm_enqueue(int curve, const MsmJob& job, uint32_t wrank, uint32_t wworld, MsmTicket* tk);
+// fixed-base table (see msm_host.cuh:msm_table_run)
+int msm_table_build(int curve, int group, const void* d_pts, size_t n, uint32_t world, uint32_t* c, uint32_t* W, void* d_table);
 // A batch: phase 1 (sort + accumulate) of every job back to back on the library stream, then all phase 2s (the latency-bound
 // folds / bucket reductions) concurrently on side streams, joined back into the library stream.
 int msm_enqueue_batch(int curve, const MsmJob* jobs, int njobs, uint32_t wrank, uint32_t wworld, MsmTicket* tickets);

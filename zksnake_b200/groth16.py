@@ -7,6 +7,7 @@ there too (CSR), and prove() is ONE call into the C ABI (zkb_groth16_prove_witne
 randomness hook is the module-level `get_random_int`, the name the reference's harnesses monkeypatch (protocol.py:11).
 """
 import ctypes
+import os
 import random
 
 import numpy as np
@@ -71,7 +72,7 @@ class VerifyingKey:
 
 
 class Groth16:
-    def __init__(self, r1cs: R1CS, curve: str = "BN254", shard=None, shard_mode="windows"):
+    def __init__(self, r1cs: R1CS, curve: str = "BN254", shard=None, shard_mode="windows", tables=None):
         """shard = (rank, world): this process proves cooperatively with the other ranks (zksnake_b200/dist.py).  Default: the
         torch.distributed world, else (0, 1).  shard_mode "windows" (default): every rank holds the whole key and runs the
         scalar windows [W*rank/world, W*(rank+1)/world) of every MSM -- sort, accumulation and bucket reduction all shrink by
@@ -80,6 +81,9 @@ class Groth16:
         self.rank, self.world = shard if shard is not None else dist.world()
         assert shard_mode in ("windows", "points")
         self.shard_mode = shard_mode
+        # fixed-base tables for the four key vectors (zkb_msm_table_create): ~14x the key's memory, ~20 % faster MSMs.
+        # Default: on, unless ZKB_MSM_TABLES=0.
+        self.tables = (os.environ.get("ZKB_MSM_TABLES", "1") != "0") if tables is None else bool(tables)
         self.curve_name = curve
         self.curve = _CURVES[curve]
         self.ec = _EC[self.curve]
@@ -172,6 +176,8 @@ class Groth16:
         self._singles = singles
         if self.shard_mode == "windows" and self.world > 1:
             nat.check(nat.lib.zkb_groth16_pk_set_window_shard(h, self.rank, self.world))
+        if self.tables:
+            nat.check(nat.lib.zkb_groth16_pk_build_tables(h, self.world if self.shard_mode == "windows" else 1))
         n_rows = max((t[0] for arr in (self.r1cs.A, self.r1cs.B, self.r1cs.C) for t in arr.triplets), default=-1) + 1
         csr = [arr.to_csr(n_rows) for arr in (self.r1cs.A, self.r1cs.B, self.r1cs.C)]
         self._csr = csr

@@ -96,6 +96,24 @@ int zkb_fr_reduce(int curve, size_t n, uint64_t* inout);            /* arbitrary
 int zkb_fr_reduce_dev(int curve, size_t n, void* d_inout);
 int zkb_fr_powers_dev(int curve, const uint64_t base[4], const uint64_t scale[4], size_t n, void* d_out); /* scale*base^i */
 
+/* Device-resident vector primitives for the PlonK prover glue (python/zksnake/plonk/protocol.py:270-466, utils.py:42-62,
+ * src/bn254/polynomial.rs:404-489): all pointers are device Fr vectors (canonical), scalars are canonical host words (values
+ * >= r are reduced).  Asynchronous on the library stream unless they return host data. */
+int zkb_fr_axpy_dev(int curve, size_t n, const uint64_t s[4], const void* d_x, size_t nx, const void* d_y, size_t ny,
+                    void* d_out);                       /* out[i] = s*x[i] + y[i], i < n; x / y zero-extended (d_y may be null) */
+int zkb_fr_mul_powers_dev(int curve, size_t n, const uint64_t base[4], const uint64_t scale[4], const void* d_x,
+                          void* d_out);                 /* out[i] = x[i] * scale * base^i  (d_x null: x = 1) */
+int zkb_fr_inverse_dev(int curve, size_t n, const void* d_x, void* d_out);   /* batch inversion, 0 -> 0 (utils.py:42-62) */
+/* op 0: exclusive prefix product, n+1 outputs (out[0] = 1, out[n] = product of all) -- the grand-product accumulator of
+ * protocol.py:307-313.  op 1: inclusive suffix sum, n outputs (out[i] = x[i] + ... + x[n-1]). */
+int zkb_fr_scan_dev(int curve, int op, size_t n, const void* d_x, void* d_out);
+int zkb_fr_gather_dev(int curve, size_t n, const void* d_src, size_t stride, size_t offset, void* d_out);  /* src[offset + i*stride] */
+int zkb_fr_gather_index_dev(int curve, size_t n, const void* d_src, const void* d_idx_u32, void* d_out);   /* src[idx[i]] */
+int zkb_fr_eval_dev(int curve, size_t n, const void* d_coeffs, const uint64_t point[4], uint64_t out[4]);   /* sum c_i z^i (sync) */
+/* q = p / (X^d - 1) (len - d coefficients, polynomial.rs:466-489); *exact = 0 when the remainder is non-zero (sync) */
+int zkb_fr_div_vanishing_dev(int curve, size_t len, size_t d, const void* d_p, void* d_q, int* exact);
+int zkb_fr_add_sparse_dev(int curve, void* d_vec, size_t k, const uint64_t* idx, const uint64_t* vals, int subtract); /* k <= 64 */
+
 /* ---- points and MSM --------------------------------------------------------------------------------------- */
 size_t zkb_affine_bytes(int curve, int group);
 int zkb_points_upload(int curve, int group, const uint64_t* pts, size_t n, void* d_out);    /* canonical -> device Montgomery */

@@ -57,6 +57,15 @@ def _load():
         "zkb_fr_reduce": (c_int, [c_int, c_sz, c_vp]),
         "zkb_fr_reduce_dev": (c_int, [c_int, c_sz, c_vp]),
         "zkb_fr_powers_dev": (c_int, [c_int, c_vp, c_vp, c_sz, c_vp]),
+        "zkb_fr_axpy_dev": (c_int, [c_int, c_sz, c_vp, c_vp, c_sz, c_vp, c_sz, c_vp]),
+        "zkb_fr_mul_powers_dev": (c_int, [c_int, c_sz, c_vp, c_vp, c_vp, c_vp]),
+        "zkb_fr_inverse_dev": (c_int, [c_int, c_sz, c_vp, c_vp]),
+        "zkb_fr_scan_dev": (c_int, [c_int, c_int, c_sz, c_vp, c_vp]),
+        "zkb_fr_gather_dev": (c_int, [c_int, c_sz, c_vp, c_sz, c_sz, c_vp]),
+        "zkb_fr_gather_index_dev": (c_int, [c_int, c_sz, c_vp, c_vp, c_vp]),
+        "zkb_fr_eval_dev": (c_int, [c_int, c_sz, c_vp, c_vp, c_vp]),
+        "zkb_fr_div_vanishing_dev": (c_int, [c_int, c_sz, c_sz, c_vp, c_vp, ctypes.POINTER(c_int)]),
+        "zkb_fr_add_sparse_dev": (c_int, [c_int, c_vp, c_sz, c_vp, c_vp, c_int]),
         "zkb_affine_bytes": (c_sz, [c_int, c_int]),
         "zkb_points_upload": (c_int, [c_int, c_int, c_vp, c_sz, c_vp]),
         "zkb_points_download": (c_int, [c_int, c_int, c_vp, c_sz, c_vp]),

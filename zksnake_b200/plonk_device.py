@@ -1,0 +1,261 @@
+"""Device-resident PlonK prover: the same protocol, transcript, blinding order and proof bytes as `zksnake_b200.plonk.Plonk`
+(which mirrors /root/reference/python/zksnake/plonk/protocol.py:39-484 call by call over Python lists), with every vector kept
+in HBM as an `FrVec` and every step a kernel launch -- SURVEY.md section 8f rank 3.  What changes is only HOW each polynomial is
+computed, never WHICH polynomial:
+
+  * products that the reference sends through `mul_over_fft` with its padding rule (8n domain, polynomial.py:126-165) are
+    computed on the 8n domain directly -- the product polynomial is unique;
+  * the grand-product accumulator (protocol.py:302-313: batch_modinv + a Python loop) is a batch-inversion kernel, a pointwise
+    product and an exclusive prefix-product scan;
+  * divisions by X - zeta (polynomial.rs:404-438 long division) are two power scalings around a suffix-sum scan;
+  * Horner evaluations, Z(omega X), the linearisation polynomial and the quotient split are axpy / power-scaling / sparse-add
+    kernels;
+  * the 9 commitments are MSMs over a fixed-base table of the SRS with device-resident scalars (zkb_msm_table_dev).
+
+`prove()` accepts the reference's arguments (dict of public inputs, interleaved private witness list); `prove_packed()` takes
+the three wire columns as (n, 4) uint64 arrays so that a 2^20-gate proof involves no Python big-int loop at all.  Verification is
+inherited (host pairing).  `timings` holds per-round wall-clock milliseconds of the last proof."""
+import ctypes
+import time
+
+import numpy as np
+
+from . import _native as nat
+from . import plonk as _plonk
+from .frvec import FrVec
+from .plonk import K1, K2, Plonk, Proof, ProvingKey, VerifyingKey
+from .polynomial import barycentric_eval, get_evaluation_point
+from .transcript import FiatShamirTranscript
+
+
+class DevicePlonk(Plonk):
+    def __init__(self, constraints, curve="BN254"):
+        super().__init__(constraints, curve)
+        self.cid = self.E.curve.CURVE_ID
+        self.table = None      # fixed-base table of the SRS
+        self.timings = {}
+
+    # ------------------------------------------------------------------------------------------------------------ helpers
+    def _commit(self, vec, count=None):
+        """[P(tau)]G1 for the coefficient vector `vec` (first `count` coefficients)."""
+        count = vec.n if count is None else count
+        assert count <= self.srs_len, "polynomial longer than the SRS"
+        ab = nat.lib.zkb_affine_bytes(self.cid, 1)
+        out = np.zeros(ab // 8, dtype=np.uint64)
+        inf = ctypes.c_int(0)
+        nat.check(nat.lib.zkb_msm_table_dev(self.table, vec.ptr, count, 0, 1, nat.ptr(out), ctypes.byref(inf)))
+        return self.E.curve.PointG1._from_flat(out, inf.value)
+
+    def __del__(self):
+        try:
+            if self.table:
+                nat.lib.zkb_msm_table_free(self.table)
+                self.table = None
+        except Exception:
+            pass
+
+    # -------------------------------------------------------------------------------------------------------------- setup
+    def setup(self):
+        """protocol.py:39-155 with the SRS, selector / permutation polynomials and their 4n-domain evaluations left in HBM."""
+        nat.ensure_init()
+        p, cs, cid = self.order, self.constraints, self.cid
+        n = cs.length
+        assert n >= 4, "PlonK needs at least 4 gates (the blinding polynomials have up to 3 coefficients)"
+        tau = _plonk.get_random_int(p - 1)
+        self.tau = tau
+        self.srs_len = n + 6
+        # [tau^i]G1: powers on the device, then the fixed-base scalar-multiplication kernel; table for the prover's MSMs
+        powers = FrVec.powers(cid, self.srs_len, tau)
+        gen = self.E.curve.upload_points([self.E.G1()], 1)
+        self.G1_tau = self.E.curve.PointVector(cid, 1, self.srs_len)
+        nat.check(nat.lib.zkb_batch_mul_dev(cid, 1, gen.ptr, 1, powers.ptr, self.srs_len, self.G1_tau.ptr))
+        self.G2_tau = self.E.G2() * tau
+        tab = ctypes.c_void_p()
+        nat.check(nat.lib.zkb_msm_table_create(cid, 1, self.G1_tau.ptr, self.srs_len, 0, 1, ctypes.byref(tab)))
+        self.table = tab
+
+        omega = get_evaluation_point(n, 1, p)
+        self.omega = omega
+        ids = [FrVec.powers(cid, n, omega, k) for k in (1, K1, K2)]            # identity permutation values on H, k1 H, k2 H
+        all_ids = FrVec(cid, 3 * n)
+        for k in range(3):
+            nat.check(nat.lib.zkb_d2d(all_ids.at(k * n), ids[k].ptr, n * 32))
+        perm = np.asarray(cs.permutation, dtype=np.uint32)
+        d_perm = nat.DeviceBuffer(perm.nbytes).upload(perm)
+        sigma_ev = all_ids.gather_index(d_perm, 3 * n)
+        d_perm.free()
+        sel_ev_n = {k: FrVec.from_ints(cid, v) for k, v in (("L", cs.qL), ("R", cs.qR), ("O", cs.qO), ("M", cs.qM), ("C", cs.qC))}
+        selector_poly = {k: v.intt() for k, v in sel_ev_n.items()}
+        permutation_poly = [sigma_ev.copy(k * n, (k + 1) * n).intt() for k in range(3)]
+        identity_poly = [v.intt() for v in ids]
+        selector_eval = {k: q.ntt(4 * n) for k, q in selector_poly.items()}
+        tau_selector = {k: self._commit(q) for k, q in selector_poly.items()}
+        tau_permutation = [self._commit(s) for s in permutation_poly]
+        l1 = FrVec.zeros(cid, n)
+        l1.add_sparse({0: 1})
+        lagrange_evals = l1.intt().ntt(4 * n)
+        self.proving_key = ProvingKey(n, self.G1_tau, selector_poly, selector_eval, permutation_poly, identity_poly, tau_selector,
+                                      tau_permutation, lagrange_evals, self.E.name)
+        self.verifying_key = VerifyingKey(n, self.G2_tau, tau_selector, tau_permutation, self.E.name)
+        self._roots = [1, omega]    # verify() only needs omega
+        nat.check(nat.lib.zkb_sync())
+
+    # -------------------------------------------------------------------------------------------------------------- prove
+    def prove(self, public_witness: dict, private_witness: list):
+        n, cid = self.proving_key.n, self.cid
+        cols = []
+        for k in range(3):
+            col = [int(x) % self.order for x in private_witness[k::3]]
+            cols.append(nat.ints_to_limbs(col + [0] * (n - len(col))))
+        return self.prove_packed(public_witness, cols)
+
+    def prove_packed(self, public_witness: dict, wire_columns):
+        """wire_columns: three (n, 4) uint64 arrays (a, b, c wire values, canonical), host memory."""
+        assert self.proving_key, "ProvingKey has not been generated"
+        pk, p, cid = self.proving_key, self.order, self.cid
+        n, N4, N8 = pk.n, 4 * pk.n, 8 * pk.n
+        omega = self.omega
+        rnd = _plonk.get_random_int
+        sel, sel_ev, ident, sig = pk.selector_poly, pk.selector_eval, pk.identity_poly, pk.permutation_poly
+        T = {}
+        t0 = time.perf_counter()
+
+        def lap(name):
+            nonlocal t0
+            nat.check(nat.lib.zkb_sync())
+            t1 = time.perf_counter()
+            T[name] = (t1 - t0) * 1e3
+            t0 = t1
+
+        def blind(poly_n, randoms):
+            """poly + (r0 + r1 X + ...) (X^n - 1): subtract the r_i at X^i, append them at X^(n+i)."""
+            out = poly_n.copy(0, n, n=n + len(randoms))
+            out.add_sparse([(i, r) for i, r in enumerate(randoms)], subtract=True)
+            out.add_sparse([(n + i, r) for i, r in enumerate(randoms)])
+            return out
+
+        tr = FiatShamirTranscript(field=p)
+        for k in "LROMC":
+            tr.append(pk.tau_selector_poly[k])
+        for s in pk.tau_permutation_poly:
+            tr.append(s)
+        for _, v in public_witness.items():
+            tr.append(v)
+
+        # ---- round 1 ----
+        wires = [FrVec.from_limbs(cid, np.asarray(w, dtype=np.uint64)) for w in wire_columns]
+        assert all(w.n == n for w in wires)
+        pi_ev_n = FrVec.zeros(cid, n)
+        if public_witness:
+            pi_ev_n.add_sparse({k: v % p for k, v in public_witness.items()})
+        A, B, C = (blind(w.intt(), [rnd(p - 1) for _ in range(2)]) for w in wires)
+        PI = pi_ev_n.intt()
+        a_ev, b_ev, c_ev, pi_ev = (x.ntt(N4) for x in (A, B, C, PI))
+        g_ev = a_ev.mul(sel_ev["L"]).add(b_ev.mul(sel_ev["R"])).add(c_ev.mul(sel_ev["O"])) \
+            .add(a_ev.mul(b_ev).mul(sel_ev["M"])).add(sel_ev["C"]).add(pi_ev)
+        G = g_ev.intt()
+        del a_ev, b_ev, c_ev, pi_ev, g_ev
+        tau_a, tau_b, tau_c = self._commit(A), self._commit(B), self._commit(C)
+        for c in (tau_a, tau_b, tau_c):
+            tr.append(c)
+        lap("round1")
+
+        # ---- round 2 ----
+        beta, gamma = tr.get_challenge_scalar(), tr.get_challenge_scalar()
+        zr = [rnd(p - 1) for _ in range(3)]
+
+        def triple_product(parts):
+            prod = None
+            for w, s in zip((A, B, C), parts):
+                lin = s.axpy(beta, w)                     # beta * s + w
+                lin.add_sparse({0: gamma})
+                ev = lin.ntt(N4)
+                prod = ev if prod is None else prod.mul(ev)
+            return prod
+
+        nom_ev = triple_product(ident)
+        den_ev = triple_product(sig)
+        ratio = nom_ev.gather(n, 4).mul(den_ev.gather(n, 4).inverse())    # the n-domain points are every 4th of the 4n domain
+        acc = ratio.prefix_product()
+        assert acc.item(n) == 1, "Copy constraints are not satisfied"
+        Z = blind(acc.copy(0, n).intt(), zr)
+        nom_poly, den_poly = nom_ev.intt(), den_ev.intt()
+        del nom_ev, den_ev, ratio, acc
+        tau_z = self._commit(Z)
+        tr.append(tau_z)
+        lap("round2")
+
+        # ---- round 3 ----
+        alpha = tr.get_challenge_scalar()
+        Z_omega = Z.mul_powers(omega)                                      # Z(omega X)
+        z8 = Z.ntt(N8)
+        nom_Z = nom_poly.ntt(N8).mul(z8).intt()
+        den_Zw = den_poly.ntt(N8).mul(Z_omega.ntt(N8)).intt()
+        del z8, nom_poly, den_poly
+        z_minus_1 = Z.copy()
+        z_minus_1.add_sparse({0: 1}, subtract=True)
+        z1_l1 = z_minus_1.ntt(N4).mul(pk.lagrange_evals).intt()
+        numer = nom_Z.sub(den_Zw).axpy(alpha, G, n=N8)
+        numer = z1_l1.axpy(alpha * alpha % p, numer, n=N8)
+        del nom_Z, den_Zw, z1_l1, G
+        Tq, exact = numer.div_vanishing(n)
+        assert exact
+        del numer
+        b10, b11 = (rnd(p - 1) for _ in range(2))
+        T_lo = Tq.copy(0, n, n=n + 1)
+        T_lo.add_sparse({n: b10})
+        T_mid = Tq.copy(n, 2 * n, n=n + 1)
+        T_mid.add_sparse({0: b10}, subtract=True)
+        T_mid.add_sparse({n: b11})
+        T_hi = Tq.copy(2 * n, 3 * n + 6)
+        T_hi.add_sparse({0: b11}, subtract=True)
+        del Tq
+        tau_t = [self._commit(x) for x in (T_lo, T_mid, T_hi)]
+        for c in tau_t:
+            tr.append(c)
+        lap("round3")
+
+        # ---- round 4 ----
+        zeta = tr.get_challenge_scalar()
+        za, zb, zc = A.eval(zeta), B.eval(zeta), C.eval(zeta)
+        zs1, zs2, zzw = sig[0].eval(zeta), sig[1].eval(zeta), Z_omega.eval(zeta)
+        L1_zeta = barycentric_eval(n, {0: 1}, zeta, p)
+        PI_zeta = barycentric_eval(n, {k: v % p for k, v in public_witness.items()}, zeta, p) if public_witness else 0
+        Zh_zeta = (pow(zeta, n, p) - 1) % p
+        perm_id = (za + beta * zeta + gamma) * (zb + beta * K1 * zeta + gamma) * (zc + beta * K2 * zeta + gamma) % p
+        perm_sig = (za + beta * zs1 + gamma) * (zb + beta * zs2 + gamma) % p
+        a2 = alpha * alpha % p
+        L = n + 6
+        R = sel["L"].axpy(za, sel["C"], n=L)
+        R = sel["R"].axpy(zb, R, n=L)
+        R = sel["O"].axpy(zc, R, n=L)
+        R = sel["M"].axpy(za * zb % p, R, n=L)
+        R = Z.axpy((alpha * perm_id + a2 * L1_zeta) % p, R, n=L)
+        R = sig[2].axpy(-alpha * perm_sig * zzw * beta % p, R, n=L)
+        R = T_lo.axpy(-Zh_zeta % p, R, n=L)
+        R = T_mid.axpy(-Zh_zeta * pow(zeta, n, p) % p, R, n=L)
+        R = T_hi.axpy(-Zh_zeta * pow(zeta, 2 * n, p) % p, R, n=L)
+        R.add_sparse({0: (PI_zeta - alpha * perm_sig * zzw * (zc + gamma) - a2 * L1_zeta) % p})
+        for v in (za, zb, zc, zs1, zs2, zzw):
+            tr.append(v)
+        lap("round4")
+
+        # ---- round 5 ----
+        v = tr.get_challenge_scalar()
+        W = R
+        const = 0
+        for k, (poly, val) in enumerate(((A, za), (B, zb), (C, zc), (sig[0], zs1), (sig[1], zs2)), start=1):
+            vk = pow(v, k, p)
+            W = poly.axpy(vk, W, n=L)
+            const += vk * val
+        W.add_sparse({0: const % p}, subtract=True)
+        W_zeta, rem = W.div_linear(zeta, p)
+        assert rem == 0
+        zw = Z.copy()
+        zw.add_sparse({0: zzw}, subtract=True)
+        W_zeta_omega, rem = zw.div_linear(zeta * omega % p, p)
+        assert rem == 0
+        tau_w, tau_ww = self._commit(W_zeta, min(W_zeta.n, self.srs_len)), self._commit(W_zeta_omega)
+        lap("round5")
+        self.timings = T
+        return Proof(tau_a, tau_b, tau_c, tau_z, tau_t[0], tau_t[1], tau_t[2], tau_w, tau_ww, za, zb, zc, zs1, zs2, zzw)

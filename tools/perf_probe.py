@@ -100,10 +100,10 @@ if __name__ == "__main__":
     nat.ensure_init()
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("ntt", "all"):
-        for maxk in (10, 8, 7):
+        for maxk in (11, 10, 8):
             os.environ["ZKB_NTT_MAXK"] = str(maxk)
             print("ZKB_NTT_MAXK", maxk)
-            for ln in (16, 20, 22, 24):
+            for ln in (16, 20, 21, 22, 23, 24):
                 time_ntt(0, ln)
         os.environ["ZKB_NTT_MAXK"] = "10"
         time_ntt(1, 20)

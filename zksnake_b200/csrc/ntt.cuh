@@ -14,8 +14,10 @@
 //   the digit-reversed, i.e. natural, order -- again C*32-byte contiguous segments.
 // Data is kept in CANONICAL form in HBM; twiddles are in Montgomery form, so mont_mul(data, twiddle) is again
 // canonical and no conversion pass exists.  Inter-pass / coset twiddles w^e come from a two-level table
-// (w^e = HI[e >> h] * LO[e & (2^h-1)], 2 x 2^h x 32 B, L1/L2 resident) instead of an N-entry table, which
-// would add 32 B/element of HBM traffic per pass.
+// (w^e = HI[e >> h] * LO[e & (2^h-1)], 2 x 2^h x 32 B, L1/L2 resident) for the coset / scaled tables; the plain twiddle
+// tables w^e and w^-e are DIRECT (N entries, one 32-byte load per twiddle) up to N = 2^23: the transform is bound by
+// Montgomery products, not by HBM, so 32 B/element/pass of extra traffic buys back one product of
+// the ~13 per element.
 //
 // Shared-memory layout: element slot x = row*C + col is split into two 16-byte planes (plane stride padded by
 // 64 B) and the slot index is XOR-swizzled so that the 8 lanes of a quarter-warp (one LDS.128/STS.128
@@ -31,6 +33,7 @@ struct PowTable {      // base^e = hi[e >> h] * lo[e & mask]   (Montgomery form;
   const F* lo;
   const F* hi;
   uint32_t h;
+  uint32_t direct;     // 1: lo holds ALL powers (h = log N, no constant factor): one load, no product
 };
 
 struct NttPass {
@@ -96,6 +99,7 @@ __device__ __forceinline__ void ntt_st(F* p, const F& v) {
 }
 template <class F>
 __device__ __forceinline__ F pow_lookup(const PowTable<F>& t, unsigned long long e) {
+  if (t.direct) return ntt_ldg(t.lo + e);
   F lo = ntt_ldg(t.lo + (e & ((1ull << t.h) - 1)));
   F hi = ntt_ldg(t.hi + (e >> t.h));
   return lo * hi;

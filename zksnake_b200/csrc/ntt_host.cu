@@ -10,6 +10,11 @@ namespace zkb {
 
 static inline cudaStream_t S() { return (cudaStream_t)ctx_stream(); }
 
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // power tables
 // ------------------------------------------------------------------------------------------------------
@@ -18,13 +23,15 @@ struct DevTable {
   F* lo = nullptr;
   F* hi = nullptr;
   uint32_t h = 0;
-  PowTable<F> view() const { PowTable<F> t; t.lo = lo; t.hi = hi; t.h = h; return t; }
+  uint32_t direct = 0;
+  PowTable<F> view() const { PowTable<F> t; t.lo = lo; t.hi = hi; t.h = h; t.direct = direct; return t; }
 };
 
 // lo[j] = base^j (j < 2^h), hi[j] = scale * base^(j 2^h) (j < 2^(log_n - h))
 template <class F>
-static int build_table(DevTable<F>& t, const F& base, const F& scale, uint32_t log_n) {
-  uint32_t h = (log_n + 1) / 2;
+static int build_table(DevTable<F>& t, const F& base, const F& scale, uint32_t log_n, bool direct = false) {
+  uint32_t h = direct ? log_n : (log_n + 1) / 2;
+  t.direct = direct ? 1 : 0;
   t.h = h;
   size_t nlo = (size_t)1 << h, nhi = (size_t)1 << (log_n - h);
   ZKB_CUDA(cudaMalloc((void**)&t.lo, nlo * sizeof(F)));
@@ -79,8 +86,9 @@ static int get_domain(uint32_t log_n, bool need_gen, Domain<F>** out) {
     F w = host_root<F>(log_n, false), wi = host_root<F>(log_n, true);
     d.n_inv = inv(host_small<F>(1ull << log_n));
     int rc;
-    if ((rc = build_table(d.fwd, w, F::one(), log_n))) return rc;
-    if ((rc = build_table(d.inv, wi, F::one(), log_n))) return rc;
+    const bool direct = log_n <= (uint32_t)env_int("ZKB_NTT_DIRECT_MAX", 23);
+    if ((rc = build_table(d.fwd, w, F::one(), log_n, direct))) return rc;
+    if ((rc = build_table(d.inv, wi, F::one(), log_n, direct))) return rc;
     if ((rc = build_table(d.inv_scaled, wi, d.n_inv, log_n))) return rc;
     it = m.emplace(log_n, d).first;
   }
@@ -112,10 +120,6 @@ static int get_domain(uint32_t log_n, bool need_gen, Domain<F>** out) {
 // ------------------------------------------------------------------------------------------------------
 // pass planning
 // ------------------------------------------------------------------------------------------------------
-static int env_int(const char* name, int dflt) {
-  const char* s = getenv(name);
-  return s ? atoi(s) : dflt;
-}
 
 struct Plan {
   std::vector<uint32_t> k;   // radix bits per pass
@@ -124,9 +128,9 @@ struct Plan {
 
 static Plan make_plan(uint32_t log_n) {
   Plan p;
-  uint32_t maxk = (uint32_t)env_int("ZKB_NTT_MAXK", 10);
+  uint32_t maxk = (uint32_t)env_int("ZKB_NTT_MAXK", 11);
   if (maxk < 3) maxk = 3;
-  if (maxk > 10) maxk = 10;
+  if (maxk > 11) maxk = 11;
   uint32_t npass = log_n <= 10 ? 1 : (log_n + maxk - 1) / maxk;
   if (npass > 4) npass = 4;
   uint32_t rem = log_n;
@@ -178,6 +182,7 @@ static int ntt_exec(const F* in, size_t in_len, F* out, uint32_t log_n, const Po
   PowTable<F> none;
   none.lo = none.hi = nullptr;
   none.h = 0;
+  none.direct = 0;
   prof_begin(PROF_NTT);
   for (uint32_t p = 0; p < P; p++) {
     NttPass pp;

@@ -46,6 +46,17 @@ class DevicePlonk(Plonk):
         nat.check(nat.lib.zkb_msm_table_dev(self.table, vec.ptr, count, 0, 1, nat.ptr(out), ctypes.byref(inf)))
         return self.E.curve.PointG1._from_flat(out, inf.value)
 
+    def _commit_many(self, vecs):
+        """several commitments as one MSM batch (zkb_msm_table_batch_dev): reductions overlap the next accumulation"""
+        k = len(vecs)
+        limbs = nat.lib.zkb_affine_bytes(self.cid, 1) // 8
+        ptrs = (ctypes.c_void_p * k)(*[v.ptr for v in vecs])
+        lens = (ctypes.c_size_t * k)(*[min(v.n, self.srs_len) for v in vecs])
+        out = np.zeros((k, limbs), dtype=np.uint64)
+        inf = (ctypes.c_int * k)()
+        nat.check(nat.lib.zkb_msm_table_batch_dev(self.table, k, ptrs, lens, nat.ptr(out), inf))
+        return [self.E.curve.PointG1._from_flat(out[i], inf[i]) for i in range(k)]
+
     def __del__(self):
         try:
             if self.table:
@@ -155,7 +166,7 @@ class DevicePlonk(Plonk):
             .add(a_ev.mul(b_ev).mul(sel_ev["M"])).add(sel_ev["C"]).add(pi_ev)
         G = g_ev.intt()
         del a_ev, b_ev, c_ev, pi_ev, g_ev
-        tau_a, tau_b, tau_c = self._commit(A), self._commit(B), self._commit(C)
+        tau_a, tau_b, tau_c = self._commit_many([A, B, C])
         for c in (tau_a, tau_b, tau_c):
             tr.append(c)
         lap("round1")
@@ -210,7 +221,7 @@ class DevicePlonk(Plonk):
         T_hi = Tq.copy(2 * n, 3 * n + 6)
         T_hi.add_sparse({0: b11}, subtract=True)
         del Tq
-        tau_t = [self._commit(x) for x in (T_lo, T_mid, T_hi)]
+        tau_t = self._commit_many([T_lo, T_mid, T_hi])
         for c in tau_t:
             tr.append(c)
         lap("round3")
@@ -255,7 +266,7 @@ class DevicePlonk(Plonk):
         zw.add_sparse({0: zzw}, subtract=True)
         W_zeta_omega, rem = zw.div_linear(zeta * omega % p, p)
         assert rem == 0
-        tau_w, tau_ww = self._commit(W_zeta, min(W_zeta.n, self.srs_len)), self._commit(W_zeta_omega)
+        tau_w, tau_ww = self._commit_many([W_zeta, W_zeta_omega])
         lap("round5")
         self.timings = T
         return Proof(tau_a, tau_b, tau_c, tau_z, tau_t[0], tau_t[1], tau_t[2], tau_w, tau_ww, za, zb, zc, zs1, zs2, zzw)

@@ -112,7 +112,7 @@ int zkb_fr_gather_index_dev(int curve, size_t n, const void* d_src, const void* 
 int zkb_fr_eval_dev(int curve, size_t n, const void* d_coeffs, const uint64_t point[4], uint64_t out[4]);   /* sum c_i z^i (sync) */
 /* q = p / (X^d - 1) (len - d coefficients, polynomial.rs:466-489); *exact = 0 when the remainder is non-zero (sync) */
 int zkb_fr_div_vanishing_dev(int curve, size_t len, size_t d, const void* d_p, void* d_q, int* exact);
-int zkb_fr_add_sparse_dev(int curve, void* d_vec, size_t k, const uint64_t* idx, const uint64_t* vals, int subtract); /* k <= 64 */
+int zkb_fr_add_sparse_dev(int curve, void* d_vec, size_t k, const uint64_t* idx, const uint64_t* vals, int subtract); /* async */
 
 /* ---- points and MSM --------------------------------------------------------------------------------------- */
 size_t zkb_affine_bytes(int curve, int group);

@@ -222,14 +222,31 @@ __global__ void div_vanishing_kernel(unsigned long long len, unsigned long long 
   }
 }
 
-// v[idx[k]] += / -= vals[k]
+// v[idx[k]] += / -= vals[k] for up to 8 entries passed BY VALUE (no staging copy, no synchronisation)
 template <class F>
-__global__ void add_sparse_kernel(uint32_t k, const unsigned long long* __restrict__ idx, const F* __restrict__ vals, int subtract,
-                                  F* v) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= k) return;
-  F a = ntt_ld(v + idx[t]), b = ntt_ld(vals + t);
-  ntt_st(v + idx[t], subtract ? a - b : a + b);
+struct SparseArgs {
+  unsigned long long idx[8];
+  F val[8];
+  uint32_t k;
+};
+template <class F>
+__global__ void add_sparse_kernel(SparseArgs<F> a, int subtract, F* v) {
+  uint32_t t = threadIdx.x;
+  if (t >= a.k) return;
+  // entries may repeat an index: serialise through thread 0 when they do (k <= 8)
+  bool dup = false;
+  for (uint32_t j = 0; j < a.k; j++)
+    for (uint32_t i = 0; i < j; i++) dup |= a.idx[i] == a.idx[j];
+  if (dup) {
+    if (t != 0) return;
+    for (uint32_t j = 0; j < a.k; j++) {
+      F x = ntt_ld(v + a.idx[j]);
+      ntt_st(v + a.idx[j], subtract ? x - a.val[j] : x + a.val[j]);
+    }
+    return;
+  }
+  F x = ntt_ld(v + a.idx[t]);
+  ntt_st(v + a.idx[t], subtract ? x - a.val[t] : x + a.val[t]);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------------
@@ -347,25 +364,20 @@ struct FrVecOps {
     return ZKB_OK;
   }
   static int add_sparse(void* v, size_t k, const uint64_t* idx, const uint64_t* vals, int subtract) {
-    if (k == 0) return ZKB_OK;
-    if (k > 64) return set_error(ZKB_ERR_ARG, "add_sparse: at most 64 entries");
-    int rc;
-    if ((rc = scratch_reserve(64 * 40 + 4096))) return rc;
-    scratch_reset();
-    unsigned long long* d_idx = (unsigned long long*)scratch_take(64 * 8);
-    F* d_val = (F*)scratch_take(64 * 32);
-    std::vector<F> hv(k);
-    for (size_t i = 0; i < k; i++) {
-      F x;
-      memcpy(x.v, vals + 4 * i, 32);
-      hv[i] = from_mont(F::r2() * x);   // reduce mod r
+    for (size_t done = 0; done < k; done += 8) {
+      SparseArgs<F> a;
+      memset(&a, 0, sizeof(a));
+      a.k = (uint32_t)(k - done < 8 ? k - done : 8);
+      for (uint32_t i = 0; i < a.k; i++) {
+        a.idx[i] = idx[done + i];
+        F x;
+        memcpy(x.v, vals + 4 * (done + i), 32);
+        a.val[i] = from_mont(F::r2() * x);   // reduce mod r
+      }
+      add_sparse_kernel<F><<<1, 32, 0, S()>>>(a, subtract, (F*)v);
+      count_launch();
     }
-    ZKB_CUDA(ZKB_H2D(d_idx, idx, k * 8));
-    ZKB_CUDA(ZKB_H2D(d_val, hv.data(), k * 32));
-    add_sparse_kernel<F><<<1, 64, 0, S()>>>((uint32_t)k, d_idx, d_val, subtract, (F*)v);
-    count_launch();
     ZKB_CUDA(cudaGetLastError());
-    ZKB_CUDA(cudaStreamSynchronize(S()));   // the staging vectors above live on this stack frame
     return ZKB_OK;
   }
 };

@@ -74,7 +74,9 @@ class FrVec:
 
     @classmethod
     def from_limbs(cls, curve, arr, reduce=True):
-        arr = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
+        if not (isinstance(arr, np.ndarray) and arr.dtype == np.uint64 and arr.flags["C_CONTIGUOUS"]):
+            arr = np.ascontiguousarray(arr, dtype=np.uint64)   # (a pinned array passes through untouched)
+        arr = arr.reshape(-1, 4)
         v = cls(curve, len(arr))
         if len(arr):
             nat.check(nat.lib.zkb_h2d(v.ptr, nat.ptr(arr), arr.nbytes))

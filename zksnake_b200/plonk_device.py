@@ -154,7 +154,7 @@ class DevicePlonk(Plonk):
             tr.append(v)
 
         # ---- round 1 ----
-        wires = [FrVec.from_limbs(cid, np.asarray(w, dtype=np.uint64)) for w in wire_columns]
+        wires = [FrVec.from_limbs(cid, w) for w in wire_columns]
         assert all(w.n == n for w in wires)
         pi_ev_n = FrVec.zeros(cid, n)
         if public_witness:

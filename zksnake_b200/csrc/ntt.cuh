@@ -15,7 +15,7 @@
 // Data is kept in CANONICAL form in HBM; twiddles are in Montgomery form, so mont_mul(data, twiddle) is again
 // canonical and no conversion pass exists.  Inter-pass / coset twiddles w^e come from a two-level table
 // (w^e = HI[e >> h] * LO[e & (2^h-1)], 2 x 2^h x 32 B, L1/L2 resident) for the coset / scaled tables; the plain twiddle
-// tables w^e and w^-e are DIRECT (N entries, one 32-byte load per twiddle) up to N = 2^23: the transform is bound by
+// tables w^e and w^-e are DIRECT (N entries, one 32-byte load per twiddle) up to N = 2^26: the transform is bound by
 // Montgomery products, not by HBM, so 32 B/element/pass of extra traffic buys back one product of
 // the ~13 per element.
 //

@@ -86,7 +86,7 @@ static int get_domain(uint32_t log_n, bool need_gen, Domain<F>** out) {
     F w = host_root<F>(log_n, false), wi = host_root<F>(log_n, true);
     d.n_inv = inv(host_small<F>(1ull << log_n));
     int rc;
-    const bool direct = log_n <= (uint32_t)env_int("ZKB_NTT_DIRECT_MAX", 23);
+    const bool direct = log_n <= (uint32_t)env_int("ZKB_NTT_DIRECT_MAX", 26);
     if ((rc = build_table(d.fwd, w, F::one(), log_n, direct))) return rc;
     if ((rc = build_table(d.inv, wi, F::one(), log_n, direct))) return rc;
     if ((rc = build_table(d.inv_scaled, wi, d.n_inv, log_n))) return rc;

@@ -13,6 +13,9 @@ using namespace zkb;
 
 struct FqBN254Inl : FqBN254 { static constexpr bool NOINLINE_MUL = false; };
 struct FqBLS381Inl : FqBLS381 { static constexpr bool NOINLINE_MUL = false; };
+struct FqBN254Split : FqBN254 { static constexpr bool NOINLINE_MUL = false; static constexpr bool SPLIT_MUL = true; };
+struct FqBN254SplitCall : FqBN254 { static constexpr bool SPLIT_MUL = true; };
+struct FqBLS381Split : FqBLS381 { static constexpr bool NOINLINE_MUL = false; static constexpr bool SPLIT_MUL = true; };
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA %s at %d\n", cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
 
@@ -292,6 +295,25 @@ int main(int argc, char** argv) {
   uint32_t* d;
   CK(cudaMalloc(&d, 4096));
   const int it = 2048;
+  if (argc > 1 && atoi(argv[1]) == 3) {
+    for (int bps : {2, 4}) {
+      bench_field<Fp<FqBN254Inl>>("FqBN254 fused inline", bps);
+      bench_field<Fp<FqBN254Split>>("FqBN254 split inline", bps);
+      bench_field<Fp<FqBN254SplitCall>>("FqBN254 split call", bps);
+    }
+    bench_field<Fp<FqBLS381Inl>>("FqBLS381 fused inline", 4);
+    bench_field<Fp<FqBLS381Split>>("FqBLS381 split inline", 4);
+    for (int bps : {3, 4}) {
+      bench_madd<Fp<FqBN254Inl>>("G1 BN254 fused inline", bps);
+      bench_madd<Fp<FqBN254Split>>("G1 BN254 split inline", bps);
+      bench_madd<Fp<FqBN254SplitCall>>("G1 BN254 split call", bps);
+    }
+    bench_madd<Fp<FqBLS381Inl>>("G1 BLS381 fused inline", 3);
+    bench_madd<Fp<FqBLS381Split>>("G1 BLS381 split inline", 3);
+    bench_madd<Fp2<FqBN254>>("G2 BN254 fused call", 2);
+    bench_madd<Fp2<FqBN254SplitCall>>("G2 BN254 split call", 2);
+    return 0;
+  }
   if (argc > 1 && atoi(argv[1]) == 2) {
     double* dd = (double*)d;
     unsigned long long* du = (unsigned long long*)d;

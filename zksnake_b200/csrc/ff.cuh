@@ -265,20 +265,34 @@ ZKB_HD Fp<P> mont_mul(const Fp<P>& A, const Fp<P>& B) {
   return r;
 }
 
+// split multiplier (ff_wide.cuh, included at the end of this file): Karatsuba product + separate reduction
+template <class P>
+ZKB_HD Fp<P> mont_mul_split(const Fp<P>& a, const Fp<P>& b);
+// a parameter struct opts in with `static constexpr bool SPLIT_MUL = true;`
+template <class P, class = void>
+struct uses_split_mul { static constexpr bool value = false; };
+template <class P>
+struct uses_split_mul<P, decltype((void)P::SPLIT_MUL)> { static constexpr bool value = P::SPLIT_MUL; };
+
 // The base fields of the curves (Fq) call the multiplier out of line on the device: a fully inlined XYZZ addition
 // would be 10-40 copies of a 300-600 instruction body, far beyond the instruction cache, and ptxas time explodes.
 // The scalar fields (Fr, one multiply per butterfly) keep it inline.
 #if defined(__CUDA_ARCH__)
 template <class P>
-__device__ __noinline__ Fp<P> mont_mul_call(Fp<P> a, Fp<P> b) { return mont_mul(a, b); }
+__device__ __noinline__ Fp<P> mont_mul_call(Fp<P> a, Fp<P> b) {
+  if constexpr (uses_split_mul<P>::value) return mont_mul_split(a, b);
+  else return mont_mul(a, b);
+}
 #endif
 template <class P>
 ZKB_HD Fp<P> operator*(const Fp<P>& a, const Fp<P>& b) {
 #if defined(__CUDA_ARCH__)
   if constexpr (P::NOINLINE_MUL) return mont_mul_call<P>(a, b);
+  else if constexpr (uses_split_mul<P>::value) return mont_mul_split(a, b);
   else return mont_mul(a, b);
 #else
-  return mont_mul(a, b);
+  if constexpr (uses_split_mul<P>::value) return mont_mul_split(a, b);
+  else return mont_mul(a, b);
 #endif
 }
 
@@ -405,3 +419,5 @@ typedef Fp2<FqBN254> fq2_bn;
 typedef Fp2<FqBLS381> fq2_bls;
 
 }  // namespace zkb
+
+#include "ff_wide.cuh"

@@ -17,13 +17,6 @@ namespace zkb {
 
 static inline cudaStream_t S() { return (cudaStream_t)ctx_stream(); }
 
-template <class F>
-__device__ __forceinline__ F raw_one() {   // the integer 1 (stands for 1/R as a Montgomery value)
-  F x = F::zero();
-  x.v[0] = 1;
-  return x;
-}
-
 // out[i] = s * x[i] + y[i]   (x, y zero-extended beyond nx, ny; s in Montgomery form)
 template <class F>
 __global__ void axpy_kernel(unsigned long long n, F s, const F* __restrict__ x, unsigned long long nx, const F* __restrict__ y,

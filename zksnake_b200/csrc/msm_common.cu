@@ -15,7 +15,7 @@ void msm_set_tuning(int c, int seg, int kchunk) {
 #define DECL(SUFFIX)                                                                      \
   int msm_need_##SUFFIX(size_t n, uint32_t wr, uint32_t ww, uint32_t tc, size_t tn, size_t* need);                     \
   int msm_phase1_##SUFFIX(const void* p, const void* s, size_t n, uint32_t wr, uint32_t ww, uint32_t tc, size_t tn,     \
-                          MsmTicket* tk);                                                                                \
+                          const MsmTicket* share, MsmTicket* tk);                                                        \
   int msm_phase2_##SUFFIX(MsmTicket* tk, void* stream);                                                                 \
   int msm_table_##SUFFIX(const void* pts, size_t n, uint32_t world, uint32_t* c, uint32_t* W, void* table);             \
   int points_conv_##SUFFIX(int to, size_t n, void* p);                                   \
@@ -57,12 +57,12 @@ static int msm_need(int curve, const MsmJob& j, uint32_t wr, uint32_t ww, size_t
   DISPATCH(msm_need_g1bn(j.n, wr, ww, j.table_c, j.table_n, need), msm_need_g2bn(j.n, wr, ww, j.table_c, j.table_n, need),
            msm_need_g1bls(j.n, wr, ww, j.table_c, j.table_n, need), msm_need_g2bls(j.n, wr, ww, j.table_c, j.table_n, need))
 }
-static int msm_phase1(int curve, const MsmJob& j, uint32_t wr, uint32_t ww, MsmTicket* tk) {
+static int msm_phase1(int curve, const MsmJob& j, uint32_t wr, uint32_t ww, const MsmTicket* share, MsmTicket* tk) {
   const int group = j.group;
-  DISPATCH(msm_phase1_g1bn(j.points, j.scalars, j.n, wr, ww, j.table_c, j.table_n, tk),
-           msm_phase1_g2bn(j.points, j.scalars, j.n, wr, ww, j.table_c, j.table_n, tk),
-           msm_phase1_g1bls(j.points, j.scalars, j.n, wr, ww, j.table_c, j.table_n, tk),
-           msm_phase1_g2bls(j.points, j.scalars, j.n, wr, ww, j.table_c, j.table_n, tk))
+  DISPATCH(msm_phase1_g1bn(j.points, j.scalars, j.n, wr, ww, j.table_c, j.table_n, share, tk),
+           msm_phase1_g2bn(j.points, j.scalars, j.n, wr, ww, j.table_c, j.table_n, share, tk),
+           msm_phase1_g1bls(j.points, j.scalars, j.n, wr, ww, j.table_c, j.table_n, share, tk),
+           msm_phase1_g2bls(j.points, j.scalars, j.n, wr, ww, j.table_c, j.table_n, share, tk))
 }
 int msm_table_build(int curve, int group, const void* p, size_t n, uint32_t world, uint32_t* c, uint32_t* W, void* t) {
   DISPATCH(msm_table_g1bn(p, n, world, c, W, t), msm_table_g2bn(p, n, world, c, W, t), msm_table_g1bls(p, n, world, c, W, t),
@@ -78,7 +78,7 @@ int msm_enqueue(int curve, const MsmJob& job, uint32_t wr, uint32_t ww, MsmTicke
   if ((rc = msm_need(curve, job, wr, ww, &need))) return rc;
   if ((rc = scratch_reserve(need))) return rc;
   scratch_reset();
-  if ((rc = msm_phase1(curve, job, wr, ww, tk))) return rc;
+  if ((rc = msm_phase1(curve, job, wr, ww, nullptr, tk))) return rc;
   prof_begin(PROF_MSM_REDUCE);
   rc = msm_phase2(tk, ctx_stream());
   prof_end(PROF_MSM_REDUCE);
@@ -101,7 +101,11 @@ int msm_enqueue_batch(int curve, const MsmJob* jobs, int njobs, uint32_t wr, uin
   // short reduction kernels borrow); join at the end so later library work is ordered after all of them
   static cudaEvent_t fork_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int i = 0; i < njobs; i++) {
-    if ((rc = msm_phase1(curve, jobs[i], wr, ww, &tickets[i]))) return rc;
+    // reuse the digit sort of an earlier job over the same scalars (phase 1 checks that the geometry matches too)
+    const MsmTicket* share = nullptr;
+    for (int j = 0; j < i && !share; j++)
+      if (!tickets[j].empty && jobs[j].scalars == jobs[i].scalars && jobs[j].n == jobs[i].n) share = &tickets[j];
+    if ((rc = msm_phase1(curve, jobs[i], wr, ww, share, &tickets[i]))) return rc;
     if (tickets[i].empty) continue;
     if (!fork_ev[i]) ZKB_CUDA(cudaEventCreateWithFlags(&fork_ev[i], cudaEventDisableTiming));
     cudaStream_t side = (cudaStream_t)ctx_side_stream(i);

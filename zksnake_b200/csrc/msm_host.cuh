@@ -167,7 +167,7 @@ int msm_need_t(size_t n, uint32_t wrank, uint32_t wworld, uint32_t table_c, size
 // (the caller reserved and reset once for the whole batch), so several MSMs can be between phase 1 and phase 2 at once.
 template <class F, int SCALAR_BITS>
 int msm_phase1_t(int curve, int group, const void* d_points, const void* d_scalars, size_t n, uint32_t wrank, uint32_t wworld,
-                 uint32_t table_c, size_t table_n, MsmTicket* tk) {
+                 uint32_t table_c, size_t table_n, const MsmTicket* share, MsmTicket* tk) {
   typedef typename AccumField<F>::type FA;   // G1: inline-multiplier twin (same layout); G2: F itself
   typedef XYZZ<FA> X;
   static_assert(sizeof(FA) == sizeof(F), "inline twin must share the layout");
@@ -183,49 +183,76 @@ int msm_phase1_t(int curve, int group, const void* d_points, const void* d_scala
   const MsmPlan& pl = g.pl;
   if ((rc = ticket_reserve(tk, g.out_bytes))) return rc;
   const size_t nb = g.nb;
-  uint32_t* cnt = (uint32_t*)scratch_take((nb + 1) * 4);
-  uint32_t* start = (uint32_t*)scratch_take((nb + 1) * 4);
-  uint32_t* cursor = (uint32_t*)scratch_take((nb + 1) * 4);
-  uint32_t* npieces = (uint32_t*)scratch_take((nb + 1) * 4);
+  // A job whose scalars, length, table geometry and window shard equal an earlier job's of the batch (Groth16: [B]_1 and [B]_2
+  // are both MSMs over V) reuses that job's digit sort: same references, bucket offsets, piece plan and hot lists.
+  const MsmSorted* sh = share ? &share->sorted : nullptr;
+  if (sh && !(sh->scalars == d_scalars && sh->n == n && sh->table_c == table_c && sh->table_n == table_n && sh->wrank == wrank &&
+              sh->wworld == wworld && sh->nb == nb && sh->krun == pl.krun))
+    sh = nullptr;
+  uint32_t *cnt = nullptr, *start, *cursor = nullptr, *npieces, *refs, *run_bucket, *part = nullptr;
   d->np_eff = (uint32_t*)scratch_take((nb + 1) * 4);
-  d->pstart = (uint32_t*)scratch_take((nb + 1) * 4);
-  uint32_t* refs = (uint32_t*)scratch_take(g.nrefs * 4);
-  uint32_t* run_bucket = (uint32_t*)scratch_take((pl.max_runs + 1) * 4);
-  d->hot_list = (uint32_t*)scratch_take(nb * 4);
-  d->vhot_list = (uint32_t*)scratch_take(g.max_vhot * 4);
-  uint32_t* part = (uint32_t*)scratch_take(g.nparts * 4);
   d->counters = (uint32_t*)scratch_take(256);   // [0] hot count, [1] accumulate work counter, [2] very hot count
+  if (sh) {
+    start = sh->start;
+    npieces = sh->npieces;
+    refs = sh->refs;
+    run_bucket = sh->run_bucket;
+    d->pstart = sh->pstart;
+    d->hot_list = sh->hot_list;
+    d->vhot_list = sh->vhot_list;
+  } else {
+    cnt = (uint32_t*)scratch_take((nb + 1) * 4);
+    start = (uint32_t*)scratch_take((nb + 1) * 4);
+    cursor = (uint32_t*)scratch_take((nb + 1) * 4);
+    npieces = (uint32_t*)scratch_take((nb + 1) * 4);
+    d->pstart = (uint32_t*)scratch_take((nb + 1) * 4);
+    refs = (uint32_t*)scratch_take(g.nrefs * 4);
+    run_bucket = (uint32_t*)scratch_take((pl.max_runs + 1) * 4);
+    d->hot_list = (uint32_t*)scratch_take(nb * 4);
+    d->vhot_list = (uint32_t*)scratch_take(g.max_vhot * 4);
+    part = (uint32_t*)scratch_take(g.nparts * 4);
+  }
   d->pieces = (X*)scratch_take(g.max_pieces * sizeof(X));
   d->lev_t = (X*)scratch_take(g.lev_elems * sizeof(X));
   d->lev_r = (X*)scratch_take(g.lev_elems * sizeof(X));
   d->side = (X*)scratch_take(g.max_vhot * ZKB_MSM_VHOT_SPLIT * sizeof(X));
   d->sums = (X*)scratch_take(g.out_bytes);
-  if (!cnt || !start || !cursor || !npieces || !d->np_eff || !d->pstart || !refs || !run_bucket || !d->hot_list || !d->vhot_list ||
-      !part || !d->counters || !d->pieces || !d->lev_t || !d->lev_r || !d->side || !d->sums)
+  if ((!sh && (!cnt || !cursor || !part)) || !start || !npieces || !d->np_eff || !d->pstart || !refs || !run_bucket ||
+      !d->hot_list || !d->vhot_list || !d->counters || !d->pieces || !d->lev_t || !d->lev_r || !d->side || !d->sums)
     return set_error(ZKB_ERR_CUDA, "msm: scratch exhausted");
 
   cudaStream_t st = MS();
   const uint32_t* sc = (const uint32_t*)d_scalars;
-  ZKB_CUDA(cudaMemsetAsync(cnt, 0, (nb + 1) * 4, st));
-  ZKB_CUDA(cudaMemsetAsync(d->counters, 0, 256, st));
-  unsigned pblocks = (unsigned)((n + 255) / 256);
-  unsigned bblocks = (unsigned)((nb + 255) / 256);
   prof_begin(PROF_MSM_SORT);
-  msm_count_kernel<<<pblocks, 256, 0, st>>>(pl, sc, cnt);
-  scan_u32(cnt, start, nb, part, st);
-  ZKB_CUDA(cudaMemcpyAsync(cursor, start, (nb + 1) * 4, cudaMemcpyDeviceToDevice, st));
-  msm_scatter_kernel<<<pblocks, 256, 0, st>>>(pl, sc, cursor, refs);
-  msm_piece_plan_kernel<<<bblocks, 256, 0, st>>>(pl, cnt, start, npieces, d->np_eff, run_bucket, d->hot_list, d->vhot_list,
-                                                 d->counters);
-  scan_u32(npieces, d->pstart, nb, part, st);
+  if (sh) {
+    // own copies of what the folds rewrite (np_eff) and of the counters (hot counts kept, work counter cleared)
+    ZKB_CUDA(cudaMemcpyAsync(d->np_eff, npieces, (nb + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    ZKB_CUDA(cudaMemcpyAsync(d->counters, sh->counters, 256, cudaMemcpyDeviceToDevice, st));
+    ZKB_CUDA(cudaMemsetAsync(d->counters + 1, 0, 4, st));
+  } else {
+    ZKB_CUDA(cudaMemsetAsync(cnt, 0, (nb + 1) * 4, st));
+    ZKB_CUDA(cudaMemsetAsync(d->counters, 0, 256, st));
+    unsigned pblocks = (unsigned)((n + 255) / 256);
+    unsigned bblocks = (unsigned)((nb + 255) / 256);
+    msm_count_kernel<<<pblocks, 256, 0, st>>>(pl, sc, cnt);
+    scan_u32(cnt, start, nb, part, st);
+    ZKB_CUDA(cudaMemcpyAsync(cursor, start, (nb + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    msm_scatter_kernel<<<pblocks, 256, 0, st>>>(pl, sc, cursor, refs);
+    msm_piece_plan_kernel<<<bblocks, 256, 0, st>>>(pl, cnt, start, npieces, d->np_eff, run_bucket, d->hot_list, d->vhot_list,
+                                                   d->counters);
+    scan_u32(npieces, d->pstart, nb, part, st);
+    count_launch(10);
+  }
   prof_end(PROF_MSM_SORT);
+  tk->sorted = MsmSorted{d_scalars, n, table_c, table_n, wrank, wworld, nb, pl.krun, start, d->pstart, npieces, refs, run_bucket,
+                         d->hot_list, d->vhot_list, d->counters};
   const int acc_tag = group == 2 ? PROF_MSM_ACCUM_G2 : PROF_MSM_ACCUM_G1;
   prof_begin(acc_tag);
   constexpr int MINB = AccumField<F>::MINB;
   msm_accumulate_kernel<FA, MINB><<<148 * MINB, 128, 0, st>>>(pl, (const Affine<FA>*)d_points, refs, start, d->pstart, run_bucket,
                                                               d->pieces, d->counters + 1);
   prof_end(acc_tag);
-  count_launch(11);
+  count_launch(1);
   ZKB_CUDA(cudaGetLastError());
   return ZKB_OK;
 }
@@ -345,8 +372,8 @@ int batch_mul_run(const void* d_bases, int single_base, const void* d_scalars, s
     return msm_need_t<FIELD, BITS>(n, wr, ww, tc, tn, need);                                                            \
   }                                                                                                                      \
   int msm_phase1_##SUFFIX(const void* p, const void* s, size_t n, uint32_t wr, uint32_t ww, uint32_t tc, size_t tn,     \
-                          MsmTicket* tk) {                                                                               \
-    return msm_phase1_t<FIELD, BITS>(CURVE, GROUP, p, s, n, wr, ww, tc, tn, tk);                                        \
+                          const MsmTicket* share, MsmTicket* tk) {                                                       \
+    return msm_phase1_t<FIELD, BITS>(CURVE, GROUP, p, s, n, wr, ww, tc, tn, share, tk);                                 \
   }                                                                                                                      \
   int msm_phase2_##SUFFIX(MsmTicket* tk, void* stream) { return msm_phase2_t<FIELD, BITS>(tk, (cudaStream_t)stream); }  \
   int msm_table_##SUFFIX(const void* pts, size_t n, uint32_t world, uint32_t* c, uint32_t* W, void* table) {            \

@@ -69,7 +69,19 @@ int spmv_dev(int curve, size_t n_out, size_t n_rows, const void* row_ptr, const 
 // An MSM is enqueued on the library stream (no synchronisation) against a ticket that owns a pinned result buffer and an
 // event; msm_finish waits for that event and recombines the per-window sums on the host -- so the host part of MSM i
 // overlaps the kernels of MSM i+1.  A ticket can be reused after msm_finish.
+// what one MSM's digit sort produced; another MSM of the same batch over the SAME scalars can reuse it
+struct MsmSorted {
+  const void* scalars;
+  size_t n;
+  uint32_t table_c;
+  size_t table_n;
+  uint32_t wrank, wworld;
+  size_t nb;
+  uint32_t krun;
+  uint32_t *start, *pstart, *npieces, *refs, *run_bucket, *hot_list, *vhot_list, *counters;
+};
 struct MsmTicket {
+  MsmSorted sorted = {};
   int curve = 0, group = 1;
   bool empty = true;
   uint32_t nwin = 0, win0 = 0, c = 0, nlev = 0, nbits = 0, logk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, parts[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -388,7 +388,8 @@ def main_own(args):
                     "imad_lo_peak": imad.value / 1e12,
                     "algorithmic_ops_per_point": ops_per_pt, "points_per_launch": pts_per_launch,
                     "launch_ms": per_launch_ms, "launches": acc_cnt,
-                    "traffic": traffic.get("msm_accumulate_g1"), "share_of_step": acc_ms / args.steps / dev_ms}
+                    "traffic": (traffic.get("msm_accumulate_g1") or {}).get("dram_bytes"),
+                    "traffic_detail": traffic.get("msm_accumulate_g1"), "share_of_step": acc_ms / args.steps / dev_ms}
         msm_all_ms = sum(prof[k][0] for k in ("msm_sort", "msm_accum_g1", "msm_accum_g2", "msm_reduce")) / args.steps
         # the same algorithmic count over ALL FIVE MSMs of the proof (G2 = 3 Fq products per Fq2 product) and all MSM kernels
         ops_step = pts_per_launch * ops_per_pt * (4 + 3)
@@ -401,7 +402,9 @@ def main_own(args):
         roofline_ntt = {"kernel": "ntt_pass_kernel (all passes of one 2^%d transform)" % args.log_n, "bound": "hbm",
                         "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": hbm_src,
                         "algorithmic_bytes": 64 * n, "launch_ms": per, "launches": ntt_cnt,
-                        "traffic": traffic.get("ntt"), "share_of_step": ntt_ms / args.steps / dev_ms}
+                        "traffic": (traffic.get("ntt_pass") or {}).get("dram_bytes"),
+                        "traffic_detail": dict(traffic.get("ntt_pass") or {}, note="one PASS of the transform (a 2^20 transform is 2 passes)"),
+                        "share_of_step": ntt_ms / args.steps / dev_ms}
     breakdown = {k: v[0] / args.steps for k, v in prof.items()}
     msm_ms_total = breakdown["msm_sort"] + breakdown["msm_accum_g1"] + breakdown["msm_accum_g2"] + breakdown["msm_reduce"]
 

@@ -207,6 +207,108 @@ __global__ void __launch_bounds__(128) k_madd(const Affine<F>* pts, XYZZ<F>* out
   if (acc.ZZ == acc.X && acc.Y == acc.ZZZ) out[t & 1023] = acc;
 }
 
+#define P52_0 154029749239111LL
+#define P52_1 2558044347618242LL
+#define P52_2 423691504025962LL
+#define P52_3 2817616741948264LL
+#define P52_4 53207371014449LL
+#define PINV52 571208714576777LL
+
+// ---- 5. PROTOTYPE: Montgomery product on the FP64 pipe (52-bit limbs, R = 2^260; Fq BN254) --------------------------------
+// Every 52x52-bit partial product is 2 DFMA.RZ + 1 DADD (hi = fma_rz(a,b,2^104), lo = fma_rz(a,b,2^104 + 2^52 - hi)) whose bit
+// patterns are accumulated as int64 -- no IMAD at all.  B200 issues DFMA at twice the IMAD.WIDE rate.
+struct D52 { double v[5]; };
+__device__ __constant__ double D52_P[5] = {(double)P52_0, (double)P52_1, (double)P52_2, (double)P52_3, (double)P52_4};
+__device__ __forceinline__ D52 d52_mul(const D52& a, const D52& b) {
+  const double C1 = 0x1p104, C2 = 0x1p104 + 0x1p52, PINV = (double)PINV52;
+  const long long LO = 0x4330000000000000LL, HI = 0x4670000000000000LL, MASK = 0x000fffffffffffffLL;
+  const double P0 = (double)P52_0, P1 = (double)P52_1, P2 = (double)P52_2, P3 = (double)P52_3, P4 = (double)P52_4;
+  const double P[5] = {P0, P1, P2, P3, P4};
+  long long c[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+      double hi = __fma_rz(a.v[j], b.v[i], C1);
+      double lo = __fma_rz(a.v[j], b.v[i], C2 - hi);
+      c[j] += __double_as_longlong(lo) - LO;
+      c[j + 1] += __double_as_longlong(hi) - HI;
+    }
+    double vd = __longlong_as_double((c[0] & MASK) | LO) - 0x1p52;
+    double qh = __fma_rz(vd, PINV, C1);
+    double qd = __fma_rz(vd, PINV, C2 - qh) - 0x1p52;   // (v * p') mod 2^52
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+      double hi = __fma_rz(qd, P[j], C1);
+      double lo = __fma_rz(qd, P[j], C2 - hi);
+      c[j] += __double_as_longlong(lo) - LO;
+      c[j + 1] += __double_as_longlong(hi) - HI;
+    }
+    long long carry = c[0] >> 52;     // c[0] is a multiple of 2^52 now
+    c[0] = c[1] + carry; c[1] = c[2]; c[2] = c[3]; c[3] = c[4]; c[4] = c[5]; c[5] = 0;
+  }
+  // normalise, conditional subtraction of p, back to doubles
+#pragma unroll
+  for (int k = 0; k < 4; k++) { c[k + 1] += c[k] >> 52; c[k] &= MASK; }
+  const long long PL[5] = {P52_0, P52_1, P52_2, P52_3, P52_4};
+  long long d[5], borrow = 0;
+#pragma unroll
+  for (int k = 0; k < 5; k++) { long long t = c[k] - PL[k] - borrow; borrow = (t >> 63) & 1; d[k] = t & MASK; }
+  D52 r;
+#pragma unroll
+  for (int k = 0; k < 5; k++) r.v[k] = __longlong_as_double((borrow ? c[k] : d[k]) | LO) - 0x1p52;
+  return r;
+}
+__device__ __forceinline__ D52 to52(const uint32_t* v) {
+  unsigned long long w0 = v[0] | ((unsigned long long)v[1] << 32), w1 = v[2] | ((unsigned long long)v[3] << 32);
+  unsigned long long w2 = v[4] | ((unsigned long long)v[5] << 32), w3 = v[6] | ((unsigned long long)v[7] << 32);
+  const unsigned long long M = 0x000fffffffffffffull;
+  D52 r;
+  r.v[0] = (double)(long long)(w0 & M);
+  r.v[1] = (double)(long long)(((w0 >> 52) | (w1 << 12)) & M);
+  r.v[2] = (double)(long long)(((w1 >> 40) | (w2 << 24)) & M);
+  r.v[3] = (double)(long long)(((w2 >> 28) | (w3 << 36)) & M);
+  r.v[4] = (double)(long long)(w3 >> 16);
+  return r;
+}
+__device__ __forceinline__ void from52(const D52& a, uint32_t* v) {
+  unsigned long long l0 = (unsigned long long)a.v[0], l1 = (unsigned long long)a.v[1], l2 = (unsigned long long)a.v[2];
+  unsigned long long l3 = (unsigned long long)a.v[3], l4 = (unsigned long long)a.v[4];
+  unsigned long long w0 = l0 | (l1 << 52), w1 = (l1 >> 12) | (l2 << 40), w2 = (l2 >> 24) | (l3 << 28), w3 = (l3 >> 36) | (l4 << 16);
+  v[0] = (uint32_t)w0; v[1] = (uint32_t)(w0 >> 32); v[2] = (uint32_t)w1; v[3] = (uint32_t)(w1 >> 32);
+  v[4] = (uint32_t)w2; v[5] = (uint32_t)(w2 >> 32); v[6] = (uint32_t)w3; v[7] = (uint32_t)(w3 >> 32);
+}
+// check: d52_mul(a, b) = a b 2^-260 mod p  ==  mont_mul(mont_mul(a, b), 2^252)   (integer multiplier: x y 2^-256)
+__global__ void k_d52_check(const Fp<FqBN254>* in, int n, int* bad) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  Fp<FqBN254> a = in[t], b = in[(t * 7 + 3) % n];
+  Fp<FqBN254> k = Fp<FqBN254>::zero();
+  k.v[7] = 0x10000000u;   // 2^252
+  Fp<FqBN254> want = mont_mul(mont_mul(a, b), k);
+  D52 r = d52_mul(to52(a.v), to52(b.v));
+  Fp<FqBN254> got;
+  from52(r, got.v);
+  if (!(got == want)) atomicAdd(bad, 1);
+}
+template <int ST>
+__global__ void __launch_bounds__(128) k_d52_mul(const Fp<FqBN254>* io, uint32_t* out, int iters) {
+  D52 x[ST], y[ST];
+  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int s = 0; s < ST; s++) { x[s] = to52(io[(t * ST + s) & 1023].v); y[s] = to52(io[(t * ST + s + 7) & 1023].v); }
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int s = 0; s < ST; s++) x[s] = d52_mul(x[s], y[s]);
+#pragma unroll
+    for (int s = 0; s < ST; s++) y[s] = d52_mul(y[s], x[s]);
+  }
+  double r = 0;
+#pragma unroll
+  for (int s = 0; s < ST; s++) r += x[s].v[0] + y[s].v[4];
+  if (r == 1234.5) out[0] = 1;
+}
+
 template <class K, class... A>
 static float run(const char* name, double ops_per_thread, int blocks, int threads, K kern, A... args) {
   cudaEvent_t e0, e1;
@@ -295,6 +397,29 @@ int main(int argc, char** argv) {
   uint32_t* d;
   CK(cudaMalloc(&d, 4096));
   const int it = 2048;
+  if (argc > 1 && atoi(argv[1]) == 4) {
+    Fp<FqBN254>* dv;
+    CK(cudaMalloc(&dv, 65536 * sizeof(Fp<FqBN254>)));
+    fill_field(dv, 65536);
+    int* bad;
+    CK(cudaMalloc(&bad, 4));
+    CK(cudaMemset(bad, 0, 4));
+    k_d52_check<<<256, 256>>>(dv, 65536, bad);
+    int hb = -1;
+    CK(cudaMemcpy(&hb, bad, 4, cudaMemcpyDeviceToHost));
+    printf("d52_mul correctness vs integer multiplier on 65536 pairs: %d mismatches\n", hb);
+    const int iters = 2000;
+    for (int bps : {2, 4, 8}) {
+      char name[128];
+      snprintf(name, sizeof(name), "d52 mont_mul FqBN254 streams=1 (%d blk/SM x128)", bps);
+      run(name, 2.0 * iters, 148 * bps, 128, k_d52_mul<1>, (const Fp<FqBN254>*)dv, d, iters);
+      snprintf(name, sizeof(name), "d52 mont_mul FqBN254 streams=2 (%d blk/SM x128)", bps);
+      run(name, 4.0 * iters, 148 * bps, 128, k_d52_mul<2>, (const Fp<FqBN254>*)dv, d, iters);
+    }
+    bench_field<Fp<FqBN254Inl>>("FqBN254 integer fused inline", 4);
+    return 0;
+  }
+#ifndef D52_ONLY
   if (argc > 1 && atoi(argv[1]) == 3) {
     for (int bps : {2, 4}) {
       bench_field<Fp<FqBN254Inl>>("FqBN254 fused inline", bps);
@@ -347,5 +472,6 @@ int main(int argc, char** argv) {
   bench_madd<Fp<FqBLS381Inl>>("G1 BLS381 inline", 3);
   bench_madd<Fp<FqBLS381>>("G1 BLS381 call", 3);
   bench_madd<Fp2<FqBN254>>("G2 BN254 call", 2);
+#endif
   return 0;
 }

@@ -81,7 +81,8 @@ def test_prove_matches_oracle_small(gpu, curve_name):
             assert not g.verify(proof, forged)
 
 
-@pytest.mark.parametrize("curve_name,n", [("BN254", 1 << 12), ("BLS12_381", 1 << 10), ("BN254", 1 << 16)])
+@pytest.mark.parametrize("curve_name,n", [("BN254", 1 << 12), ("BLS12_381", 1 << 10), ("BN254", 1 << 16), ("BLS12_381", 1 << 16),
+                                          ("BN254", 1 << 20)])   # the last one is BASELINE.json's full size
 def test_prove_matches_closed_form_large(gpu, curve_name, n):
     from zksnake_b200 import groth16 as gm
     from zksnake_b200 import r1cs as rm

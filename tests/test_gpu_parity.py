@@ -260,6 +260,11 @@ def test_msm_g1_discrete_log(gpu, curve, kind):
         dlog_msm_case(gpu, group(curve, False), n, kind, seed=n)
 
 
+def test_msm_g1_discrete_log_full_size(gpu):
+    """2^20 points (BASELINE.json's size), uniform scalars: the result must equal (sum s_i k_i) * G."""
+    dlog_msm_case(gpu, group(0, False), 1 << 20, "uniform", seed=2020)
+
+
 @pytest.mark.parametrize("curve", CURVES)
 def test_msm_g2_discrete_log(gpu, curve):
     for n, kind in ((1 << 12, "uniform"), (1 << 14, "bits"), (1 << 16, "uniform")):

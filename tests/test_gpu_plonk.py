@@ -155,3 +155,16 @@ def test_device_prover_large_and_bad_witness(gpu):
     bad[4] = (bad[4] + 1) % r
     with pytest.raises(AssertionError):
         dev.prove(pub, bad)
+
+
+def test_device_prover_2p16_verifies(gpu):
+    """2^16 gates: transforms on the 2^16 / 2^18 / 2^19 domains, MSMs of 65 542 points over the SRS table; verify() must pass."""
+    from zksnake_b200.plonk_device import DevicePlonk
+    from zksnake_b200.plonkish import chain_gates
+    cs, pub, priv = chain_gates(1 << 16, "BN254")
+    plonk = DevicePlonk(cs, "BN254")
+    plonk.setup()
+    proof = plonk.prove(pub, priv)
+    assert plonk.verify(proof, pub)
+    k = next(iter(pub))
+    assert not plonk.verify(proof, {k: (pub[k] + 1) % plonk.order})

@@ -60,7 +60,7 @@ def main():
     line = {
         "metric": "plonk_prove_ms", "value": float(np.median(times)), "unit": "ms", "n_gpus": 1, "steps": steps,
         "config": {"workload": f"plonk-prove chain circuit (benchmarks/benchmark_plonk.py) 2^{log_n} gates {curve}",
-                   "msm": "9 x G1 over the SRS table", "ntt": "domains n, 4n, 8n"},
+                   "msm": "9 x G1 over the SRS table", "ntt": "5 x n, 6 x 4n (coset quotient)"},
         "rounds_ms": {k: float(np.median([r[k] for r in rounds])) for k in rounds[0]},
         "device_ms_by_family": {k: v[0] / steps for k, v in prof.items() if v[1]},
         "family_launch_groups": {k: v[1] // steps for k, v in prof.items() if v[1]},

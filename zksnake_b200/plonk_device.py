@@ -3,8 +3,13 @@
 in HBM as an `FrVec` and every step a kernel launch -- SURVEY.md section 8f rank 3.  What changes is only HOW each polynomial is
 computed, never WHICH polynomial:
 
-  * products that the reference sends through `mul_over_fft` with its padding rule (8n domain, polynomial.py:126-165) are
-    computed on the 8n domain directly -- the product polynomial is unique;
+  * the quotient T = (G + alpha (nom Z - den Z_omega) + alpha^2 (Z - 1) L1) / (X^n - 1) is unique, so it is computed the way a
+    GPU wants it instead of the reference's 15 transforms on the 4n domain and 6 on the 8n domain (protocol.py:240-262,
+    284-300, 338-352 with polynomial.py:126-165): every factor polynomial has degree < 4n, so it is evaluated on ONE coset
+    g<omega_4n> (5 coset transforms of size 4n: A, B, C, Z, PI; the selectors, sigma polynomials and L1 are pre-evaluated in
+    setup; id_k(x) = k x needs no transform; Z(omega x) is a rotation by 4), the numerator is formed pointwise, divided
+    pointwise by X^n - 1 (four distinct values on that coset) and brought back with ONE inverse coset transform.  The
+    grand-product numerators and denominators are read off the witness values directly (the blinding terms vanish on H);
   * the grand-product accumulator (protocol.py:302-313: batch_modinv + a Python loop) is a batch-inversion kernel, a pointwise
     product and an exclusive prefix-product scan;
   * divisions by X - zeta (polynomial.rs:404-438 long division) are two power scalings around a suffix-sum scan;
@@ -87,29 +92,52 @@ class DevicePlonk(Plonk):
 
         omega = get_evaluation_point(n, 1, p)
         self.omega = omega
-        ids = [FrVec.powers(cid, n, omega, k) for k in (1, K1, K2)]            # identity permutation values on H, k1 H, k2 H
+        # quotient domain: every factor polynomial (degree <= n + 2) and T (degree <= 3n + 5) must fit: 4n, or 8n below 8 gates
+        N4 = self.NQ = 4 * n if n >= 8 else 8 * n
+        omega4 = get_evaluation_point(N4, 1, p)
+        g = 5 if cid == 0 else 7               # multiplicative generator of Fr: g^(4n) != 1, so X^n - 1 has no zero on g<omega_4n>
+        self.coset_g = g
+        roots = FrVec.powers(cid, n, omega)    # omega^i
         all_ids = FrVec(cid, 3 * n)
-        for k in range(3):
-            nat.check(nat.lib.zkb_d2d(all_ids.at(k * n), ids[k].ptr, n * 32))
+        for k, kk in enumerate((1, K1, K2)):   # identity permutation values on H, k1 H, k2 H
+            nat.check(nat.lib.zkb_d2d(all_ids.at(k * n), roots.scale(kk).ptr if kk != 1 else roots.ptr, n * 32))
         perm = np.asarray(cs.permutation, dtype=np.uint32)
         d_perm = nat.DeviceBuffer(perm.nbytes).upload(perm)
-        sigma_ev = all_ids.gather_index(d_perm, 3 * n)
+        sigma_all = all_ids.gather_index(d_perm, 3 * n)
         d_perm.free()
+        sigma_ev = [sigma_all.copy(k * n, (k + 1) * n) for k in range(3)]
         sel_ev_n = {k: FrVec.from_ints(cid, v) for k, v in (("L", cs.qL), ("R", cs.qR), ("O", cs.qO), ("M", cs.qM), ("C", cs.qC))}
         selector_poly = {k: v.intt() for k, v in sel_ev_n.items()}
-        permutation_poly = [sigma_ev.copy(k * n, (k + 1) * n).intt() for k in range(3)]
-        identity_poly = [v.intt() for v in ids]
-        selector_eval = {k: q.ntt(4 * n) for k, q in selector_poly.items()}
+        permutation_poly = [s.intt() for s in sigma_ev]
         tau_selector = {k: self._commit(q) for k, q in selector_poly.items()}
         tau_permutation = [self._commit(s) for s in permutation_poly]
+        # everything the quotient needs, pre-evaluated on the coset g <omega_4n>
+        self.selector_coset = {k: self._coset_ntt(q) for k, q in selector_poly.items()}
+        self.sigma_coset = [self._coset_ntt(s) for s in permutation_poly]
         l1 = FrVec.zeros(cid, n)
         l1.add_sparse({0: 1})
-        lagrange_evals = l1.intt().ntt(4 * n)
-        self.proving_key = ProvingKey(n, self.G1_tau, selector_poly, selector_eval, permutation_poly, identity_poly, tau_selector,
-                                      tau_permutation, lagrange_evals, self.E.name)
+        self.l1_coset = self._coset_ntt(l1.intt())
+        self.x_coset = FrVec.powers(cid, N4, omega4, g)                        # the coset points g omega_4n^i
+        self.ones4 = FrVec.powers(cid, N4, 1)
+        per = N4 // n                                                          # 4 (or 8): omega_NQ^n is a primitive per-th root of unity
+        i4 = pow(omega4, n, p)
+        gn = pow(g, n, p)
+        zh_inv = [pow((gn * pow(i4, k, p) - 1) % p, -1, p) for k in range(per)]  # 1 / (x^n - 1) at coset point i depends on i mod per
+        self.zh_inv_coset = FrVec.from_limbs(cid, np.tile(nat.ints_to_limbs(zh_inv), (n, 1)), reduce=False)
+        self.roots, self.sigma_ev = roots, sigma_ev
+        self.proving_key = ProvingKey(n, self.G1_tau, selector_poly, None, permutation_poly, None, tau_selector, tau_permutation,
+                                      None, self.E.name)
         self.verifying_key = VerifyingKey(n, self.G2_tau, tau_selector, tau_permutation, self.E.name)
         self._roots = [1, omega]    # verify() only needs omega
         nat.check(nat.lib.zkb_sync())
+
+    def _coset_ntt(self, poly):
+        """evaluations of a polynomial (fewer than 4n coefficients) on the coset g <omega_4n>"""
+        return poly.mul_powers(self.coset_g).ntt(self.NQ)
+
+    def _coset_intt(self, evals):
+        p = self.order
+        return evals.intt().mul_powers(pow(self.coset_g, -1, p))
 
     # -------------------------------------------------------------------------------------------------------------- prove
     def prove(self, public_witness: dict, private_witness: list):
@@ -124,10 +152,11 @@ class DevicePlonk(Plonk):
         """wire_columns: three (n, 4) uint64 arrays (a, b, c wire values, canonical), host memory."""
         assert self.proving_key, "ProvingKey has not been generated"
         pk, p, cid = self.proving_key, self.order, self.cid
-        n, N4, N8 = pk.n, 4 * pk.n, 8 * pk.n
+        n, N4 = pk.n, self.NQ
         omega = self.omega
         rnd = _plonk.get_random_int
-        sel, sel_ev, ident, sig = pk.selector_poly, pk.selector_eval, pk.identity_poly, pk.permutation_poly
+        sel, sig = pk.selector_poly, pk.permutation_poly
+        selc, sigc = self.selector_coset, self.sigma_coset
         T = {}
         t0 = time.perf_counter()
 
@@ -161,57 +190,57 @@ class DevicePlonk(Plonk):
             pi_ev_n.add_sparse({k: v % p for k, v in public_witness.items()})
         A, B, C = (blind(w.intt(), [rnd(p - 1) for _ in range(2)]) for w in wires)
         PI = pi_ev_n.intt()
-        a_ev, b_ev, c_ev, pi_ev = (x.ntt(N4) for x in (A, B, C, PI))
-        g_ev = a_ev.mul(sel_ev["L"]).add(b_ev.mul(sel_ev["R"])).add(c_ev.mul(sel_ev["O"])) \
-            .add(a_ev.mul(b_ev).mul(sel_ev["M"])).add(sel_ev["C"]).add(pi_ev)
-        G = g_ev.intt()
-        del a_ev, b_ev, c_ev, pi_ev, g_ev
         tau_a, tau_b, tau_c = self._commit_many([A, B, C])
         for c in (tau_a, tau_b, tau_c):
             tr.append(c)
         lap("round1")
 
-        # ---- round 2 ----
+        # ---- round 2: grand product from the witness values (the blinding terms vanish on the domain H) ----
         beta, gamma = tr.get_challenge_scalar(), tr.get_challenge_scalar()
         zr = [rnd(p - 1) for _ in range(3)]
-
-        def triple_product(parts):
-            prod = None
-            for w, s in zip((A, B, C), parts):
-                lin = s.axpy(beta, w)                     # beta * s + w
-                lin.add_sparse({0: gamma})
-                ev = lin.ntt(N4)
-                prod = ev if prod is None else prod.mul(ev)
-            return prod
-
-        nom_ev = triple_product(ident)
-        den_ev = triple_product(sig)
-        ratio = nom_ev.gather(n, 4).mul(den_ev.gather(n, 4).inverse())    # the n-domain points are every 4th of the 4n domain
-        acc = ratio.prefix_product()
+        ones_n = FrVec.powers(cid, n, 1)
+        num = den = None
+        for w, kk, s_ev in zip(wires, (1, K1, K2), self.sigma_ev):
+            f_id = ones_n.axpy(gamma, self.roots.axpy(beta * kk % p, w))        # w + beta k omega^i + gamma
+            f_sg = ones_n.axpy(gamma, s_ev.axpy(beta, w))                       # w + beta sigma(omega^i) + gamma
+            num = f_id if num is None else num.mul(f_id)
+            den = f_sg if den is None else den.mul(f_sg)
+        acc = num.mul(den.inverse()).prefix_product()
         assert acc.item(n) == 1, "Copy constraints are not satisfied"
         Z = blind(acc.copy(0, n).intt(), zr)
-        nom_poly, den_poly = nom_ev.intt(), den_ev.intt()
-        del nom_ev, den_ev, ratio, acc
+        del num, den, acc
         tau_z = self._commit(Z)
         tr.append(tau_z)
         lap("round2")
 
-        # ---- round 3 ----
+        # ---- round 3: the quotient on the coset g <omega_4n> ----
         alpha = tr.get_challenge_scalar()
-        Z_omega = Z.mul_powers(omega)                                      # Z(omega X)
-        z8 = Z.ntt(N8)
-        nom_Z = nom_poly.ntt(N8).mul(z8).intt()
-        den_Zw = den_poly.ntt(N8).mul(Z_omega.ntt(N8)).intt()
-        del z8, nom_poly, den_poly
-        z_minus_1 = Z.copy()
-        z_minus_1.add_sparse({0: 1}, subtract=True)
-        z1_l1 = z_minus_1.ntt(N4).mul(pk.lagrange_evals).intt()
-        numer = nom_Z.sub(den_Zw).axpy(alpha, G, n=N8)
-        numer = z1_l1.axpy(alpha * alpha % p, numer, n=N8)
-        del nom_Z, den_Zw, z1_l1, G
-        Tq, exact = numer.div_vanishing(n)
-        assert exact
+        Z_omega = Z.mul_powers(omega)                                          # Z(omega X), needed as coefficients in round 4
+        Ac, Bc, Cc, Zc, PIc = (self._coset_ntt(x) for x in (A, B, C, Z, PI))
+        numer = Ac.mul(selc["L"]).add(Bc.mul(selc["R"])).add(Cc.mul(selc["O"])).add(Ac.mul(Bc).mul(selc["M"])) \
+            .add(selc["C"]).add(PIc)                                            # the gate polynomial G
+        nomc = denc = None
+        for wc, kk, sc in zip((Ac, Bc, Cc), (1, K1, K2), sigc):
+            f_id = self.ones4.axpy(gamma, self.x_coset.axpy(beta * kk % p, wc))   # W(x) + beta k x + gamma
+            f_sg = self.ones4.axpy(gamma, sc.axpy(beta, wc))                      # W(x) + beta sigma(x) + gamma
+            nomc = f_id if nomc is None else nomc.mul(f_id)
+            denc = f_sg if denc is None else denc.mul(f_sg)
+        del Ac, Bc, Cc, PIc
+        rot = N4 // n                                                          # omega = omega_NQ^rot
+        Zwc = FrVec(cid, N4)                                                   # Z(omega x) on the coset: a rotation by `rot`
+        nat.check(nat.lib.zkb_d2d(Zwc.ptr, Zc.at(rot), (N4 - rot) * 32))
+        nat.check(nat.lib.zkb_d2d(Zwc.at(N4 - rot), Zc.ptr, rot * 32))
+        numer = nomc.mul(Zc).sub(denc.mul(Zwc)).axpy(alpha, numer)
+        numer = Zc.sub(self.ones4).mul(self.l1_coset).axpy(alpha * alpha % p, numer)
+        del nomc, denc, Zwc, Zc
+        Tq = self._coset_intt(numer.mul(self.zh_inv_coset))                    # 4n coefficients; deg T <= 3n + 5
         del numer
+        # the reference asserts a zero remainder (protocol.py:354-360): here an unsatisfied gate shows up as non-zero
+        # coefficients above degree 3n + 5 -- tested by evaluating that tail at two points (Schwartz-Zippel; the points come
+        # from the transcript challenge, not from the blinding stream, so the proof bytes stay those of the reference's order)
+        tail = Tq.copy(3 * n + 6, N4)
+        assert tail.eval((alpha * alpha + 7) % p) == 0 and tail.eval(1) == 0, "gate constraints are not satisfied"
+        del tail
         b10, b11 = (rnd(p - 1) for _ in range(2))
         T_lo = Tq.copy(0, n, n=n + 1)
         T_lo.add_sparse({n: b10})

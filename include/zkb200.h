@@ -86,7 +86,8 @@ int zkb_memset(void* dst, int value, size_t bytes);
 
 /* ---- Fr vectors ------------------------------------------------------------------------------------------- */
 /* N = 2^log_n.  in_len <= any; inputs are zero-padded or truncated to N.  coset: 0 = plain, 1 = the reference's
- * coset (offset = generator of the size-N domain).  out holds N elements. */
+ * coset (offset = generator of the size-N domain), 2 = the coset g<w> with g the multiplicative generator of Fr (5 on BN254,
+ * 7 on BLS12-381; used for quotient polynomials: X^n - 1 has no zero on it).  out holds N elements. */
 int zkb_ntt(int curve, int inverse, int coset, uint32_t log_n, const uint64_t* in, size_t in_len, uint64_t* out);
 int zkb_ntt_dev(int curve, int inverse, int coset, uint32_t log_n, const void* d_in, size_t in_len, void* d_out);
 /* out[i] = a[i] op b[i] for i < n; a / b shorter than n are zero-extended (mul_over_evaluation_domain semantics). */
@@ -112,6 +113,13 @@ int zkb_fr_gather_index_dev(int curve, size_t n, const void* d_src, const void* 
 int zkb_fr_eval_dev(int curve, size_t n, const void* d_coeffs, const uint64_t point[4], uint64_t out[4]);   /* sum c_i z^i (sync) */
 /* q = p / (X^d - 1) (len - d coefficients, polynomial.rs:466-489); *exact = 0 when the remainder is non-zero (sync) */
 int zkb_fr_div_vanishing_dev(int curve, size_t len, size_t d, const void* d_p, void* d_q, int* exact);
+/* PlonK quotient evaluations on the coset g<w_q> of size q (2n..8n) in one pass (python/zksnake/plonk/protocol.py:240-262, 284-300,
+ * 338-360 reach the same polynomial through ~20 transforms): d_inputs = coset evaluations of a, b, c, z, pi, qL, qR, qO, qM, qC,
+ * sigma1, sigma2, sigma3, L1;  out[i] = (gate + alpha (id z - sg z(omega x)) + alpha^2 (z - 1) L1) / (x^n - 1) at x = g w_q^i;
+ * zh_inv = the q/n distinct values of 1 / (x^n - 1) on the coset (index i mod q/n). */
+int zkb_plonk_quotient_dev(int curve, size_t q, size_t n, const void* const d_inputs[14], const uint64_t g[4], const uint64_t omega_q[4],
+                           const uint64_t beta[4], const uint64_t gamma[4], const uint64_t alpha[4], const uint64_t* zh_inv,
+                           void* d_out);
 int zkb_fr_add_sparse_dev(int curve, void* d_vec, size_t k, const uint64_t* idx, const uint64_t* vals, int subtract); /* async */
 
 /* ---- points and MSM --------------------------------------------------------------------------------------- */

@@ -65,6 +65,7 @@ def _load():
         "zkb_fr_gather_index_dev": (c_int, [c_int, c_sz, c_vp, c_vp, c_vp]),
         "zkb_fr_eval_dev": (c_int, [c_int, c_sz, c_vp, c_vp, c_vp]),
         "zkb_fr_div_vanishing_dev": (c_int, [c_int, c_sz, c_sz, c_vp, c_vp, ctypes.POINTER(c_int)]),
+        "zkb_plonk_quotient_dev": (c_int, [c_int, c_sz, c_sz, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "zkb_fr_add_sparse_dev": (c_int, [c_int, c_vp, c_sz, c_vp, c_vp, c_int]),
         "zkb_affine_bytes": (c_sz, [c_int, c_int]),
         "zkb_points_upload": (c_int, [c_int, c_int, c_vp, c_sz, c_vp]),

@@ -242,6 +242,53 @@ __global__ void add_sparse_kernel(SparseArgs<F> a, int subtract, F* v) {
   ntt_st(v + a.idx[t], subtract ? x - a.val[t] : x + a.val[t]);
 }
 
+
+// ---- PlonK quotient on the coset g<w_q> (q = coset size, a multiple `per` = q / n of the gate count) --------------------------
+// t[i] = ( gate + alpha (id z - sg z_w) + alpha^2 (z - 1) l1 ) / (x^n - 1)   at x = g w_q^i, with
+//   gate = a ql + b qr + c qo + a b qm + qc + pi,
+//   id = (a + beta x + gamma)(b + 2 beta x + gamma)(c + 3 beta x + gamma),  sg = (a + beta s1 + gamma)(b + beta s2 + gamma)(c + beta s3 + gamma),
+//   z_w = z[(i + per) mod q]  (Z(omega x): omega = w_q^per).
+// One pass over 14 input vectors instead of ~45 element-wise launches (python/zksnake/plonk/protocol.py:240-262, 284-300,
+// 338-352 compute the same numerator through NTT round trips).  Inputs canonical; wire-like values are lifted to Montgomery
+// form in registers so that every product lands in the form its consumer needs (mont_mul(canonical, montgomery) = canonical).
+template <class F>
+struct QuotientArgs {
+  const F *a, *b, *c, *z, *pi, *ql, *qr, *qo, *qm, *qc, *s1, *s2, *s3, *l1;
+  F g, wq, beta, beta_r2, gamma, alpha_c, alpha2, zh_inv[8];   // Montgomery except alpha_c (canonical); beta_r2 = beta R^2
+  unsigned long long q;
+  uint32_t per;
+};
+#define ZKB_QUOT_CH 8
+template <class F>
+__global__ void __launch_bounds__(128) plonk_quotient_kernel(QuotientArgs<F> A, F* __restrict__ t) {
+  unsigned long long lo = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) * ZKB_QUOT_CH;
+  if (lo >= A.q) return;
+  F x = pow_u64(A.wq, lo) * A.g;   // Montgomery(g w^lo)
+  const F r2 = F::r2();
+  for (int k = 0; k < ZKB_QUOT_CH; k++) {
+    unsigned long long i = lo + k;
+    if (i >= A.q) break;
+    unsigned long long iw = i + A.per;
+    if (iw >= A.q) iw -= A.q;
+    F a = ntt_ld(A.a + i) * r2, b = ntt_ld(A.b + i) * r2, c = ntt_ld(A.c + i) * r2;
+    F z = ntt_ld(A.z + i) * r2, zw = ntt_ld(A.z + iw) * r2;
+    // gate constraint (canonical)
+    F gate = a * ntt_ld(A.ql + i) + b * ntt_ld(A.qr + i) + c * ntt_ld(A.qo + i) + (a * b) * ntt_ld(A.qm + i) + ntt_ld(A.qc + i) +
+             ntt_ld(A.pi + i);
+    // permutation argument (Montgomery)
+    F bx = A.beta * x;
+    F bx2 = bx + bx;
+    F id = ((a + bx + A.gamma) * (b + bx2 + A.gamma)) * (c + (bx2 + bx) + A.gamma);
+    F sg = ((a + A.beta_r2 * ntt_ld(A.s1 + i) + A.gamma) * (b + A.beta_r2 * ntt_ld(A.s2 + i) + A.gamma)) *
+           (c + A.beta_r2 * ntt_ld(A.s3 + i) + A.gamma);
+    F perm = id * z - sg * zw;                              // Montgomery
+    F l1t = (z - F::one()) * ntt_ld(A.l1 + i);              // canonical
+    F num = gate + perm * A.alpha_c + l1t * A.alpha2;       // canonical
+    ntt_st(t + i, num * A.zh_inv[i % A.per]);
+    x = x * A.wq;
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------------------
 template <class F>
 static F mont_from_words(const uint64_t w[4]) {
@@ -356,6 +403,32 @@ struct FrVecOps {
     *exact = h ? 0 : 1;
     return ZKB_OK;
   }
+
+  static int quotient(size_t q, size_t n, const void* const* in, const uint64_t* g, const uint64_t* wq, const uint64_t* beta,
+                      const uint64_t* gamma, const uint64_t* alpha, const uint64_t* zh_inv, void* out) {
+    if (n == 0 || q % n || q / n > 8 || q / n < 2) return set_error(ZKB_ERR_ARG, "plonk quotient: coset size must be 2n..8n");
+    QuotientArgs<F> A;
+    const F** slots[14] = {&A.a, &A.b, &A.c, &A.z, &A.pi, &A.ql, &A.qr, &A.qo, &A.qm, &A.qc, &A.s1, &A.s2, &A.s3, &A.l1};
+    for (int k = 0; k < 14; k++) *slots[k] = (const F*)in[k];
+    A.g = mont_from_words<F>(g);
+    A.wq = mont_from_words<F>(wq);
+    A.beta = mont_from_words<F>(beta);
+    A.beta_r2 = A.beta * F::r2();
+    A.gamma = mont_from_words<F>(gamma);
+    F al = mont_from_words<F>(alpha);
+    A.alpha_c = from_mont(al);
+    A.alpha2 = al * al;
+    A.q = q;
+    A.per = (uint32_t)(q / n);
+    for (uint32_t k = 0; k < 8; k++) A.zh_inv[k] = k < A.per ? mont_from_words<F>(zh_inv + 4 * k) : F::zero();
+    size_t threads = (q + ZKB_QUOT_CH - 1) / ZKB_QUOT_CH;
+    prof_begin(PROF_VEC);
+    plonk_quotient_kernel<F><<<(unsigned)((threads + 127) / 128), 128, 0, S()>>>(A, (F*)out);
+    prof_end(PROF_VEC);
+    count_launch();
+    ZKB_CUDA(cudaGetLastError());
+    return ZKB_OK;
+  }
   static int add_sparse(void* v, size_t k, const uint64_t* idx, const uint64_t* vals, int subtract) {
     for (size_t done = 0; done < k; done += 8) {
       SparseArgs<F> a;
@@ -424,6 +497,13 @@ int zkb_fr_div_vanishing_dev(int curve, size_t len, size_t d, const void* d_p, v
   NEED_INIT();
   if (d == 0) return set_error(ZKB_ERR_ARG, "div_vanishing: d must be positive");
   BY_CURVE(FrVecOps<fr_bn>::div_vanishing(len, d, d_p, d_q, exact), FrVecOps<fr_bls>::div_vanishing(len, d, d_p, d_q, exact))
+}
+int zkb_plonk_quotient_dev(int curve, size_t q, size_t n, const void* const d_inputs[14], const uint64_t g[4], const uint64_t omega_q[4],
+                           const uint64_t beta[4], const uint64_t gamma[4], const uint64_t alpha[4], const uint64_t* zh_inv,
+                           void* d_out) {
+  NEED_INIT();
+  BY_CURVE(FrVecOps<fr_bn>::quotient(q, n, d_inputs, g, omega_q, beta, gamma, alpha, zh_inv, d_out),
+           FrVecOps<fr_bls>::quotient(q, n, d_inputs, g, omega_q, beta, gamma, alpha, zh_inv, d_out))
 }
 int zkb_fr_add_sparse_dev(int curve, void* d_vec, size_t k, const uint64_t* idx, const uint64_t* vals, int subtract) {
   NEED_INIT();

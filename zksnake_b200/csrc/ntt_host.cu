@@ -48,6 +48,7 @@ struct Domain {
   DevTable<F> inv_scaled;        // w^-j * N^-1      (coset_ifft post-scale)
   DevTable<F> gen_pre, gen_pre_r;  // g^j, g^j / R     (H pipeline coset, g = multiplicative generator)
   DevTable<F> gen_post;          // g^-j * R / (N (g^N - 1))
+  DevTable<F> gen_ipost;         // g^-j / N                  (inverse transform from the coset g<w>)
   F n_inv;                       // Montgomery(N^-1)
   bool have_gen = false;
 };
@@ -111,6 +112,7 @@ static int get_domain(uint32_t log_n, bool need_gen, Domain<F>** out) {
     if ((rc = build_table(d.gen_pre, g, F::one(), log_n))) return rc;
     if ((rc = build_table(d.gen_pre_r, g, r_inv, log_n))) return rc;
     if ((rc = build_table(d.gen_post, gi, post_c, log_n))) return rc;
+    if ((rc = build_table(d.gen_ipost, gi, d.n_inv, log_n))) return rc;
     d.have_gen = true;
   }
   *out = &d;
@@ -224,7 +226,7 @@ static int ntt_dev_t(int inverse, int coset, uint32_t log_n, const void* d_in, s
   if (log_n > (uint32_t)P::TWO_ADICITY || log_n > 30)
     return set_error(ZKB_ERR_DOMAIN, "Domain size is too large");
   Domain<F>* d;
-  int rc = get_domain<F>(log_n, false, &d);
+  int rc = get_domain<F>(log_n, coset == 2, &d);
   if (rc) return rc;
   F* tmp = nullptr;
   if (log_n > 10) {
@@ -233,6 +235,11 @@ static int ntt_dev_t(int inverse, int coset, uint32_t log_n, const void* d_in, s
     tmp = (F*)scratch_take((size_t)32 << log_n);
   }
   PowTable<F> fwd = d->fwd.view(), inv_t = d->inv.view(), inv_s = d->inv_scaled.view();
+  if (coset == 2) {   // coset g <w>, g = the field's multiplicative generator (5 / 7)
+    PowTable<F> gpre = d->gen_pre.view(), gipost = d->gen_ipost.view();
+    if (!inverse) return ntt_exec<F>((const F*)d_in, in_len, (F*)d_out, log_n, fwd, &gpre, nullptr, nullptr, tmp);
+    return ntt_exec<F>((const F*)d_in, in_len, (F*)d_out, log_n, inv_t, nullptr, &gipost, nullptr, tmp);
+  }
   if (!inverse) return ntt_exec<F>((const F*)d_in, in_len, (F*)d_out, log_n, fwd, coset ? &fwd : nullptr, nullptr, nullptr, tmp);
   if (coset) return ntt_exec<F>((const F*)d_in, in_len, (F*)d_out, log_n, inv_t, nullptr, &inv_s, nullptr, tmp);
   return ntt_exec<F>((const F*)d_in, in_len, (F*)d_out, log_n, inv_t, nullptr, nullptr, &d->n_inv, tmp);

@@ -52,6 +52,7 @@ unsigned long long launches();
 
 // ---- NTT (ntt_host.cu) ----
 // coset: 0 none | 1 reference coset (offset = group generator of the same domain, polynomial.rs:553-556, 579-582)
+//        | 2 coset g<w> with g the multiplicative generator of Fr (5 for BN254, 7 for BLS12-381): quotient computations
 int ntt_dev(int curve, int inverse, int coset, uint32_t log_n, const void* d_in, size_t in_len, void* d_out);
 int vec_op_dev(int curve, int op, size_t n, const void* a, size_t na, const void* b, size_t nb, const void* c, void* out);
 int fr_reduce_dev(int curve, size_t n, void* v);

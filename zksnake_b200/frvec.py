@@ -113,15 +113,16 @@ class FrVec:
         return out
 
     # ---- transforms ----
-    def ntt(self, size, inverse=False):
-        """N = next power of two >= size; input zero-padded / truncated to N (polynomial.rs:536-571)."""
+    def ntt(self, size, inverse=False, coset=0):
+        """N = next power of two >= size; input zero-padded / truncated to N (polynomial.rs:536-571).  coset: 0 plain, 1 the
+        reference's coset (offset = the domain's own generator), 2 the coset g<w> of the field's multiplicative generator."""
         log_n = max(int(size) - 1, 0).bit_length()
         out = FrVec(self.curve, 1 << log_n)
-        nat.check(nat.lib.zkb_ntt_dev(self.curve, 1 if inverse else 0, 0, log_n, self.ptr, self.n, out.ptr))
+        nat.check(nat.lib.zkb_ntt_dev(self.curve, 1 if inverse else 0, coset, log_n, self.ptr, self.n, out.ptr))
         return out
 
-    def intt(self, size=None):
-        return self.ntt(self.n if size is None else size, inverse=True)
+    def intt(self, size=None, coset=0):
+        return self.ntt(self.n if size is None else size, inverse=True, coset=coset)
 
     # ---- element-wise ----
     def _binary(self, op, other, n=None):

@@ -7,8 +7,9 @@ computed, never WHICH polynomial:
     GPU wants it instead of the reference's 15 transforms on the 4n domain and 6 on the 8n domain (protocol.py:240-262,
     284-300, 338-352 with polynomial.py:126-165): every factor polynomial has degree < 4n, so it is evaluated on ONE coset
     g<omega_4n> (5 coset transforms of size 4n: A, B, C, Z, PI; the selectors, sigma polynomials and L1 are pre-evaluated in
-    setup; id_k(x) = k x needs no transform; Z(omega x) is a rotation by 4), the numerator is formed pointwise, divided
-    pointwise by X^n - 1 (four distinct values on that coset) and brought back with ONE inverse coset transform.  The
+    setup; id_k(x) = k x needs no transform; Z(omega x) is a rotation by 4), the numerator is formed and divided by X^n - 1
+    (four distinct values on that coset) pointwise by ONE fused kernel (zkb_plonk_quotient_dev) and brought back with ONE
+    inverse coset transform.  The
     grand-product numerators and denominators are read off the witness values directly (the blinding terms vanish on H);
   * the grand-product accumulator (protocol.py:302-313: batch_modinv + a Python loop) is a batch-inversion kernel, a pointwise
     product and an exclusive prefix-product scan;
@@ -117,13 +118,12 @@ class DevicePlonk(Plonk):
         l1 = FrVec.zeros(cid, n)
         l1.add_sparse({0: 1})
         self.l1_coset = self._coset_ntt(l1.intt())
-        self.x_coset = FrVec.powers(cid, N4, omega4, g)                        # the coset points g omega_4n^i
-        self.ones4 = FrVec.powers(cid, N4, 1)
         per = N4 // n                                                          # 4 (or 8): omega_NQ^n is a primitive per-th root of unity
         i4 = pow(omega4, n, p)
         gn = pow(g, n, p)
         zh_inv = [pow((gn * pow(i4, k, p) - 1) % p, -1, p) for k in range(per)]  # 1 / (x^n - 1) at coset point i depends on i mod per
-        self.zh_inv_coset = FrVec.from_limbs(cid, np.tile(nat.ints_to_limbs(zh_inv), (n, 1)), reduce=False)
+        self.zh_inv_words = nat.ints_to_limbs(zh_inv)
+        self.omega_q = omega4
         self.roots, self.sigma_ev = roots, sigma_ev
         self.proving_key = ProvingKey(n, self.G1_tau, selector_poly, None, permutation_poly, None, tau_selector, tau_permutation,
                                       None, self.E.name)
@@ -133,11 +133,10 @@ class DevicePlonk(Plonk):
 
     def _coset_ntt(self, poly):
         """evaluations of a polynomial (fewer than 4n coefficients) on the coset g <omega_4n>"""
-        return poly.mul_powers(self.coset_g).ntt(self.NQ)
+        return poly.ntt(self.NQ, coset=2)          # the pre-scaling by g^j is folded into the transform's first pass
 
     def _coset_intt(self, evals):
-        p = self.order
-        return evals.intt().mul_powers(pow(self.coset_g, -1, p))
+        return evals.intt(coset=2)                 # ... and the g^-j / N into its last pass
 
     # -------------------------------------------------------------------------------------------------------------- prove
     def prove(self, public_witness: dict, private_witness: list):
@@ -217,24 +216,15 @@ class DevicePlonk(Plonk):
         alpha = tr.get_challenge_scalar()
         Z_omega = Z.mul_powers(omega)                                          # Z(omega X), needed as coefficients in round 4
         Ac, Bc, Cc, Zc, PIc = (self._coset_ntt(x) for x in (A, B, C, Z, PI))
-        numer = Ac.mul(selc["L"]).add(Bc.mul(selc["R"])).add(Cc.mul(selc["O"])).add(Ac.mul(Bc).mul(selc["M"])) \
-            .add(selc["C"]).add(PIc)                                            # the gate polynomial G
-        nomc = denc = None
-        for wc, kk, sc in zip((Ac, Bc, Cc), (1, K1, K2), sigc):
-            f_id = self.ones4.axpy(gamma, self.x_coset.axpy(beta * kk % p, wc))   # W(x) + beta k x + gamma
-            f_sg = self.ones4.axpy(gamma, sc.axpy(beta, wc))                      # W(x) + beta sigma(x) + gamma
-            nomc = f_id if nomc is None else nomc.mul(f_id)
-            denc = f_sg if denc is None else denc.mul(f_sg)
-        del Ac, Bc, Cc, PIc
-        rot = N4 // n                                                          # omega = omega_NQ^rot
-        Zwc = FrVec(cid, N4)                                                   # Z(omega x) on the coset: a rotation by `rot`
-        nat.check(nat.lib.zkb_d2d(Zwc.ptr, Zc.at(rot), (N4 - rot) * 32))
-        nat.check(nat.lib.zkb_d2d(Zwc.at(N4 - rot), Zc.ptr, rot * 32))
-        numer = nomc.mul(Zc).sub(denc.mul(Zwc)).axpy(alpha, numer)
-        numer = Zc.sub(self.ones4).mul(self.l1_coset).axpy(alpha * alpha % p, numer)
-        del nomc, denc, Zwc, Zc
-        Tq = self._coset_intt(numer.mul(self.zh_inv_coset))                    # 4n coefficients; deg T <= 3n + 5
-        del numer
+        # numerator / (X^n - 1) on the coset in ONE fused kernel (csrc/frvec.cu: plonk_quotient_kernel)
+        ins = [Ac, Bc, Cc, Zc, PIc, selc["L"], selc["R"], selc["O"], selc["M"], selc["C"], sigc[0], sigc[1], sigc[2], self.l1_coset]
+        ptrs = (ctypes.c_void_p * 14)(*[v.ptr for v in ins])
+        w = lambda x: nat.ptr(nat.ints_to_limbs([int(x) % p]))  # noqa: E731
+        Tc = FrVec(cid, N4)
+        nat.check(nat.lib.zkb_plonk_quotient_dev(cid, N4, n, ptrs, w(self.coset_g), w(self.omega_q), w(beta), w(gamma), w(alpha),
+                                                 nat.ptr(self.zh_inv_words), Tc.ptr))
+        Tq = self._coset_intt(Tc)                                              # 4n coefficients; deg T <= 3n + 5
+        del Ac, Bc, Cc, Zc, PIc, Tc, ins
         # the reference asserts a zero remainder (protocol.py:354-360): here an unsatisfied gate shows up as non-zero
         # coefficients above degree 3n + 5 -- tested by evaluating that tail at two points (Schwartz-Zippel; the points come
         # from the transcript challenge, not from the blinding stream, so the proof bytes stay those of the reference's order)

@@ -154,9 +154,10 @@ int zkb_msm_table_info(const zkb_msm_table* t, uint32_t* window_bits, uint32_t* 
 int zkb_msm_table_dev(zkb_msm_table* t, const void* d_scalars, size_t n_scalars, uint32_t wrank, uint32_t wworld,
                       uint64_t* out_xy, int* out_inf);
 /* `count` (<= 8) MSMs over the same table as one batch: the accumulations run back to back, the latency-bound bucket
- * reductions overlap on side streams (the three commitments of a PlonK round).  out_xy: count affine points, tightly packed. */
-int zkb_msm_table_batch_dev(zkb_msm_table* t, int count, const void* const* d_scalars, const size_t* n_scalars, uint64_t* out_xy,
-                            int* out_inf);
+ * reductions overlap on side streams (the three commitments of a PlonK round).  out_xy: count affine points, tightly packed.
+ * wrank / wworld: window shard as in zkb_msm_table_dev (0, 1 = the whole MSMs). */
+int zkb_msm_table_batch_dev(zkb_msm_table* t, int count, const void* const* d_scalars, const size_t* n_scalars, uint32_t wrank,
+                            uint32_t wworld, uint64_t* out_xy, int* out_inf);
 
 /* ---- Groth16 ---------------------------------------------------------------------------------------------- */
 /* a, b, c: the vectors A.w, B.w, C.w (n = 2^log_n each).  u, v, w, h receive n coefficients each (h[n-1] = 0).

@@ -118,3 +118,36 @@ def test_partial_msm_exchange_world_size_2_gloo(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def _gather_worker(rank, world, port, q):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import numpy as np
+    import torch.distributed as td
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    from zksnake_b200 import dist
+    arr = np.arange(6, dtype=np.uint64).reshape(2, 3) + 100 * rank
+    got = dist.all_gather_array(arr)
+    rnd = dist.shared_random(lambda n_max: 12345 + rank)     # each rank would draw something different on its own
+    vals = [rnd(10 ** 30) for _ in range(3)]
+    q.put((rank, got.tolist(), vals))
+    td.destroy_process_group()
+
+
+def test_all_gather_array_and_shared_random_gloo():
+    """world-size-2 gloo run of the helpers the multi-GPU provers rely on: every rank sees every rank's array, and the shared
+    random stream is identical everywhere (it is derived from rank 0's draw)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29631
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    want = [[[0, 1, 2], [3, 4, 5]], [[100, 101, 102], [103, 104, 105]]]
+    assert res[0][1] == want and res[1][1] == want
+    assert res[0][2] == res[1][2] and len(set(res[0][2])) == 3 and all(1 <= v <= 10 ** 30 for v in res[0][2])

@@ -168,3 +168,35 @@ def test_device_prover_2p16_verifies(gpu):
     assert plonk.verify(proof, pub)
     k = next(iter(pub))
     assert not plonk.verify(proof, {k: (pub[k] + 1) % plonk.order})
+
+
+def test_commitment_window_shards_add_up(gpu):
+    """DevicePlonk with shard=(r, W): each "rank" returns its window shard of every commitment; emulated here by calling the
+    batch MSM for every shard and adding the partial points -- must equal the single-rank commitments."""
+    import ctypes
+
+    import numpy as np
+
+    from zksnake_b200 import _native as nat
+    from zksnake_b200.frvec import FrVec
+    from zksnake_b200.plonk_device import DevicePlonk
+    from zksnake_b200.plonkish import chain_gates
+    cs, pub, priv = chain_gates(300, "BN254")
+    plonk = DevicePlonk(cs, "BN254")
+    plonk.setup()
+    r = plonk.order
+    rnd = random.Random(8)
+    vecs = [FrVec.from_ints(0, [rnd.randrange(r) for _ in range(k)]) for k in (512, 518, 100)]
+    want = plonk._commit_many(vecs)
+    limbs = nat.lib.zkb_affine_bytes(0, 1) // 8
+    world = 3
+    acc = [plonk.E.curve.PointG1.identity() for _ in vecs]
+    for rank in range(world):
+        ptrs = (ctypes.c_void_p * 3)(*[v.ptr for v in vecs])
+        lens = (ctypes.c_size_t * 3)(*[v.n for v in vecs])
+        xy = np.zeros((3, limbs), dtype=np.uint64)
+        inf = (ctypes.c_int * 3)()
+        nat.check(nat.lib.zkb_msm_table_batch_dev(plonk.table, 3, ptrs, lens, rank, world, nat.ptr(xy), inf))
+        for i in range(3):
+            acc[i] = acc[i] + plonk.E.curve.PointG1._from_flat(xy[i], inf[i])
+    assert acc == want

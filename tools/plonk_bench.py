@@ -22,14 +22,21 @@ def main():
     curve = sys.argv[2] if len(sys.argv) > 2 else "BN254"
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
     n = 1 << log_n
-    nat.ensure_init()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    td = None
+    if world > 1:   # torchrun: one process per GPU; the commitment MSMs are window-sharded, everything else is replicated
+        import torch
+        import torch.distributed as td
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        td.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+    nat.ensure_init(int(os.environ.get("LOCAL_RANK", "0")))
     t0 = time.perf_counter()
     cs, pub, priv = chain_gates(n, curve)
     t_circuit = time.perf_counter() - t0
     import random
     rnd = random.Random(3)
     pm.get_random_int = lambda n_max: rnd.randint(1, n_max)
-    plonk = DevicePlonk(cs, curve)
+    plonk = DevicePlonk(cs, curve, shard=(rank, world))
     t0 = time.perf_counter()
     plonk.setup()
     t_setup = time.perf_counter() - t0
@@ -49,6 +56,8 @@ def main():
     nat.check(nat.lib.zkb_prof_enable(1))
     l0 = nat.lib.zkb_launch_count()
     for _ in range(steps):
+        if td is not None:
+            td.barrier()
         t0 = time.perf_counter()
         proof = plonk.prove_packed(pub, cols)
         blob = proof.to_bytes()
@@ -67,7 +76,16 @@ def main():
         "gpu_launches": int(launches), "verify": bool(ok), "proof_bytes": len(blob),
         "setup_s": t_setup, "circuit_s": t_circuit,
     }
-    print(json.dumps(line), flush=True)
+    line["n_gpus"] = world
+    line["proof_sha"] = __import__("hashlib").sha256(blob).hexdigest()[:16]
+    if td is not None:
+        import torch
+        t = torch.tensor([line["value"]], dtype=torch.float64, device="cuda")
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        line["value"] = float(t.item())
+        td.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -76,7 +76,7 @@ def _load():
         "zkb_msm_table_free": (None, [c_vp]),
         "zkb_msm_table_info": (c_int, [c_vp, ctypes.POINTER(c_u32), ctypes.POINTER(c_u32), ctypes.POINTER(c_sz)]),
         "zkb_msm_table_dev": (c_int, [c_vp, c_vp, c_sz, c_u32, c_u32, c_vp, ctypes.POINTER(c_int)]),
-        "zkb_msm_table_batch_dev": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+        "zkb_msm_table_batch_dev": (c_int, [c_vp, c_int, c_vp, c_vp, c_u32, c_u32, c_vp, c_vp]),
         "zkb_groth16_pk_build_tables": (c_int, [c_vp, c_u32]),
         "zkb_msm_dev_windows": (c_int, [c_int, c_int, c_vp, c_vp, c_sz, c_u32, c_u32, c_vp, ctypes.POINTER(c_int)]),
         "zkb_groth16_pk_set_window_shard": (c_int, [c_vp, c_u32, c_u32]),

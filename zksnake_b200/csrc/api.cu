@@ -205,8 +205,8 @@ int zkb_msm_table_info(const zkb_msm_table* t, uint32_t* window_bits, uint32_t* 
   if (bytes) *bytes = (size_t)t->W * t->n * affine_bytes(t->curve, t->group);
   return ZKB_OK;
 }
-int zkb_msm_table_batch_dev(zkb_msm_table* t, int count, const void* const* d_scalars, const size_t* n_scalars, uint64_t* out_xy,
-                            int* out_inf) {
+int zkb_msm_table_batch_dev(zkb_msm_table* t, int count, const void* const* d_scalars, const size_t* n_scalars, uint32_t wrank,
+                            uint32_t wworld, uint64_t* out_xy, int* out_inf) {
   NEED_INIT();
   if (!t) return set_error(ZKB_ERR_ARG, "null table");
   if (count < 1 || count > 8) return set_error(ZKB_ERR_ARG, "msm batch: 1..8 jobs");
@@ -217,7 +217,7 @@ int zkb_msm_table_batch_dev(zkb_msm_table* t, int count, const void* const* d_sc
     jobs[i] = MsmJob{t->group, t->d_table, d_scalars[i], n_scalars[i], t->c, t->n};
   }
   int rc;
-  if ((rc = msm_enqueue_batch(t->curve, jobs, count, 0, 1, tk))) return rc;
+  if ((rc = msm_enqueue_batch(t->curve, jobs, count, wrank, wworld, tk))) return rc;
   const size_t limbs = affine_bytes(t->curve, t->group) / 8;
   for (int i = 0; i < count; i++)
     if ((rc = msm_finish(&tk[i], out_xy + i * limbs, &out_inf[i]))) return rc;

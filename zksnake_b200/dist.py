@@ -78,3 +78,41 @@ def add_partials(curve, all_xy, all_inf):
         out_xy[slot, :limbs] = res
         out_inf[slot] = inf.value
     return out_xy, out_inf
+
+
+def all_gather_array(arr, device=None):
+    """all-gather of one small numpy array per rank (same shape and dtype everywhere) -> array of shape (world,) + arr.shape.
+    NCCL on GPUs (the payload is staged through a CUDA tensor), gloo on CPU; identity when not distributed."""
+    import torch
+    import torch.distributed as td
+    rank, ws = world()
+    if ws == 1:
+        return arr[None].copy()
+    flat = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+    t = torch.from_numpy(flat.copy())
+    if td.get_backend() == "nccl":
+        t = t.cuda(device) if device is not None else t.cuda()
+    out = torch.empty(ws * t.numel(), dtype=torch.uint8, device=t.device)
+    td.all_gather_into_tensor(out, t)
+    return out.cpu().numpy().view(arr.dtype).reshape((ws,) + arr.shape)
+
+
+def shared_random(draw):
+    """Randomness every rank agrees on.  `draw(n_max)` is the module's get_random_int hook (uniform in [1, n_max]).  With one
+    rank this IS `draw`.  With several, rank 0 draws one 256-bit seed, it is all-gathered once, and every rank expands it with
+    blake2b in counter mode -- toxic waste, prover randomness and blinding scalars must be identical everywhere, otherwise the
+    ranks' partial sums belong to different keys / proofs."""
+    import hashlib
+    rank, ws = world()
+    if ws == 1:
+        return draw
+    seed = np.frombuffer(int(draw((1 << 256) - 1)).to_bytes(32, "little"), dtype=np.uint8).copy()
+    seed = bytes(all_gather_array(seed)[0])
+    state = {"ctr": 0}
+
+    def shared(n_max):
+        state["ctr"] += 1
+        h = hashlib.blake2b(seed + state["ctr"].to_bytes(8, "little"), digest_size=64).digest()
+        return 1 + int.from_bytes(h, "little") % n_max
+
+    return shared

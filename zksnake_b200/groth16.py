@@ -111,7 +111,8 @@ class Groth16:
         o = self.order
         ec = self.ec
         G1, G2 = ec.g1(), ec.g2()
-        tau, alpha, beta, gamma, delta = (get_random_int(o - 1) for _ in range(5))
+        rand = dist.shared_random(get_random_int) if self.world > 1 else get_random_int   # all ranks need the SAME toxic waste
+        tau, alpha, beta, gamma, delta = (rand(o - 1) for _ in range(5))
         self.toxic = (tau, alpha, beta, gamma, delta)
         inv_gamma, inv_delta = pow(gamma, -1, o), pow(delta, -1, o)
         n, m = self.n, self.m
@@ -195,8 +196,9 @@ class Groth16:
         assert self.proving_key, "ProvingKey has not been generated"
         assert self.m - self.n_public == len(private_witness), \
             "Length of kdelta_1 and private_witness must be equal"
-        r = get_random_int(self.order - 1)
-        s = get_random_int(self.order - 1)
+        rand = dist.shared_random(get_random_int) if self.world > 1 else get_random_int
+        r = rand(self.order - 1)
+        s = rand(self.order - 1)
         w = nat.ints_to_limbs([int(x) % self.order for x in list(public_witness) + list(private_witness)])
         try:
             return self.prove_packed(w, r, s)

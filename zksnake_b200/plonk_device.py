@@ -27,6 +27,7 @@ import time
 import numpy as np
 
 from . import _native as nat
+from . import dist
 from . import plonk as _plonk
 from .frvec import FrVec
 from .plonk import K1, K2, Plonk, Proof, ProvingKey, VerifyingKey
@@ -35,33 +36,45 @@ from .transcript import FiatShamirTranscript
 
 
 class DevicePlonk(Plonk):
-    def __init__(self, constraints, curve="BN254"):
+    def __init__(self, constraints, curve="BN254", shard=None):
+        """shard = (rank, world): one process per GPU (torch.distributed); every rank runs the whole protocol but only its window
+        shard of each commitment MSM, and the partial points are all-gathered and added (zksnake_b200/dist.py) -- every rank ends
+        up with the same commitments, the same transcript and the same proof.  Default: the torch.distributed world, else (0, 1)."""
         super().__init__(constraints, curve)
+        self.rank, self.world = shard if shard is not None else dist.world()
         self.cid = self.E.curve.CURVE_ID
         self.table = None      # fixed-base table of the SRS
         self.timings = {}
 
     # ------------------------------------------------------------------------------------------------------------ helpers
     def _commit(self, vec, count=None):
-        """[P(tau)]G1 for the coefficient vector `vec` (first `count` coefficients)."""
-        count = vec.n if count is None else count
-        assert count <= self.srs_len, "polynomial longer than the SRS"
-        ab = nat.lib.zkb_affine_bytes(self.cid, 1)
-        out = np.zeros(ab // 8, dtype=np.uint64)
-        inf = ctypes.c_int(0)
-        nat.check(nat.lib.zkb_msm_table_dev(self.table, vec.ptr, count, 0, 1, nat.ptr(out), ctypes.byref(inf)))
-        return self.E.curve.PointG1._from_flat(out, inf.value)
+        """[P(tau)]G1 for the coefficient vector `vec`."""
+        return self._commit_many([vec])[0]
 
     def _commit_many(self, vecs):
-        """several commitments as one MSM batch (zkb_msm_table_batch_dev): reductions overlap the next accumulation"""
+        """several commitments as one MSM batch (zkb_msm_table_batch_dev): reductions overlap the next accumulation.  With more
+        than one rank each computes its window shard and the partial points are all-gathered and added."""
         k = len(vecs)
         limbs = nat.lib.zkb_affine_bytes(self.cid, 1) // 8
         ptrs = (ctypes.c_void_p * k)(*[v.ptr for v in vecs])
         lens = (ctypes.c_size_t * k)(*[min(v.n, self.srs_len) for v in vecs])
-        out = np.zeros((k, limbs), dtype=np.uint64)
+        out = np.zeros((k, limbs + 1), dtype=np.uint64)      # last column: infinity flag
+        xy = np.zeros((k, limbs), dtype=np.uint64)
         inf = (ctypes.c_int * k)()
-        nat.check(nat.lib.zkb_msm_table_batch_dev(self.table, k, ptrs, lens, nat.ptr(out), inf))
-        return [self.E.curve.PointG1._from_flat(out[i], inf[i]) for i in range(k)]
+        nat.check(nat.lib.zkb_msm_table_batch_dev(self.table, k, ptrs, lens, self.rank, self.world, nat.ptr(xy), inf))
+        P = self.E.curve.PointG1
+        if self.world == 1:
+            return [P._from_flat(xy[i], inf[i]) for i in range(k)]
+        out[:, :limbs] = xy
+        out[:, limbs] = [inf[i] for i in range(k)]
+        parts = dist.all_gather_array(out)                   # (world, k, limbs + 1)
+        res = []
+        for i in range(k):
+            acc = P.identity()
+            for r in range(self.world):
+                acc = acc + P._from_flat(np.ascontiguousarray(parts[r, i, :limbs]), int(parts[r, i, limbs]))
+            res.append(acc)
+        return res
 
     def __del__(self):
         try:
@@ -78,7 +91,7 @@ class DevicePlonk(Plonk):
         p, cs, cid = self.order, self.constraints, self.cid
         n = cs.length
         assert n >= 4, "PlonK needs at least 4 gates (the blinding polynomials have up to 3 coefficients)"
-        tau = _plonk.get_random_int(p - 1)
+        tau = (dist.shared_random(_plonk.get_random_int) if self.world > 1 else _plonk.get_random_int)(p - 1)
         self.tau = tau
         self.srs_len = n + 6
         # [tau^i]G1: powers on the device, then the fixed-base scalar-multiplication kernel; table for the prover's MSMs
@@ -88,7 +101,7 @@ class DevicePlonk(Plonk):
         nat.check(nat.lib.zkb_batch_mul_dev(cid, 1, gen.ptr, 1, powers.ptr, self.srs_len, self.G1_tau.ptr))
         self.G2_tau = self.E.G2() * tau
         tab = ctypes.c_void_p()
-        nat.check(nat.lib.zkb_msm_table_create(cid, 1, self.G1_tau.ptr, self.srs_len, 0, 1, ctypes.byref(tab)))
+        nat.check(nat.lib.zkb_msm_table_create(cid, 1, self.G1_tau.ptr, self.srs_len, 0, self.world, ctypes.byref(tab)))
         self.table = tab
 
         omega = get_evaluation_point(n, 1, p)
@@ -153,7 +166,7 @@ class DevicePlonk(Plonk):
         pk, p, cid = self.proving_key, self.order, self.cid
         n, N4 = pk.n, self.NQ
         omega = self.omega
-        rnd = _plonk.get_random_int
+        rnd = dist.shared_random(_plonk.get_random_int) if self.world > 1 else _plonk.get_random_int
         sel, sig = pk.selector_poly, pk.permutation_poly
         selc, sigc = self.selector_coset, self.sigma_coset
         T = {}

@@ -69,11 +69,17 @@ class DevicePlonk(Plonk):
         out[:, limbs] = [inf[i] for i in range(k)]
         parts = dist.all_gather_array(out)                   # (world, k, limbs + 1)
         res = []
-        for i in range(k):
-            acc = P.identity()
-            for r in range(self.world):
-                acc = acc + P._from_flat(np.ascontiguousarray(parts[r, i, :limbs]), int(parts[r, i, limbs]))
-            res.append(acc)
+        ws = self.world
+        for i in range(k):                                   # one host linear combination (exact group law) per commitment
+            pts = np.ascontiguousarray(parts[:, i, :limbs])
+            infs = np.ascontiguousarray(parts[:, i, limbs].astype(np.int32))
+            scal = np.zeros((ws, 4), dtype=np.uint64)
+            has = np.zeros(ws, dtype=np.int32)
+            acc = np.zeros(limbs, dtype=np.uint64)
+            ainf = ctypes.c_int()
+            nat.check(nat.lib.zkb_point_lincomb(self.cid, 1, ws, nat.ptr(pts), nat.ptr(infs), nat.ptr(scal), nat.ptr(has),
+                                                nat.ptr(acc), ctypes.byref(ainf)))
+            res.append(P._from_flat(acc, ainf.value))
         return res
 
     def __del__(self):

@@ -206,6 +206,9 @@ int zkb_r1cs_create(int curve, size_t n_rows, size_t n_cols, const uint64_t* con
 void zkb_r1cs_free(zkb_r1cs* r1cs);
 /* a = A.w etc. into host buffers (n_out elements each, rows >= n_rows are zero) */
 int zkb_r1cs_eval(zkb_r1cs* r1cs, const uint64_t* witness, size_t n_out, uint64_t* a, uint64_t* b, uint64_t* c);
+/* the same with the vector and the three products resident on the device (asynchronous).  With the TRANSPOSED matrices and the
+ * Lagrange coefficients L_i(tau) as the vector this is the L / R / O loop of Groth16.setup (groth16/protocol.py:64-77). */
+int zkb_r1cs_eval_dev(zkb_r1cs* r1cs, const void* d_witness, size_t n_out, void* d_a, void* d_b, void* d_c);
 /* Groth16.prove(public + private witness) end to end: witness (m = n_cols canonical scalars, public part first, n_public of
  * them) is the ONLY per-proof host->device traffic; outputs as zkb_groth16_prove. */
 int zkb_groth16_prove_witness(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const uint64_t* witness, size_t n_public,

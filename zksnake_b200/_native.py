@@ -94,6 +94,7 @@ def _load():
         "zkb_r1cs_create": (c_int, [c_int, c_sz, c_sz, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)]),
         "zkb_r1cs_free": (None, [c_vp]),
         "zkb_r1cs_eval": (c_int, [c_vp, c_vp, c_sz, c_vp, c_vp, c_vp]),
+        "zkb_r1cs_eval_dev": (c_int, [c_vp, c_vp, c_sz, c_vp, c_vp, c_vp]),
         "zkb_groth16_prove_witness": (c_int, [c_vp, c_vp, c_vp, c_sz, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "zkb_groth16_prove_witness_dev": (c_int, [c_vp, c_vp, c_vp, c_sz, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "zkb_groth16_partial": (c_int, [c_vp, c_vp, c_vp, c_int, c_sz, c_vp, c_vp]),

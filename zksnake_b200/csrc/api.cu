@@ -633,6 +633,14 @@ int zkb_r1cs_eval(zkb_r1cs* r, const uint64_t* witness, size_t n_out, uint64_t* 
   return ZKB_OK;
 }
 
+int zkb_r1cs_eval_dev(zkb_r1cs* r, const void* d_witness, size_t n_out, void* d_a, void* d_b, void* d_c) {
+  NEED_INIT();
+  if (!r) return set_error(ZKB_ERR_ARG, "null r1cs");
+  int rc;
+  if ((rc = r1cs_load_witness(r, d_witness, 1))) return rc;
+  return r1cs_spmv3(r, n_out, d_a, d_b, d_c);
+}
+
 static int prove_witness_checks(zkb_groth16_pk* pk, zkb_r1cs* r1cs, size_t n_public) {
   if (!pk || !r1cs) return set_error(ZKB_ERR_ARG, "null proving key or r1cs");
   if (pk->curve != r1cs->curve) return set_error(ZKB_ERR_ARG, "proving key and r1cs are on different curves");

@@ -15,6 +15,7 @@ import numpy as np
 from . import _native as nat
 from . import dist
 from ._algebra import ec_bls12_381, ec_bn254, polynomial_bls12_381, polynomial_bn254
+from .frvec import FrVec
 from .r1cs import R1CS
 
 _CURVES = {"BN128": 0, "BN254": 0, "ALT_BN128": 0, "BLS12_381": 1}
@@ -116,12 +117,22 @@ class Groth16:
         self.toxic = (tau, alpha, beta, gamma, delta)
         inv_gamma, inv_delta = pow(gamma, -1, o), pow(delta, -1, o)
         n, m = self.n, self.m
-        lagrange = self.poly.evaluate_lagrange_coefficients(n, tau)
-        L, R, O = [0] * m, [0] * m, [0] * m
-        for arr, acc in ((self.r1cs.A, L), (self.r1cs.B, R), (self.r1cs.C, O)):
-            for row, col, value in arr.triplets:
-                acc[col] += lagrange[row] * value
-        K = [(L[i] * beta + R[i] * alpha + O[i]) % o for i in range(m)]
+        # L_i(tau) on the device: one inverse transform of the powers of tau (polynomial.rs:646-652)
+        lagrange = FrVec.powers(self.curve, n, tau).intt()
+        # L = A^T lambda, R = B^T lambda, O = C^T lambda (protocol.py:64-77) as a device SpMV over the transposed matrices, then
+        # K = beta L + alpha R + O -- no Python loop over the triplets
+        csr_t = [arr.to_csr_transposed(m) for arr in (self.r1cs.A, self.r1cs.B, self.r1cs.C)]
+        vp3 = ctypes.c_void_p * 3
+        ht = ctypes.c_void_p()
+        nat.check(nat.lib.zkb_r1cs_create(self.curve, m, n, vp3(*[c[0].ctypes.data for c in csr_t]),
+                                          vp3(*[c[1].ctypes.data if len(c[1]) else None for c in csr_t]),
+                                          vp3(*[c[2].ctypes.data if len(c[2]) else None for c in csr_t]), ctypes.byref(ht)))
+        L, R, O = (FrVec(self.curve, m) for _ in range(3))
+        nat.check(nat.lib.zkb_r1cs_eval_dev(ht, lagrange.ptr, m, L.ptr, R.ptr, O.ptr))
+        K = L.axpy(beta, R.axpy(alpha, O))
+        nat.check(nat.lib.zkb_sync())
+        nat.lib.zkb_r1cs_free(ht)
+        del csr_t, L, R, O, lagrange
         t = self.poly.evaluate_vanishing_polynomial(n, tau)
 
         by_points = self.shard_mode == "points"
@@ -150,13 +161,13 @@ class Groth16:
         n_priv = m - self.n_public
         klo, khi = dist.shard_range(n_priv, self.rank, self.world) if by_points else (0, n_priv)
         self._kslice = (klo, khi)
-        d_k = nat.DeviceBuffer(max(khi - klo, 1) * 32)
-        if khi > klo:
-            d_k.upload(nat.ints_to_limbs([k * inv_delta % o for k in K[self.n_public + klo:self.n_public + khi]]))
+        k_scaled = K.scale(inv_delta)                          # K_j / delta for the private columns of this rank's slice
+        d_k = k_scaled.copy(self.n_public + klo, self.n_public + khi, n=max(khi - klo, 1))
         k_delta_G1 = batch(G1, 1, d_k, khi - klo)
-        k_gamma_G1 = [G1 * (k * inv_gamma % o) for k in K[:self.n_public]]
-        for d in (d_pow, d_tgt, d_k):
+        k_gamma_G1 = [G1 * (k * inv_gamma % o) for k in K.to_ints(self.n_public)]
+        for d in (d_pow, d_tgt):
             d.free()
+        del k_scaled, d_k, K
         self.proving_key = ProvingKey(G1 * alpha, G1 * beta, G2 * beta, G1 * delta, G2 * delta, tau_G1, tau_G2, target_G1,
                                       k_delta_G1)
         self.verifying_key = VerifyingKey(G1 * alpha, G2 * beta, G2 * gamma, G2 * delta, k_gamma_G1)
@@ -179,7 +190,7 @@ class Groth16:
             nat.check(nat.lib.zkb_groth16_pk_set_window_shard(h, self.rank, self.world))
         if self.tables:
             nat.check(nat.lib.zkb_groth16_pk_build_tables(h, self.world if self.shard_mode == "windows" else 1))
-        n_rows = max((t[0] for arr in (self.r1cs.A, self.r1cs.B, self.r1cs.C) for t in arr.triplets), default=-1) + 1
+        n_rows = max((int(arr._arrays()[0].max()) for arr in (self.r1cs.A, self.r1cs.B, self.r1cs.C) if arr.triplets), default=-1) + 1
         csr = [arr.to_csr(n_rows) for arr in (self.r1cs.A, self.r1cs.B, self.r1cs.C)]
         self._csr = csr
         vp3 = ctypes.c_void_p * 3

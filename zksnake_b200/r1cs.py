@@ -39,17 +39,40 @@ class SparseArray:
             result[row] += vector[col] * value
         return [x % self.p for x in result]
 
+    def _arrays(self):
+        """(rows, cols int64 arrays, values as (nnz, 4) uint64 limbs mod p) of the triplet list, without per-element Python big-int
+        work when the values are small (the common case: R1CS coefficients are mostly +-1 and small constants)."""
+        trip = self.triplets
+        nnz = len(trip)
+        cached = getattr(self, "_arrays_cache", None)
+        if cached is not None and cached[0] == nnz:
+            return cached[1]
+        rows = np.fromiter((t[0] for t in trip), dtype=np.int64, count=nnz)
+        cols = np.fromiter((t[1] for t in trip), dtype=np.int64, count=nnz)
+        vals = np.zeros((nnz, 4), dtype=np.uint64)
+        p = self.p
+        try:
+            vals[:, 0] = np.fromiter((t[2] for t in trip), dtype=np.uint64, count=nnz)     # all values in [0, 2^64)
+        except (OverflowError, ValueError):
+            vals = nat.ints_to_limbs([t[2] % p for t in trip], 32) if nnz else vals
+        self._arrays_cache = (nnz, (rows, cols, vals))     # (append() only ever grows the list, so the length is the version)
+        return rows, cols, vals
+
+    def _csr(self, major, minor, vals, n_major):
+        order = np.argsort(major, kind="stable")
+        ptr = np.zeros(n_major + 1, dtype=np.uint64)
+        np.cumsum(np.bincount(major, minlength=n_major), out=ptr[1:])
+        return ptr, minor[order].astype(np.uint32), np.ascontiguousarray(vals[order])
+
     def to_csr(self, n_rows):
         """(row_ptr uint64[n_rows+1], col uint32[nnz], val uint64[nnz,4]) sorted by row."""
-        p = self.p
-        trip = sorted(self.triplets, key=lambda t: t[0])
-        row_ptr = np.zeros(n_rows + 1, dtype=np.uint64)
-        for row, _, _ in trip:
-            row_ptr[row + 1] += 1
-        row_ptr = np.cumsum(row_ptr, dtype=np.uint64)
-        col = np.array([t[1] for t in trip], dtype=np.uint32)
-        val = nat.ints_to_limbs([t[2] % p for t in trip], 32) if trip else np.zeros((0, 4), dtype=np.uint64)
-        return row_ptr, col, val
+        rows, cols, vals = self._arrays()
+        return self._csr(rows, cols, vals, n_rows)
+
+    def to_csr_transposed(self, n_cols):
+        """CSR of the transposed matrix (one row per COLUMN of this one): (ptr uint64[n_cols+1], row uint32[nnz], val)."""
+        rows, cols, vals = self._arrays()
+        return self._csr(cols, rows, vals, n_cols)
 
 
 class R1CS:

@@ -48,6 +48,7 @@ extern "C" {
 #define ZKB_ERR_DOMAIN (-4)        /* "Domain size is too large"                  -> ValueError   (polynomial.rs:638-639) */
 #define ZKB_ERR_NOT_DIVISIBLE (-5) /* "(U * V - W) did not divided by Z to zero"  -> ValueError   (qap.py:68-69) */
 #define ZKB_ERR_NOINIT (-6)        /* zkb_init not called                         -> RuntimeError */
+#define ZKB_ERR_POINT (-7)         /* "Cannot deserialize point"                  -> ValueError   (curve.rs:134-141) */
 
 #define ZKB_VEC_MUL 0
 #define ZKB_VEC_ADD 1
@@ -126,6 +127,21 @@ int zkb_fr_add_sparse_dev(int curve, void* d_vec, size_t k, const uint64_t* idx,
 size_t zkb_affine_bytes(int curve, int group);
 int zkb_points_upload(int curve, int group, const uint64_t* pts, size_t n, void* d_out);    /* canonical -> device Montgomery */
 int zkb_points_download(int curve, int group, const void* d_pts, size_t n, uint64_t* out);  /* device Montgomery -> canonical */
+
+/* Bulk wire format.  The reference's keys and proofs are concatenated ark-serialize COMPRESSED
+ * points: PointG1/PointG2.to_bytes / from_bytes (src/bn254/curve.rs:127-141, 300-314; bls12_381/curve.rs likewise), looped
+ * over a key one from_hex call per point by python/zksnake/groth16/serialization.py:70-159,181-220,
+ * plonk/serialization.py:157-173,255-262 and ecc.py:128-142.  One kernel launch per vector here.
+ *   zkb_compressed_bytes: 32 / 64 (BN254 G1 / G2), 48 / 96 (BLS12-381).
+ *   zkb_points_compress:   n device points -> n encodings in host memory.
+ *   zkb_points_decompress: n encodings in host memory -> n device points.  validate != 0 adds the prime-order subgroup check
+ *     (ark's Validate::Yes, what from_bytes does); flags, x < q, "infinity has x = 0" and "x^3 + b is a square" are always
+ *     checked.  On an invalid encoding returns ZKB_ERR_POINT with *bad_index = the first offending point and *reason =
+ *     1 flags | 2 coordinate not in field | 3 non-zero infinity | 4 not on curve | 5 not in the subgroup (both optional). */
+size_t zkb_compressed_bytes(int curve, int group);
+int zkb_points_compress(int curve, int group, const void* d_pts, size_t n, uint8_t* out);
+int zkb_points_decompress(int curve, int group, const uint8_t* in, size_t n, int validate, void* d_pts, long long* bad_index,
+                          int* reason);
 /* sum_i scalars[i] * pts[i].  n_points must equal n_scalars (else ZKB_ERR_MISMATCH).  out_xy: one affine point. */
 int zkb_msm(int curve, int group, const uint64_t* pts, size_t n_points, const uint64_t* scalars, size_t n_scalars,
             uint64_t* out_xy, int* out_inf);

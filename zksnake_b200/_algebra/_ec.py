@@ -103,6 +103,29 @@ class PointVector:
         assert 0 <= n <= self.n
         return PointVector(self.curve, self.group, n, buf=self.buf)
 
+    def to_bytes(self):
+        """The n ark-serialize compressed encodings, concatenated (what the reference's key serialisers produce by looping
+        PointG1/G2.to_bytes: groth16/serialization.py:131-159, plonk/serialization.py:255-262) -- one kernel launch."""
+        size = nat.lib.zkb_compressed_bytes(self.curve, self.group)
+        out = np.zeros(self.n * size, dtype=np.uint8)
+        nat.check(nat.lib.zkb_points_compress(self.curve, self.group, self.ptr, self.n, nat.ptr(out)))
+        return out.tobytes()
+
+    @classmethod
+    def from_bytes(cls, curve, group, data, validate=True):
+        """Inverse of to_bytes with the checks of from_bytes per point (flags, x < q, on the curve, in the subgroup); raises
+        ValueError("Cannot deserialize point: ...") naming the first offending index (ecc.py:128-142)."""
+        nat.ensure_init()
+        size = nat.lib.zkb_compressed_bytes(curve, group)
+        if len(data) % size:
+            raise ValueError("Cannot deserialize point: bad length")
+        n = len(data) // size
+        vec = cls(curve, group, n)
+        if n:
+            raw = np.frombuffer(bytes(data), dtype=np.uint8)
+            nat.check(nat.lib.zkb_points_decompress(curve, group, raw.ctypes.data, n, 1 if validate else 0, vec.ptr, None, None))
+        return vec
+
     def download(self):
         """-> uint64 array (n, affine_bytes/8), canonical coordinates (all-zero row = identity)."""
         out = np.zeros((self.n, self.affine_bytes // 8), dtype=np.uint64)

@@ -13,7 +13,7 @@ BN254, BLS12_381 = 0, 1
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libzkb200.so")
 
-ERR_CUDA, ERR_ARG, ERR_MISMATCH, ERR_DOMAIN, ERR_NOT_DIVISIBLE, ERR_NOINIT = -1, -2, -3, -4, -5, -6
+ERR_CUDA, ERR_ARG, ERR_MISMATCH, ERR_DOMAIN, ERR_NOT_DIVISIBLE, ERR_NOINIT, ERR_POINT = -1, -2, -3, -4, -5, -6, -7
 
 
 class ZkbError(RuntimeError):
@@ -70,6 +70,9 @@ def _load():
         "zkb_affine_bytes": (c_sz, [c_int, c_int]),
         "zkb_points_upload": (c_int, [c_int, c_int, c_vp, c_sz, c_vp]),
         "zkb_points_download": (c_int, [c_int, c_int, c_vp, c_sz, c_vp]),
+        "zkb_compressed_bytes": (c_sz, [c_int, c_int]),
+        "zkb_points_compress": (c_int, [c_int, c_int, c_vp, c_sz, c_vp]),
+        "zkb_points_decompress": (c_int, [c_int, c_int, c_vp, c_sz, c_int, c_vp, c_vp, c_vp]),
         "zkb_msm": (c_int, [c_int, c_int, c_vp, c_sz, c_vp, c_sz, c_vp, ctypes.POINTER(c_int)]),
         "zkb_msm_dev": (c_int, [c_int, c_int, c_vp, c_vp, c_sz, c_vp, ctypes.POINTER(c_int)]),
         "zkb_msm_table_create": (c_int, [c_int, c_int, c_vp, c_sz, c_u32, c_u32, ctypes.POINTER(c_vp)]),
@@ -125,7 +128,7 @@ def check(rc):
     if rc == 0:
         return
     msg = last_error()
-    if rc in (ERR_ARG, ERR_MISMATCH, ERR_DOMAIN, ERR_NOT_DIVISIBLE):
+    if rc in (ERR_ARG, ERR_MISMATCH, ERR_DOMAIN, ERR_NOT_DIVISIBLE, ERR_POINT):
         raise ValueError(msg)
     raise ZkbError(msg or f"libzkb200 error {rc}")
 

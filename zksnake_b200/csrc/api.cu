@@ -148,6 +148,53 @@ int zkb_points_download(int curve, int group, const void* d_pts, size_t n, uint6
   return ZKB_OK;
 }
 
+size_t zkb_compressed_bytes(int curve, int group) {
+  if ((curve != ZKB_BN254 && curve != ZKB_BLS12_381) || (group != 1 && group != 2)) return 0;
+  return compressed_bytes(curve, group);
+}
+
+int zkb_points_compress(int curve, int group, const void* d_pts, size_t n, uint8_t* out) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  CHECK_GROUP(group);
+  if (n == 0) return ZKB_OK;
+  size_t bytes = n * compressed_bytes(curve, group);
+  void* d_tmp;
+  int rc;
+  if ((rc = stage(3, bytes, &d_tmp))) return rc;
+  if ((rc = points_compress_dev(curve, group, d_pts, n, d_tmp))) return rc;
+  ZKB_CUDA(ZKB_D2H(out, d_tmp, bytes));
+  ZKB_CUDA(cudaStreamSynchronize(S()));
+  return ZKB_OK;
+}
+
+int zkb_points_decompress(int curve, int group, const uint8_t* in, size_t n, int validate, void* d_pts, long long* bad_index,
+                          int* reason) {
+  NEED_INIT();
+  CHECK_CURVE(curve);
+  CHECK_GROUP(group);
+  if (bad_index) *bad_index = -1;
+  if (reason) *reason = 0;
+  if (n == 0) return ZKB_OK;
+  size_t bytes = n * compressed_bytes(curve, group);
+  void* d_tmp;
+  int rc;
+  if ((rc = stage(3, bytes, &d_tmp))) return rc;
+  ZKB_CUDA(ZKB_H2D(d_tmp, in, bytes));
+  unsigned long long bad = ~0ull;
+  if ((rc = points_decompress_dev(curve, group, d_tmp, n, validate, d_pts, &bad))) return rc;
+  if (bad != ~0ull) {
+    static const char* why[] = {"", "invalid flags", "coordinate not in field", "non-zero infinity", "not on curve",
+                                "not in the prime-order subgroup"};
+    int r = (int)(bad & 0xff);
+    if (bad_index) *bad_index = (long long)(bad >> 8);
+    if (reason) *reason = r;
+    return set_error(ZKB_ERR_POINT, std::string("Cannot deserialize point: ") + why[r < 6 ? r : 0] + " (index " +
+                                        std::to_string(bad >> 8) + ")");
+  }
+  return ZKB_OK;
+}
+
 int zkb_msm_dev_windows(int curve, int group, const void* d_pts, const void* d_scalars, size_t n, uint32_t wrank,
                         uint32_t wworld, uint64_t* out_xy, int* out_inf) {
   NEED_INIT();

@@ -14,6 +14,7 @@
 #define ZKB_ERR_DOMAIN (-4)       // "Domain size is too large"              (polynomial.rs:638-639)
 #define ZKB_ERR_NOT_DIVISIBLE (-5)  // "(U * V - W) did not divided by Z to zero" (qap.py:68-69)
 #define ZKB_ERR_NOINIT (-6)
+#define ZKB_ERR_POINT (-7)        // "Cannot deserialize point" (ecc.py:128-142 -> curve.rs:134-141)
 
 namespace zkb {
 
@@ -64,6 +65,11 @@ int groth16_h_dev(int curve, uint32_t log_n, const void* d_a, const void* d_b, c
 size_t ntt_scratch_bytes(uint32_t log_n);
 int spmv_dev(int curve, size_t n_out, size_t n_rows, const void* row_ptr, const void* col, const void* val, const void* w,
              void* out);
+
+// ---- point codec (codec.cu) ----
+size_t compressed_bytes(int curve, int group);
+int points_compress_dev(int curve, int group, const void* d_pts, size_t n, void* d_out);
+int points_decompress_dev(int curve, int group, const void* d_in, size_t n, int validate, void* d_pts, unsigned long long* bad);
 
 // ---- MSM (msm_host.cuh instantiations) ----
 // d_points: affine, Montgomery form; d_scalars: canonical 4 x u64.  Result: affine canonical coordinates on the host.

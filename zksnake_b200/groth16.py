@@ -56,13 +56,50 @@ class Proof:
         return cls(ec.PointG1.from_bytes(s[:n]), ec.PointG2.from_bytes(s[n:3 * n]), ec.PointG1.from_bytes(s[3 * n:]))
 
 
+def _take(buf, pos, size):
+    if pos + size > len(buf):
+        raise AssertionError("Invalid key length")
+    return buf[pos:pos + size], pos + size
+
+
 class ProvingKey:
-    """serialization.py:45-66.  The four vectors are device-resident PointVectors (zksnake_b200._algebra._ec.PointVector)."""
+    """serialization.py:45-159.  The four vectors are device-resident PointVectors (zksnake_b200._algebra._ec.PointVector);
+    to_bytes / from_bytes produce and read the reference's byte layout with ONE bulk (de)compression kernel per vector instead
+    of one from_hex call per point."""
 
     def __init__(self, alpha_G1, beta_G1, beta_G2, delta_G1, delta_G2, tau_G1, tau_G2, target_G1, k_delta_G1):
         self.alpha_1, self.beta_1, self.beta_2 = alpha_G1, beta_G1, beta_G2
         self.delta_1, self.delta_2 = delta_G1, delta_G2
         self.tau_1, self.tau_2, self.target_1, self.kdelta_1 = tau_G1, tau_G2, target_G1, k_delta_G1
+
+    def to_bytes(self) -> bytes:
+        """serialization.py:131-159: alpha_1 | beta_2 | delta_2 | beta_1 | delta_1, then each vector as u64 length + points."""
+        s = bytes(self.alpha_1.to_bytes() + self.beta_2.to_bytes() + self.delta_2.to_bytes() + self.beta_1.to_bytes()
+                  + self.delta_1.to_bytes())
+        for vec in (self.tau_1, self.tau_2, self.target_1, self.kdelta_1):
+            s += len(vec).to_bytes(8, "little") + vec.to_bytes()
+        return s
+
+    @classmethod
+    def from_bytes(cls, b: bytes, crv="BN254"):
+        """serialization.py:68-129"""
+        cid = _CURVES[crv]
+        ec = _EC[cid]
+        n = POINT_SIZE[cid]
+        b = bytes(b)
+        assert len(b) >= 7 * n, "Invalid proving key length"
+        alpha_1 = ec.PointG1.from_bytes(b[:n])
+        beta_2 = ec.PointG2.from_bytes(b[n:3 * n])
+        delta_2 = ec.PointG2.from_bytes(b[3 * n:5 * n])
+        beta_1 = ec.PointG1.from_bytes(b[5 * n:6 * n])
+        delta_1 = ec.PointG1.from_bytes(b[6 * n:7 * n])
+        pos = 7 * n
+        vecs = []
+        for group in (1, 2, 1, 1):
+            head, pos = _take(b, pos, 8)
+            raw, pos = _take(b, pos, int.from_bytes(head, "little") * n * group)
+            vecs.append(ec.PointVector.from_bytes(cid, group, raw))
+        return cls(alpha_1, beta_1, beta_2, delta_1, delta_2, *vecs)
 
 
 class VerifyingKey:
@@ -70,6 +107,26 @@ class VerifyingKey:
 
     def __init__(self, alpha_G1, beta_G2, gamma_G2, delta_G2, ic):
         self.alpha_1, self.beta_2, self.gamma_2, self.delta_2, self.ic = alpha_G1, beta_G2, gamma_G2, delta_G2, ic
+
+    def to_bytes(self) -> bytes:
+        s = bytes(self.alpha_1.to_bytes() + self.beta_2.to_bytes() + self.gamma_2.to_bytes() + self.delta_2.to_bytes())
+        s += len(self.ic).to_bytes(8, "little")
+        for pt in self.ic:
+            s += bytes(pt.to_bytes())
+        return s
+
+    @classmethod
+    def from_bytes(cls, s: bytes, crv="BN254"):
+        cid = _CURVES[crv]
+        ec = _EC[cid]
+        n = POINT_SIZE[cid]
+        s = bytes(s)
+        assert len(s) >= n * 7, "Invalid verifying key length"
+        alpha_1 = ec.PointG1.from_bytes(s[:n])
+        beta_2, gamma_2, delta_2 = (ec.PointG2.from_bytes(s[n + 2 * n * k:3 * n + 2 * n * k]) for k in range(3))
+        rest = s[7 * n + 8:]   # (the reference skips the length header and reads to the end of the buffer)
+        ic = [ec.PointG1.from_bytes(rest[i:i + n]) for i in range(0, len(rest), n)]
+        return cls(alpha_1, beta_2, gamma_2, delta_2, ic)
 
 
 class Groth16:
@@ -103,6 +160,7 @@ class Groth16:
         self.verifying_key = None
         self._pk_handle = None
         self._r1cs_handle = None
+        self._bound_key = None
         self.toxic = None  # (tau, alpha, beta, gamma, delta) kept for closed-form parity checks in tests
 
     # ------------------------------------------------------------------------------------------------ setup
@@ -173,6 +231,21 @@ class Groth16:
         self.verifying_key = VerifyingKey(G1 * alpha, G2 * beta, G2 * gamma, G2 * delta, k_gamma_G1)
         self._bind()
 
+    def _ensure_bound(self):
+        """A key assigned from outside (`prover.proving_key = ProvingKey.from_bytes(...)`, the reference's way of reusing a
+        stored key) is bound to the device prover on first use."""
+        if self._bound_key is self.proving_key and self._pk_handle is not None:
+            return
+        pk = self.proving_key
+        assert self.world == 1 or self.shard_mode == "windows", "a loaded key holds whole vectors: use shard_mode='windows'"
+        assert len(pk.tau_1) == self.n and len(pk.tau_2) == self.n and len(pk.target_1) == self.n, \
+            "ProvingKey does not match the constraint system"
+        assert len(pk.kdelta_1) == self.m - self.n_public, "Length of kdelta_1 and private_witness must be equal"
+        self._release()
+        self._slice = (0, self.n)
+        self._kslice = (0, self.m - self.n_public)
+        self._bind()
+
     def _bind(self):
         """Create the device-side prover objects (proving-key handle + CSR R1CS)."""
         pk = self.proving_key
@@ -200,6 +273,7 @@ class Groth16:
         hr = ctypes.c_void_p()
         nat.check(nat.lib.zkb_r1cs_create(self.curve, n_rows, self.m, rp, col, val, ctypes.byref(hr)))
         self._r1cs_handle = hr
+        self._bound_key = pk
 
     # ------------------------------------------------------------------------------------------------ prove
     def prove(self, public_witness: list, private_witness: list) -> Proof:
@@ -219,6 +293,7 @@ class Groth16:
     def prove_packed(self, witness_limbs, r, s):
         """witness as a (m, 4) uint64 array (host; pinned for full H2D speed) or a DeviceBuffer holding the same bytes -- the
         zero-marshalling entry used by bench.py."""
+        self._ensure_bound()
         g1b = nat.lib.zkb_affine_bytes(self.curve, 1) // 8
         g2b = nat.lib.zkb_affine_bytes(self.curve, 2) // 8
         oa, ob, oc = np.zeros(g1b, np.uint64), np.zeros(g2b, np.uint64), np.zeros(g1b, np.uint64)
@@ -277,11 +352,15 @@ class Groth16:
         return ec.pairing(proof.A, proof.B) == ec.multi_pairing([vk.alpha_1, acc, proof.C],
                                                                [vk.beta_2, vk.gamma_2, vk.delta_2])
 
+    def _release(self):
+        if self._r1cs_handle:
+            nat.lib.zkb_r1cs_free(self._r1cs_handle)
+        if self._pk_handle:
+            nat.lib.zkb_groth16_pk_free(self._pk_handle)
+        self._r1cs_handle = self._pk_handle = None
+
     def __del__(self):
         try:
-            if self._r1cs_handle:
-                nat.lib.zkb_r1cs_free(self._r1cs_handle)
-            if self._pk_handle:
-                nat.lib.zkb_groth16_pk_free(self._pk_handle)
+            self._release()
         except Exception:
             pass

@@ -191,3 +191,61 @@ def test_bulk_sizes(gpu, curve_name, grp, log_n, capsys):
     assert np.array_equal(back.download(), vec.download())
     with capsys.disabled():
         print(f"\n[codec] {curve_name} G{grp} n=2^{log_n}: compress {1e3 * (t1 - t0):.1f} ms, decompress+validate {1e3 * (t2 - t1):.1f} ms")
+
+
+@pytest.mark.parametrize("curve_name,n_gates", [("BN254", 13), ("BLS12_381", 8), ("BN254", 64)])
+def test_plonk_keys_round_trip_and_prove(gpu, curve_name, n_gates):
+    """plonk/serialization.py:157-353: the list-based prover's key and the device prover's key serialise to the SAME bytes;
+    both provers, given the re-read keys, reproduce the oracle's proof bytes."""
+    from zksnake_b200 import plonk as pm
+    from zksnake_b200.plonk_device import DevicePlonk
+    from zksnake_b200.plonkish import chain_gates
+    from oracle import plonk as op
+    from .test_gpu_plonk import seeded
+    cs, pub, priv = chain_gates(n_gates, curve_name)
+    cid = curve_id(curve_name)
+    r = PARAMS[cid].r
+    rnd = random.Random(900 + n_gates)
+    tau = rnd.randint(1, r - 1)
+    blind = [rnd.randint(1, r - 1) for _ in range(11)]
+    want, _ = op.prove(op.Circuit(cid, cs.qL, cs.qR, cs.qO, cs.qM, cs.qC, cs.permutation), tau, pub, priv, blind)
+    host, dev = pm.Plonk(cs, curve_name), DevicePlonk(cs, curve_name)
+    for prover in (host, dev):
+        old = seeded(pm, [tau])
+        try:
+            prover.setup()
+        finally:
+            pm.get_random_int = old
+    pk_bytes = host.proving_key.to_bytes()
+    vk_bytes = host.verifying_key.to_bytes()
+    assert dev.reference_proving_key().to_bytes() == pk_bytes
+    assert dev.verifying_key.to_bytes() == vk_bytes
+    with pytest.raises(AssertionError):
+        dev.proving_key.to_bytes()           # the device prover's working key has no derived fields
+    # layout: u64 SRS length, then [tau^i]G1 compressed (oracle encodings)
+    G1 = group(cid)
+    assert pk_bytes[:8] == (cs.length + 6).to_bytes(8, "little")
+    size = PARAMS[cid].fq_bytes
+    assert pk_bytes[8:8 + 3 * size] == b"".join(G1.to_bytes(G1.mul(G1.gen, pow(tau, i, r))) for i in range(3))
+    assert vk_bytes[:8] == cs.length.to_bytes(8, "little")
+    # re-read: reference-style (lists) and device-style (FrVecs)
+    pk_host = pm.ProvingKey.from_bytes(pk_bytes, curve_name)
+    assert pk_host.to_bytes() == pk_bytes and pk_host.n == cs.length
+    pk_dev = pm.ProvingKey.from_bytes(pk_bytes, curve_name, device=True)
+    assert pk_dev.to_bytes() == pk_bytes
+    vk2 = pm.VerifyingKey.from_bytes(vk_bytes, curve_name)
+    assert vk2.to_bytes() == vk_bytes
+    host2 = pm.Plonk(cs, curve_name)
+    host2.proving_key, host2.verifying_key = pk_host, vk2
+    dev2 = DevicePlonk(cs, curve_name)
+    dev2.load_keys(pk_dev, vk2)
+    for prover in (host2, dev2):
+        old = seeded(pm, blind)
+        try:
+            proof = prover.prove(pub, priv)
+        finally:
+            pm.get_random_int = old
+        assert proof.to_bytes() == want
+        assert prover.verify(proof, pub)
+    with pytest.raises(AssertionError):
+        pm.ProvingKey.from_bytes(pk_bytes[:-40], curve_name)

@@ -106,18 +106,9 @@ class DevicePlonk(Plonk):
         self.G1_tau = self.E.curve.PointVector(cid, 1, self.srs_len)
         nat.check(nat.lib.zkb_batch_mul_dev(cid, 1, gen.ptr, 1, powers.ptr, self.srs_len, self.G1_tau.ptr))
         self.G2_tau = self.E.G2() * tau
-        tab = ctypes.c_void_p()
-        nat.check(nat.lib.zkb_msm_table_create(cid, 1, self.G1_tau.ptr, self.srs_len, 0, self.world, ctypes.byref(tab)))
-        self.table = tab
+        self._build_table()
 
-        omega = get_evaluation_point(n, 1, p)
-        self.omega = omega
-        # quotient domain: every factor polynomial (degree <= n + 2) and T (degree <= 3n + 5) must fit: 4n, or 8n below 8 gates
-        N4 = self.NQ = 4 * n if n >= 8 else 8 * n
-        omega4 = get_evaluation_point(N4, 1, p)
-        g = 5 if cid == 0 else 7               # multiplicative generator of Fr: g^(4n) != 1, so X^n - 1 has no zero on g<omega_4n>
-        self.coset_g = g
-        roots = FrVec.powers(cid, n, omega)    # omega^i
+        roots = FrVec.powers(cid, n, get_evaluation_point(n, 1, p))    # omega^i
         all_ids = FrVec(cid, 3 * n)
         for k, kk in enumerate((1, K1, K2)):   # identity permutation values on H, k1 H, k2 H
             nat.check(nat.lib.zkb_d2d(all_ids.at(k * n), roots.scale(kk).ptr if kk != 1 else roots.ptr, n * 32))
@@ -131,9 +122,35 @@ class DevicePlonk(Plonk):
         permutation_poly = [s.intt() for s in sigma_ev]
         tau_selector = {k: self._commit(q) for k, q in selector_poly.items()}
         tau_permutation = [self._commit(s) for s in permutation_poly]
+        self.proving_key = ProvingKey(n, self.G1_tau, selector_poly, None, permutation_poly, None, tau_selector, tau_permutation,
+                                      None, self.E.name)
+        self.verifying_key = VerifyingKey(n, self.G2_tau, tau_selector, tau_permutation, self.E.name)
+        self._derive(roots, sigma_ev)
+        nat.check(nat.lib.zkb_sync())
+
+    def _build_table(self):
+        if self.table:
+            nat.lib.zkb_msm_table_free(self.table)
+        tab = ctypes.c_void_p()
+        nat.check(nat.lib.zkb_msm_table_create(self.cid, 1, self.G1_tau.ptr, self.srs_len, 0, self.world, ctypes.byref(tab)))
+        self.table = tab
+
+    def _derive(self, roots=None, sigma_ev=None):
+        """Everything the prover pre-evaluates from the proving key's polynomials (quotient-coset evaluations, 1/Z_H pattern)."""
+        pk, p, cid = self.proving_key, self.order, self.cid
+        n = pk.n
+        omega = get_evaluation_point(n, 1, p)
+        self.omega = omega
+        # quotient domain: every factor polynomial (degree <= n + 2) and T (degree <= 3n + 5) must fit: 4n, or 8n below 8 gates
+        N4 = self.NQ = 4 * n if n >= 8 else 8 * n
+        omega4 = get_evaluation_point(N4, 1, p)
+        g = 5 if cid == 0 else 7               # multiplicative generator of Fr: g^(4n) != 1, so X^n - 1 has no zero on g<omega_4n>
+        self.coset_g = g
+        self.roots = roots if roots is not None else FrVec.powers(cid, n, omega)
+        self.sigma_ev = sigma_ev if sigma_ev is not None else [s.ntt(n) for s in pk.permutation_poly]
         # everything the quotient needs, pre-evaluated on the coset g <omega_4n>
-        self.selector_coset = {k: self._coset_ntt(q) for k, q in selector_poly.items()}
-        self.sigma_coset = [self._coset_ntt(s) for s in permutation_poly]
+        self.selector_coset = {k: self._coset_ntt(q) for k, q in pk.selector_poly.items()}
+        self.sigma_coset = [self._coset_ntt(s) for s in pk.permutation_poly]
         l1 = FrVec.zeros(cid, n)
         l1.add_sparse({0: 1})
         self.l1_coset = self._coset_ntt(l1.intt())
@@ -143,12 +160,53 @@ class DevicePlonk(Plonk):
         zh_inv = [pow((gn * pow(i4, k, p) - 1) % p, -1, p) for k in range(per)]  # 1 / (x^n - 1) at coset point i depends on i mod per
         self.zh_inv_words = nat.ints_to_limbs(zh_inv)
         self.omega_q = omega4
-        self.roots, self.sigma_ev = roots, sigma_ev
-        self.proving_key = ProvingKey(n, self.G1_tau, selector_poly, None, permutation_poly, None, tau_selector, tau_permutation,
-                                      None, self.E.name)
-        self.verifying_key = VerifyingKey(n, self.G2_tau, tau_selector, tau_permutation, self.E.name)
         self._roots = [1, omega]    # verify() only needs omega
+
+    def load_keys(self, proving_key, verifying_key=None):
+        """Use keys read back with ProvingKey.from_bytes(..., device=True) / VerifyingKey.from_bytes (the reference assigns
+        `.proving_key` / `.verifying_key` after plonk/serialization.py:157-353): rebuilds the SRS table and the pre-evaluated
+        coset vectors from the key's polynomials."""
+        nat.ensure_init()
+        cid = self.cid
+        pk = proving_key
+
+        def dev(v):
+            if isinstance(v, FrVec):
+                return v
+            return FrVec.from_ints(cid, v.coeffs() if hasattr(v, "coeffs") else v)
+
+        n = pk.n
+        assert n == self.constraints.length, "ProvingKey does not match the constraint system"
+        assert len(pk.tau_g1) >= n + 6, "SRS too short"
+        def padded(v):      # coefficient vectors arrive with trailing zeros stripped (ark's DensePolynomial): back to length n
+            x = dev(v)
+            return x.copy(0, min(len(x), n), n=n)
+
+        sel = {k: padded(v) for k, v in pk.selector_poly.items()}
+        perm = [padded(v) for v in pk.permutation_poly]
+        self.srs_len = n + 6
+        self.G1_tau = pk.tau_g1 if len(pk.tau_g1) == self.srs_len else pk.tau_g1.prefix(self.srs_len)
+        self.proving_key = ProvingKey(n, self.G1_tau, sel, None, perm, None, pk.tau_selector_poly, pk.tau_permutation_poly, None,
+                                      self.E.name)
+        if verifying_key is not None:
+            self.verifying_key = verifying_key
+            self.G2_tau = verifying_key.tau_g2
+        self._build_table()
+        self._derive()
         nat.check(nat.lib.zkb_sync())
+
+    def reference_proving_key(self):
+        """The proving key with every field the reference's ProvingKey carries (plonk/serialization.py:128-156), the derived ones
+        computed on the device: selector_eval = the selectors on the plain 4n domain, identity_poly = the interpolants of
+        H, k1 H, k2 H, lagrange_evals = L_1 on the 4n domain (protocol.py:100-140).  Fields stay FrVecs; to_bytes() streams them."""
+        pk, n, cid = self.proving_key, self.proving_key.n, self.cid
+        selector_eval = {k: q.ntt(4 * n) for k, q in pk.selector_poly.items()}
+        identity_poly = [(self.roots if kk == 1 else self.roots.scale(kk)).intt() for kk in (1, K1, K2)]
+        l1 = FrVec.zeros(cid, n)
+        l1.add_sparse({0: 1})
+        lagrange_evals = l1.intt().ntt(4 * n)
+        return ProvingKey(n, pk.tau_g1, pk.selector_poly, selector_eval, pk.permutation_poly, identity_poly, pk.tau_selector_poly,
+                          pk.tau_permutation_poly, lagrange_evals, self.E.name)
 
     def _coset_ntt(self, poly):
         """evaluations of a polynomial (fewer than 4n coefficients) on the coset g <omega_4n>"""

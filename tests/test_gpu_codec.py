@@ -249,3 +249,21 @@ def test_plonk_keys_round_trip_and_prove(gpu, curve_name, n_gates):
         assert prover.verify(proof, pub)
     with pytest.raises(AssertionError):
         pm.ProvingKey.from_bytes(pk_bytes[:-40], curve_name)
+
+
+def test_groth16_from_circom_file(gpu, tmp_path):
+    """a circuit written to and read back from a circom .r1cs file proves to the same bytes"""
+    from zksnake_b200 import groth16 as gm
+    from zksnake_b200 import r1cs as rm
+    from .test_gpu_groth16 import make, prove_seeded
+    r = PARAMS[0].r
+    circuit = rm.chain_circuit(21, "BN254")
+    path = tmp_path / "chain.r1cs"
+    rm.write_r1cs_file(path, circuit[0], n_pub_out=1)
+    back, _ = rm.read_r1cs_file(path)
+    proofs = []
+    for c in (circuit[0], back):
+        g, st, pub, priv = make(gm, rm, (c, circuit[1], circuit[2]), "BN254", seed=33)
+        proofs.append(prove_seeded(gm, g, pub, priv, 1234567 % r, 7654321 % r).to_bytes())
+        assert g.verify(gm.Proof.from_bytes(proofs[-1]), pub)
+    assert proofs[0] == proofs[1]

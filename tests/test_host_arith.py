@@ -109,3 +109,34 @@ def test_compute_fails_loudly_without_gpu(native):
     assert rc != 0
     with pytest.raises(Exception):
         native.ensure_init()
+
+
+def test_circom_r1cs_file_round_trip(tmp_path):
+    """zksnake_b200.r1cs.read_r1cs_file: the sections /root/reference/python/zksnake/parser.py:37-90 reads, into prover triplets."""
+    from zksnake_b200 import r1cs as rm
+    for curve in ("BN254", "BLS12_381"):
+        for circuit in (rm.readme_circuit(curve), rm.chain_circuit(9, curve), rm.dense_random_circuit(6, curve)):
+            c, pub, priv = circuit
+            path = tmp_path / f"c_{curve}.r1cs"
+            n_out = min(1, c.n_public - 1)
+            rm.write_r1cs_file(path, c, n_pub_out=n_out)
+            back, header = rm.read_r1cs_file(path)
+            for x, y in ((c.A, back.A), (c.B, back.B), (c.C, back.C)):
+                assert sorted(x.triplets) == sorted(y.triplets)
+                assert y.n_col == x.n_col
+            assert back.n_public == c.n_public and back.p == c.p
+            assert header["n_wires"] == c.A.n_col and header["n_pub_out"] == n_out and header["n_pub_in"] == c.n_public - 1 - n_out
+            assert header["fs"] == 32 and list(header["wire_labels"]) == list(range(c.A.n_col))
+            assert back.is_sat(list(pub) + list(priv))
+    raw = bytearray(path.read_bytes())
+    bad = tmp_path / "bad.r1cs"
+    bad.write_bytes(b"r2cs" + bytes(raw[4:]))
+    import pytest
+    with pytest.raises(AssertionError, match="Invalid magic bytes"):
+        rm.read_r1cs_file(bad)
+    bad.write_bytes(bytes(raw[:4]) + (2).to_bytes(4, "little") + bytes(raw[8:]))
+    with pytest.raises(AssertionError, match="Unsupported r1cs file version: 2"):
+        rm.read_r1cs_file(bad)
+    bad.write_bytes(bytes(raw[:-3]))
+    with pytest.raises(AssertionError):
+        rm.read_r1cs_file(bad)

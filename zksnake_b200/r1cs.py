@@ -147,3 +147,91 @@ def dense_random_circuit(n_constraints, curve="BN254", seed=20):
     c = [(i, 1 + 2 * N + i, 1) for i in range(N)]
     r1cs = R1CS.from_triplets(a, b, c, N, 3 * N + 1, 1, curve)
     return r1cs, [1], xs + ys + zs
+
+
+# ---------------------------------------------------------------------------------------------------------- circom .r1cs files
+R1CS_FILE_VERSIONS = (1,)   # parser.py:8
+
+
+def read_r1cs_file(path):
+    """iden3/circom binary `.r1cs` -> (R1CS, header).  The sections /root/reference/python/zksnake/parser.py:37-90 reads (magic,
+    version, header = type 1, constraints = type 2, wire-to-label = type 3, in any order), but straight into the A, B, C triplets
+    the prover consumes instead of symbolic equations for the circuit compiler (which is outside the proving path, SURVEY.md
+    section 8): row i holds <A_i, w> * <B_i, w> = <C_i, w> over the file's own wire order
+    [1, outputs, public inputs, private inputs, intermediates] -- the order of a circom witness file -- and
+    n_public = 1 + n_pub_out + n_pub_in.  The curve is recognised from the header's prime."""
+    with open(path, "rb") as f:
+        data = f.read()
+    magic = data[:4]
+    assert magic == b"r1cs", f"Invalid magic bytes: {magic}"
+    version = int.from_bytes(data[4:8], "little")
+    assert version in R1CS_FILE_VERSIONS, f"Unsupported r1cs file version: {version}"
+    n_section = int.from_bytes(data[8:12], "little")
+    pos, header, raw_constraints, labels = 12, None, [], None
+    for _ in range(n_section):
+        kind = int.from_bytes(data[pos:pos + 4], "little")
+        size = int.from_bytes(data[pos + 4:pos + 12], "little")
+        body = memoryview(data)[pos + 12:pos + 12 + size]
+        assert len(body) == size, "Truncated r1cs file"
+        pos += 12 + size
+        if kind == 1:
+            fs = int.from_bytes(body[:4], "little")
+            vals = np.frombuffer(body[4 + fs:4 + fs + 16], dtype="<u4")
+            header = {"fs": fs, "prime": int.from_bytes(body[4:4 + fs], "little"), "n_wires": int(vals[0]), "n_pub_out": int(vals[1]),
+                      "n_pub_in": int(vals[2]), "n_priv_in": int(vals[3]),
+                      "n_labels": int.from_bytes(body[20 + fs:28 + fs], "little"),
+                      "m_constraints": int.from_bytes(body[28 + fs:32 + fs], "little")}
+        elif kind == 2:
+            raw_constraints.append(body)
+        elif kind == 3:
+            labels = np.frombuffer(body, dtype="<u8")
+    assert header is not None, "r1cs file without a header section"
+    curves = {_R[0]: "BN254", _R[1]: "BLS12_381"}
+    assert header["prime"] in curves, "r1cs file over an unsupported field"
+    p, fs = header["prime"], header["fs"]
+    trips = ([], [], [])
+    row = 0
+    for body in raw_constraints:
+        off, end = 0, len(body)
+        while off < end:
+            for which in range(3):
+                count = int.from_bytes(body[off:off + 4], "little")
+                off += 4
+                for _ in range(count):
+                    wire = int.from_bytes(body[off:off + 4], "little")
+                    value = int.from_bytes(body[off + 4:off + 4 + fs], "little") % p
+                    off += 4 + fs
+                    assert wire < header["n_wires"], "wire index out of range"
+                    trips[which].append((row, wire, value))
+            row += 1
+    assert row == header["m_constraints"], "constraint count does not match the header"
+    header["wire_labels"] = labels
+    n_public = 1 + header["n_pub_out"] + header["n_pub_in"]
+    return R1CS.from_triplets(trips[0], trips[1], trips[2], row, header["n_wires"], n_public, curves[p]), header
+
+
+def write_r1cs_file(path, r1cs, n_pub_out=0, n_priv_in=0):
+    """The inverse of read_r1cs_file (version 1, sections header / constraints / wire-to-label), for tests and for handing a
+    synthetic circuit to other tools."""
+    fs = 32
+    n_rows = max((t[0] for arr in (r1cs.A, r1cs.B, r1cs.C) for t in arr.triplets), default=-1) + 1
+    n_wires = r1cs.A.n_col
+    rows = [([], [], []) for _ in range(n_rows)]
+    for which, arr in enumerate((r1cs.A, r1cs.B, r1cs.C)):
+        for i, j, v in arr.triplets:
+            rows[i][which].append((j, v % r1cs.p))
+    body = bytearray()
+    for lcs in rows:
+        for lc in lcs:
+            body += len(lc).to_bytes(4, "little")
+            for j, v in lc:
+                body += j.to_bytes(4, "little") + v.to_bytes(fs, "little")
+    n_pub_in = r1cs.n_public - 1 - n_pub_out
+    head = (fs.to_bytes(4, "little") + r1cs.p.to_bytes(fs, "little") + n_wires.to_bytes(4, "little")
+            + n_pub_out.to_bytes(4, "little") + n_pub_in.to_bytes(4, "little") + n_priv_in.to_bytes(4, "little")
+            + n_wires.to_bytes(8, "little") + n_rows.to_bytes(4, "little"))
+    labels = np.arange(n_wires, dtype="<u8").tobytes()
+    with open(path, "wb") as f:
+        f.write(b"r1cs" + (1).to_bytes(4, "little") + (3).to_bytes(4, "little"))
+        for kind, content in ((2, bytes(body)), (1, head), (3, labels)):   # (constraints before the header: order is free)
+            f.write(kind.to_bytes(4, "little") + len(content).to_bytes(8, "little") + content)

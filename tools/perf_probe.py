@@ -135,6 +135,37 @@ if __name__ == "__main__":
                       f"{t.ms/3:8.3f} ms {n/(t.ms/3)/1e3:8.1f} Mpts/s  " + " ".join(f"{k}={v[0]:.3f}" for k, v in pr.items() if v[1]), flush=True)
                 nat.lib.zkb_msm_table_free(tab)
             d_pts.free(); d_s.free()
+    if what == "small":
+        # latency-bound sizes: window / run-length choices for plain and table MSMs at 2^14 .. 2^18
+        for ln in (14, 16, 18):
+            time_msm(0, 1, ln, tunings=[(0, 0, 0)] + [(c, seg, 3) for c in (ln - 6, ln - 5, ln - 4, ln - 3) for seg in (8, 16, 32)])
+        for curve, grp, ln in ((0, 1, 16), (0, 1, 18), (0, 2, 16)):
+            n = 1 << ln
+            ab = nat.lib.zkb_affine_bytes(curve, grp)
+            d_pts = make_points(curve, grp, n, 1)
+            d_s = nat.DeviceBuffer(n * 32).upload(rand_fr(n, 2, curve))
+            out = np.zeros(ab // 8, dtype=np.uint64)
+            inf = ctypes.c_int()
+            for cb in (0, ln - 5, ln - 4, ln - 3, ln - 2, ln - 1):
+                tab = ctypes.c_void_p()
+                nat.check(nat.lib.zkb_msm_table_create(curve, grp, d_pts.ptr, n, cb, 1, ctypes.byref(tab)))
+                c_, W_, by_ = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_size_t()
+                nat.lib.zkb_msm_table_info(tab, ctypes.byref(c_), ctypes.byref(W_), ctypes.byref(by_))
+                for seg in (0, 8, 16, 32, 64):
+                    nat.lib.zkb_msm_set_tuning(0, seg, 0)
+                    nat.check(nat.lib.zkb_msm_table_dev(tab, d_s.ptr, n, 0, 1, nat.ptr(out), ctypes.byref(inf)))
+                    with nat.Timer() as t:
+                        for _ in range(5):
+                            nat.check(nat.lib.zkb_msm_table_dev(tab, d_s.ptr, n, 0, 1, nat.ptr(out), ctypes.byref(inf)))
+                    nat.check(nat.lib.zkb_prof_enable(1))
+                    nat.check(nat.lib.zkb_msm_table_dev(tab, d_s.ptr, n, 0, 1, nat.ptr(out), ctypes.byref(inf)))
+                    pr = nat.prof_read()
+                    nat.check(nat.lib.zkb_prof_enable(0))
+                    print(f"table msm curve={curve} g{grp} 2^{ln} c={c_.value}{'(auto)' if cb == 0 else ''} W={W_.value} seg={seg}: "
+                          f"{t.ms/5:8.3f} ms  " + " ".join(f"{k}={v[0]:.3f}" for k, v in pr.items() if v[1]), flush=True)
+                nat.lib.zkb_msm_set_tuning(0, 0, 0)
+                nat.lib.zkb_msm_table_free(tab)
+            d_pts.free(); d_s.free()
     if what == "msmx":
         time_msm(1, 1, 20)
         time_msm(1, 1, 22, tunings=((0, 0, 0), (15, 32, 3), (16, 32, 3), (17, 32, 3)))

@@ -38,7 +38,9 @@ inline int msm_choose_window(size_t n, uint32_t scalar_bits, uint32_t wworld, bo
   for (int cc = lo; cc <= hi; cc++) {
     uint32_t W = (scalar_bits + 1 + cc - 1) / cc;
     uint32_t per_rank = (W + wworld - 1) / wworld;
-    double buckets = 5.0 * (double)(1u << (cc - 1));
+    // (below 2^20 points the bucket reduction is latency-bound and partly hidden: measured optimum sits one or two windows
+    // sizes higher than a cost of 5 per bucket predicts -- tools/perf_probe.py small, gpurun_out/small_r2g.txt)
+    double buckets = ((!table && logn <= 19) ? 3.0 : 5.0) * (double)(1u << (cc - 1));
     double cost = table ? (double)per_rank * (double)n + buckets : (double)per_rank * ((double)n + buckets);
     if (c == 0 || cost < best) {
       best = cost;
@@ -48,8 +50,9 @@ inline int msm_choose_window(size_t n, uint32_t scalar_bits, uint32_t wworld, bo
   return c;
 }
 
+// accum_threads: resident threads of the accumulation grid (148 SMs x MINB CTAs x 128)
 inline MsmPlan msm_make_plan(size_t n, uint32_t scalar_bits, uint32_t wrank, uint32_t wworld, uint32_t table_c = 0,
-                             size_t table_n = 0) {
+                             size_t table_n = 0, uint32_t accum_threads = 148 * 4 * 128) {
   MsmPlan pl;
   memset(&pl, 0, sizeof(pl));
   uint32_t logn = 0;
@@ -68,6 +71,14 @@ inline MsmPlan msm_make_plan(size_t n, uint32_t scalar_bits, uint32_t wrank, uin
   // (lane-inefficient) warp fold -- keep the typical bucket at <= 3 pieces
   pl.krun = 32u;
   while (pl.krun < 256u && (table_n ? n * pl.nwin : n) / pl.nbuck > 2 * (size_t)pl.krun) pl.krun *= 2;
+  // ... but never so long that the runs cannot fill the grid: a run is one thread's serial chain, so with fewer runs than
+  // resident threads the accumulation time is set by the chain length (2^16 points: 0.80 -> 0.20 ms)
+  {
+    size_t per_thread = n * pl.nwin / accum_threads;
+    uint32_t fill = 8;
+    while (fill < 256u && 3 * (size_t)fill <= 2 * per_thread) fill *= 2;   // power of two nearest to refs / threads, >= 8
+    if (pl.krun > fill) pl.krun = fill;
+  }
   if (g_msm_seg) pl.krun = (uint32_t)g_msm_seg;
   uint32_t maxlog = g_msm_kchunk ? (uint32_t)g_msm_kchunk : 3u;   // log2 of the reduction radix
   if (maxlog < 1) maxlog = 1;
@@ -115,7 +126,7 @@ inline int msm_geometry(size_t n, uint32_t scalar_bits, uint32_t wrank, uint32_t
     return ZKB_OK;
   }
   if (table_n && n > table_n) return set_error(ZKB_ERR_ARG, "msm: more scalars than table points");
-  g->pl = msm_make_plan(n, scalar_bits, wrank, wworld, table_c, table_n);
+  g->pl = msm_make_plan(n, scalar_bits, wrank, wworld, table_c, table_n, 148u * (sizeof(X) >= 256 ? 2u : (sizeof(X) > 128 ? 3u : 4u)) * 128u);
   const MsmPlan& pl = g->pl;
   if (pl.nwin == 0) {   // more ranks than windows
     g->skip = true;

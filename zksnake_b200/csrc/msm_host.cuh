@@ -78,6 +78,19 @@ inline MsmPlan msm_make_plan(size_t n, uint32_t scalar_bits, uint32_t wrank, uin
     uint32_t fill = 8;
     while (fill < 256u && 3 * (size_t)fill <= 2 * per_thread) fill *= 2;   // power of two nearest to refs / threads, >= 8
     if (pl.krun > fill) pl.krun = fill;
+    // ... and trimmed so that the runs come out as a whole number of grid-wide rounds: work is handed out 32 runs at a time to
+    // 148 x MINB x 4 warps, so with T references the kernel lasts ceil(T / (K P)) rounds of K additions; K = 32 at 2^20 points
+    // is 6.06 rounds -- a seventh round that keeps 6 % of the warps busy.  Pick the round count k nearest to the heuristic K
+    // and the smallest K that fits T into k rounds (2 % slack for the runs that straddle bucket boundaries).
+    double pt = (double)n * pl.nwin / accum_threads;
+    if (pt > 8.0) {
+      uint32_t k = (uint32_t)(pt / pl.krun + 0.5);
+      if (k < 1) k = 1;
+      uint32_t fit = (uint32_t)(pt * 1.02 / k) + 1;
+      if (fit < 8) fit = 8;
+      if (fit > 2 * pl.krun) fit = 2 * pl.krun;
+      if (k <= 12) pl.krun = fit;   // (with many rounds the last one costs little and K's integer steps are too coarse to aim)
+    }
   }
   if (g_msm_seg) pl.krun = (uint32_t)g_msm_seg;
   uint32_t maxlog = g_msm_kchunk ? (uint32_t)g_msm_kchunk : 3u;   // log2 of the reduction radix

@@ -237,6 +237,7 @@ class Groth16:
         if self._bound_key is self.proving_key and self._pk_handle is not None:
             return
         pk = self.proving_key
+        assert pk is not None, "ProvingKey has not been generated"
         assert self.world == 1 or self.shard_mode == "windows", "a loaded key holds whole vectors: use shard_mode='windows'"
         assert len(pk.tau_1) == self.n and len(pk.tau_2) == self.n and len(pk.target_1) == self.n, \
             "ProvingKey does not match the constraint system"

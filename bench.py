@@ -375,6 +375,9 @@ def main_own(args):
     # zkb_imad_peak(1) with loop-variant operands, tools/ffbench.cu) is therefore the roofline denominator.
     L = 8 if curve == 0 else 12
     ops_per_pt = 16 * 10 * (2 * L * L + L)
+    c_c, c_w = ctypes.c_uint32(), ctypes.c_uint32()
+    nat.check(nat.lib.zkb_groth16_pk_msm_info(prover._pk_handle, 0, ctypes.byref(c_c), ctypes.byref(c_w)))
+    win_c, win_w = int(c_c.value), int(c_w.value)
     acc_ms, acc_cnt = prof["msm_accum_g1"]
     roofline = None
     if acc_cnt:
@@ -387,6 +390,9 @@ def main_own(args):
                                    "multiplicand, 8 chains/thread)",
                     "imad_lo_peak": imad.value / 1e12,
                     "algorithmic_ops_per_point": ops_per_pt, "points_per_launch": pts_per_launch,
+                    # what the kernel really executes: W_actual (not the canonical 16) mixed additions per point
+                    "window_bits": win_c, "windows": win_w, "executed_ops_per_point": win_w * 10 * (2 * L * L + L),
+                    "frac_executed": achieved * win_w / 16.0 / (imad_wide.value / 1e12),
                     "launch_ms": per_launch_ms, "launches": acc_cnt,
                     "traffic": (traffic.get("msm_accumulate_g1") or {}).get("dram_bytes"),
                     "traffic_detail": traffic.get("msm_accumulate_g1"), "share_of_step": acc_ms / args.steps / dev_ms}

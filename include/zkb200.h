@@ -201,6 +201,9 @@ void zkb_groth16_pk_free(zkb_groth16_pk* pk);
  * zkb_groth16_partial covers only window shard `rank` of `world`.  Scales better than point slices (the digit sort and the
  * bucket reduction shrink too); costs the whole key per GPU (320 MiB at 2^20 BN254). */
 int zkb_groth16_pk_set_window_shard(zkb_groth16_pk* pk, uint32_t rank, uint32_t world);
+/* Window size c and window count W the MSM over key vector `which` (0 tau_1, 1 tau_2, 2 target_1, 3 kdelta_1) runs with --
+ * the executed work is W mixed additions per point (bench.py reports it beside the canonical 16-window count). */
+int zkb_groth16_pk_msm_info(const zkb_groth16_pk* pk, int which, uint32_t* window_bits, uint32_t* windows);
 /* Build fixed-base tables for the key's four point vectors (see zkb_msm_table_create); every later prove uses them. */
 int zkb_groth16_pk_build_tables(zkb_groth16_pk* pk, uint32_t world);
 /* Groth16.prove from host buffers: a, b, c = A.w, B.w, C.w (n each), priv = private witness (n_kdelta scalars), r, s = the

@@ -442,6 +442,17 @@ int zkb_groth16_pk_build_tables(zkb_groth16_pk* pk, uint32_t world) {
   return ZKB_OK;
 }
 
+int zkb_groth16_pk_msm_info(const zkb_groth16_pk* pk, int which, uint32_t* window_bits, uint32_t* windows) {
+  if (!pk || which < 0 || which > 3) return set_error(ZKB_ERR_ARG, "bad proving key vector");
+  if (pk->tab[which]) return zkb_msm_table_info(pk->tab[which], window_bits, windows, nullptr);
+  const size_t cnt[4] = {pk->len, pk->len, pk->len, pk->klen};
+  uint32_t c = 0, W = 0;
+  msm_plan_info(cnt[which] ? cnt[which] : 1, pk->curve == ZKB_BN254 ? 254 : 255, pk->wworld ? pk->wworld : 1, &c, &W);
+  if (window_bits) *window_bits = c;
+  if (windows) *windows = W;
+  return ZKB_OK;
+}
+
 int zkb_groth16_pk_set_window_shard(zkb_groth16_pk* pk, uint32_t rank, uint32_t world) {
   if (!pk || world == 0 || rank >= world) return set_error(ZKB_ERR_ARG, "bad window shard");
   pk->wrank = rank;

@@ -3,3 +3,12 @@
 namespace zkb {
 ZKB_MSM_INSTANTIATE(g1bn, fq_bn, 254, ZKB_BN254, 1)
 }
+
+namespace zkb {
+// the plan heuristics live in msm_host.cuh; this translation unit exports them for zkb_groth16_pk_msm_info
+void msm_plan_info(size_t n, uint32_t scalar_bits, uint32_t wworld, uint32_t* c, uint32_t* W) {
+  MsmPlan pl = msm_make_plan(n, scalar_bits, 0, wworld ? wworld : 1);
+  *c = pl.c;
+  *W = pl.nwin_total;
+}
+}  // namespace zkb

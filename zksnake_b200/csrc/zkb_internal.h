@@ -66,6 +66,9 @@ size_t ntt_scratch_bytes(uint32_t log_n);
 int spmv_dev(int curve, size_t n_out, size_t n_rows, const void* row_ptr, const void* col, const void* val, const void* w,
              void* out);
 
+// window size / window count the plain (table-less) MSM heuristic picks for n points (msm_common.cu)
+void msm_plan_info(size_t n, uint32_t scalar_bits, uint32_t wworld, uint32_t* c, uint32_t* W);
+
 // ---- point codec (codec.cu) ----
 size_t compressed_bytes(int curve, int group);
 int points_compress_dev(int curve, int group, const void* d_pts, size_t n, void* d_out);

@@ -13,6 +13,12 @@
  *   zkb_batch_mul_dev                src/bn254/curve.rs:326-354 batch_multi_scalar_g1/g2 (setup side)
  *   zkb_groth16_h / _h_dev           python/zksnake/groth16/qap.py:42-71 QAP.evaluate_witness (after the A.w/B.w/C.w dots)
  *   zkb_groth16_pk_* / _prove        python/zksnake/groth16/protocol.py:115-165 Groth16.prove
+ *   zkb_r1cs_create / _eval(_dev)    python/zksnake/array.py:36-43 SparseArray.dot (x3: groth16/qap.py:53-55); over the transposed
+ *                                    matrices: the L/R/O loop of Groth16.setup (groth16/protocol.py:64-77)
+ *   zkb_fr_*_dev, zkb_plonk_*        the Polynomial / list glue of python/zksnake/plonk/protocol.py:270-466
+ *   zkb_msm_table_*                  the same multiexp over a fixed vector (proving key, KZG SRS: commitment/polynomial/kzg.py:32-51)
+ *   zkb_points_compress / _decompress  PointG1/G2.to_bytes / from_bytes over a vector: src/bn254/curve.rs:127-141, 300-314 and
+ *                                    the key serialisers python/zksnake/groth16/serialization.py:68-220, plonk/serialization.py:157-353
  *
  * Conventions
  *   - curve: ZKB_BN254 (0) or ZKB_BLS12_381 (1); group: 1 = G1, 2 = G2.
@@ -26,6 +32,8 @@
  *   - Return value: 0 on success, a negative ZKB_ERR_* code otherwise; zkb_last_error() gives the text.  The host
  *     binding maps codes to the reference's exception types.
  *   - No exceptions and no allocator ownership cross this boundary: callers allocate outputs.
+ *   - One host thread per process drives the library (one process per GPU, as torchrun launches them): entry points are
+ *     not re-entrant -- they share one stream, one scratch arena and per-call result tickets.
  *   - There is NO CPU fallback: every compute entry point fails with ZKB_ERR_NOINIT / ZKB_ERR_CUDA without a B200.
  */
 #ifndef ZKB200_H

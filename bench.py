@@ -327,6 +327,8 @@ def main_own(args):
     barrier()
     h2d0, d2h0 = ctypes.c_ulonglong(), ctypes.c_ulonglong()
     nat.lib.zkb_transfer_count(ctypes.byref(h2d0), ctypes.byref(d2h0))
+    from zksnake_b200 import dist as zdist
+    dist_t0 = dict(zdist.TRANSFER)
     t2 = time.perf_counter()
     for _ in range(args.steps):
         p2 = prover.prove_packed(w_pinned, r_rand, s_rand)
@@ -338,6 +340,8 @@ def main_own(args):
     nat.lib.zkb_transfer_count(ctypes.byref(h2d1), ctypes.byref(d2h1))
     h2d_step = (h2d1.value - h2d0.value) // args.steps   # counted by the library around every cudaMemcpy it issues
     d2h_step = (d2h1.value - d2h0.value) // args.steps
+    h2d_step += (zdist.TRANSFER["h2d"] - dist_t0["h2d"]) // args.steps   # ... plus what zksnake_b200.dist moved through torch
+    d2h_step += (zdist.TRANSFER["d2h"] - dist_t0["d2h"]) // args.steps
     clocks = sampler.stop(t0, t3) if rank == 0 else None
 
     if td is not None:

@@ -307,6 +307,11 @@ class Groth16:
             nat.check(fn(self._pk_handle, self._r1cs_handle, wptr, self.n_public, nat.ptr(rr), nat.ptr(ss), nat.ptr(oa),
                          nat.ptr(ob), nat.ptr(oc), inf))
         else:
+            keep = None
+            if not on_dev and dist.nccl_ready() and os.environ.get("ZKB_WITNESS_SHARDED", "1") != "0":
+                # each rank uploads 1/world of the witness; NVLink all-gather instead of world x the same PCIe transfer
+                keep = dist.upload_sharded(witness_limbs)
+                wptr, on_dev = keep.data_ptr(), True
             # every rank: witness polynomials + the five MSMs over its key slice; one all-gather; identical assembly everywhere
             xy = np.zeros((dist.MSM_SLOTS, dist.SLOT_LIMBS), dtype=np.uint64)
             flags = np.zeros(dist.MSM_SLOTS, dtype=np.int32)

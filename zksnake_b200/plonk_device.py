@@ -22,6 +22,7 @@ computed, never WHICH polynomial:
 the three wire columns as (n, 4) uint64 arrays so that a 2^20-gate proof involves no Python big-int loop at all.  Verification is
 inherited (host pairing).  `timings` holds per-round wall-clock milliseconds of the last proof."""
 import ctypes
+import os
 import time
 
 import numpy as np
@@ -259,7 +260,19 @@ class DevicePlonk(Plonk):
             tr.append(v)
 
         # ---- round 1 ----
-        wires = [FrVec.from_limbs(cid, w) for w in wire_columns]
+        keep = []
+        if self.world > 1 and dist.nccl_ready() and os.environ.get("ZKB_WITNESS_SHARDED", "1") != "0":
+            # every rank uploads 1/world of each column; an NVLink all-gather completes it (3 x 32 MiB per rank otherwise)
+            wires = []
+            for w in wire_columns:
+                t = dist.upload_sharded(w)
+                v = FrVec(cid, len(w))
+                nat.check(nat.lib.zkb_d2d(v.ptr, t.data_ptr(), len(w) * 32))
+                nat.check(nat.lib.zkb_fr_reduce_dev(cid, len(w), v.ptr))
+                keep.append(t)           # (alive until the copy has run: released after the round-1 synchronisation)
+                wires.append(v)
+        else:
+            wires = [FrVec.from_limbs(cid, w) for w in wire_columns]
         assert all(w.n == n for w in wires)
         pi_ev_n = FrVec.zeros(cid, n)
         if public_witness:
@@ -270,6 +283,7 @@ class DevicePlonk(Plonk):
         for c in (tau_a, tau_b, tau_c):
             tr.append(c)
         lap("round1")
+        keep.clear()
 
         # ---- round 2: grand product from the witness values (the blinding terms vanish on the domain H) ----
         beta, gamma = tr.get_challenge_scalar(), tr.get_challenge_scalar()

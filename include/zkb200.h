@@ -209,6 +209,10 @@ void zkb_groth16_pk_free(zkb_groth16_pk* pk);
  * zkb_groth16_partial covers only window shard `rank` of `world`.  Scales better than point slices (the digit sort and the
  * bucket reduction shrink too); costs the whole key per GPU (320 MiB at 2^20 BN254). */
 int zkb_groth16_pk_set_window_shard(zkb_groth16_pk* pk, uint32_t rank, uint32_t world);
+/* Optional, host only: start computing the multiples of delta_1 / delta_2 that depend on (r, s) alone on host threads, so that
+ * they overlap the GPU work of zkb_groth16_partial; zkb_groth16_assemble picks them up when called with the same r, s (and
+ * computes them itself otherwise).  The single-call provers do this internally. */
+int zkb_groth16_precompute(zkb_groth16_pk* pk, const uint64_t r[4], const uint64_t s[4]);
 /* Window size c and window count W the MSM over key vector `which` (0 tau_1, 1 tau_2, 2 target_1, 3 kdelta_1) runs with --
  * the executed work is W mixed additions per point (bench.py reports it beside the canonical 16-window count). */
 int zkb_groth16_pk_msm_info(const zkb_groth16_pk* pk, int which, uint32_t* window_bits, uint32_t* windows);

@@ -367,7 +367,20 @@ struct zkb_groth16_pk {
   char* work;  // a, b, c, u, v, w, h (n each) + priv (n_kdelta)
   uint64_t msm_xy[5][24];
   int msm_inf[5];
+  struct Groth16Pre* pre;       // host-side products of (r, s) with the key, computed while the GPU runs (zkb_groth16_precompute)
 };
+
+// r*delta_1, s*delta_1, -(r s)*delta_1 and s*delta_2 depend on the prover's randomness and the key only, not on the MSMs:
+// four host scalar multiplications (~0.2 ms each in G1, ~0.8 ms in G2) that used to sit on the critical path AFTER the last
+// MSM.  They are computed on two host threads as soon as r and s are known, i.e. under the ~25 ms of GPU work.
+struct Groth16Pre {
+  std::thread th1, th2;
+  bool running = false, valid = false;
+  uint64_t r[4], s[4];
+  uint64_t rd1[12], sd1[12], nrsd1[12], sd2[24];
+  int inf_rd1 = 1, inf_sd1 = 1, inf_nrsd1 = 1, inf_sd2 = 1;
+};
+static void pre_join(Groth16Pre* p);
 
 int zkb_groth16_pk_create_sharded(int curve, uint32_t log_n, const void* d_tau1, const void* d_tau2, const void* d_target1,
                                   size_t off, size_t len, const void* d_kdelta1, size_t n_kdelta, size_t koff, size_t klen,
@@ -423,6 +436,10 @@ void zkb_groth16_pk_free(zkb_groth16_pk* pk) {
   if (ctx_ready()) {
     cudaStreamSynchronize(S());
     cudaFree(pk->work);
+  }
+  if (pk->pre) {
+    pre_join(pk->pre);
+    delete pk->pre;
   }
   delete pk;
 }
@@ -500,41 +517,33 @@ static int groth16_msms(zkb_groth16_pk* pk, const void* d_priv) {
   return ZKB_OK;
 }
 
-int zkb_groth16_assemble(zkb_groth16_pk* pk, const uint64_t* msm_xy, const int* msm_inf, const uint64_t r[4], const uint64_t s[4],
-                         uint64_t* out_a, uint64_t* out_b, uint64_t* out_c, int out_inf[3]) {
-  if (!pk) return set_error(ZKB_ERR_ARG, "null proving key");
+static void pre_join(Groth16Pre* p) {
+  if (p && p->running) {
+    p->th1.join();
+    p->th2.join();
+    p->running = false;
+  }
+}
+
+static void pre_start(zkb_groth16_pk* pk, const uint64_t r[4], const uint64_t s[4]) {
+  if (!pk->pre) pk->pre = new Groth16Pre();
+  Groth16Pre* p = pk->pre;
+  pre_join(p);
+  memcpy(p->r, r, 32);
+  memcpy(p->s, s, 32);
   const int curve = pk->curve;
-  // proof assembly, protocol.py:133-165
   const size_t g1 = affine_bytes(curve, 1), g2 = affine_bytes(curve, 2);
-  const uint64_t* mx[5];
-  for (int i = 0; i < 5; i++) mx[i] = msm_xy + i * 24;
-  int inf_alpha = is_zero_pt(pk->alpha1, g1), inf_beta1 = is_zero_pt(pk->beta1, g1), inf_beta2 = is_zero_pt(pk->beta2, g2);
-  int inf_d1 = is_zero_pt(pk->delta1, g1), inf_d2 = is_zero_pt(pk->delta2, g2);
-  uint64_t A[12], B1[12];
-  int infA, infB1, infB2, infC;
-  {
-    const uint64_t* pts[3] = {mx[0], pk->alpha1, pk->delta1};
-    int infs[3] = {msm_inf[0], inf_alpha, inf_d1};
-    const uint64_t* sc[3] = {nullptr, nullptr, r};
-    host_lincomb(curve, 1, 3, pts, infs, sc, A, &infA);
-  }
-  {
-    const uint64_t* pts[3] = {mx[1], pk->beta1, pk->delta1};
-    int infs[3] = {msm_inf[1], inf_beta1, inf_d1};
-    const uint64_t* sc[3] = {nullptr, nullptr, s};
-    host_lincomb(curve, 1, 3, pts, infs, sc, B1, &infB1);
-  }
-  // B (G2, the slowest of the four linear combinations) on its own host thread while A, B1 and C are computed here
-  std::thread th_b2([&]() {
-    const uint64_t* pts[3] = {mx[2], pk->beta2, pk->delta2};
-    int infs[3] = {msm_inf[2], inf_beta2, inf_d2};
-    const uint64_t* sc[3] = {nullptr, nullptr, s};
-    host_lincomb(curve, 2, 3, pts, infs, sc, out_b, &infB2);
-  });
-  {
-    // C = HZ + KW + s*A + r*B1 - (r*s)*delta1 ; the last term as (order - r*s) * delta1
+  const int inf_d1 = is_zero_pt(pk->delta1, g1), inf_d2 = is_zero_pt(pk->delta2, g2);
+  p->th1 = std::thread([pk, p, curve, inf_d1]() {
+    const uint64_t* pt[1] = {pk->delta1};
+    int infs[1] = {inf_d1};
+    const uint64_t* sc[1] = {p->r};
+    host_lincomb(curve, 1, 1, pt, infs, sc, p->rd1, &p->inf_rd1);
+    sc[0] = p->s;
+    host_lincomb(curve, 1, 1, pt, infs, sc, p->sd1, &p->inf_sd1);
+    // -(r s) as (order - r s)
     uint64_t rs[4], neg_rs[4];
-    host_fr_mul(curve, r, s, rs);
+    host_fr_mul(curve, p->r, p->s, rs);
     static const uint64_t ORD[2][4] = {
         {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull},
         {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull, 0x73eda753299d7d48ull}};
@@ -546,12 +555,82 @@ int zkb_groth16_assemble(zkb_groth16_pk* pk, const uint64_t* msm_xy, const int* 
       br = (d >> 64) & 1;
     }
     if (rs_zero) memset(neg_rs, 0, sizeof(neg_rs));
-    const uint64_t* pts[5] = {mx[3], mx[4], A, B1, pk->delta1};
-    int infs[5] = {msm_inf[3], msm_inf[4], infA, infB1, inf_d1};
-    const uint64_t* sc[5] = {nullptr, nullptr, s, r, neg_rs};
+    sc[0] = neg_rs;
+    host_lincomb(curve, 1, 1, pt, infs, sc, p->nrsd1, &p->inf_nrsd1);
+  });
+  p->th2 = std::thread([pk, p, curve, inf_d2]() {
+    const uint64_t* pt[1] = {pk->delta2};
+    int infs[1] = {inf_d2};
+    const uint64_t* sc[1] = {p->s};
+    host_lincomb(curve, 2, 1, pt, infs, sc, p->sd2, &p->inf_sd2);
+  });
+  p->running = true;
+  p->valid = true;
+}
+
+int zkb_groth16_precompute(zkb_groth16_pk* pk, const uint64_t r[4], const uint64_t s[4]) {
+  if (!pk || !r || !s) return set_error(ZKB_ERR_ARG, "null argument");
+  pre_start(pk, r, s);
+  return ZKB_OK;
+}
+
+int zkb_groth16_assemble(zkb_groth16_pk* pk, const uint64_t* msm_xy, const int* msm_inf, const uint64_t r[4], const uint64_t s[4],
+                         uint64_t* out_a, uint64_t* out_b, uint64_t* out_c, int out_inf[3]) {
+  if (!pk) return set_error(ZKB_ERR_ARG, "null proving key");
+  const int curve = pk->curve;
+  // proof assembly, protocol.py:133-165:
+  //   A = [U] + alpha + r delta,  B = [V] + beta + s delta  (in G1 and in G2),
+  //   C = [H Z] + [K w] + s A + r B1 - (r s) delta
+  // the multiples of delta come from zkb_groth16_precompute (started now if the caller did not); s A and r B1 are the only
+  // scalar multiplications left after the MSMs and run side by side.
+  if (!pk->pre || !pk->pre->valid || memcmp(pk->pre->r, r, 32) || memcmp(pk->pre->s, s, 32)) pre_start(pk, r, s);
+  Groth16Pre* pre = pk->pre;
+  pre_join(pre);
+  pre->valid = false;   // r and s are one-time values
+  const size_t g1 = affine_bytes(curve, 1), g2 = affine_bytes(curve, 2);
+  const uint64_t* mx[5];
+  for (int i = 0; i < 5; i++) mx[i] = msm_xy + i * 24;
+  int inf_alpha = is_zero_pt(pk->alpha1, g1), inf_beta1 = is_zero_pt(pk->beta1, g1), inf_beta2 = is_zero_pt(pk->beta2, g2);
+  uint64_t A[12], B1[12], sA[12], rB1[12];
+  int infA, infB1, infB2, infC, inf_sA, inf_rB1;
+  {
+    const uint64_t* pts[3] = {mx[0], pk->alpha1, pre->rd1};
+    int infs[3] = {msm_inf[0], inf_alpha, pre->inf_rd1};
+    const uint64_t* sc[3] = {nullptr, nullptr, nullptr};
+    host_lincomb(curve, 1, 3, pts, infs, sc, A, &infA);
+  }
+  std::thread th_sa([&]() {
+    const uint64_t* pts[1] = {A};
+    int infs[1] = {infA};
+    const uint64_t* sc[1] = {s};
+    host_lincomb(curve, 1, 1, pts, infs, sc, sA, &inf_sA);
+  });
+  {
+    const uint64_t* pts[3] = {mx[1], pk->beta1, pre->sd1};
+    int infs[3] = {msm_inf[1], inf_beta1, pre->inf_sd1};
+    const uint64_t* sc[3] = {nullptr, nullptr, nullptr};
+    host_lincomb(curve, 1, 3, pts, infs, sc, B1, &infB1);
+  }
+  std::thread th_rb([&]() {
+    const uint64_t* pts[1] = {B1};
+    int infs[1] = {infB1};
+    const uint64_t* sc[1] = {r};
+    host_lincomb(curve, 1, 1, pts, infs, sc, rB1, &inf_rB1);
+  });
+  {
+    const uint64_t* pts[3] = {mx[2], pk->beta2, pre->sd2};
+    int infs[3] = {msm_inf[2], inf_beta2, pre->inf_sd2};
+    const uint64_t* sc[3] = {nullptr, nullptr, nullptr};
+    host_lincomb(curve, 2, 3, pts, infs, sc, out_b, &infB2);
+  }
+  th_sa.join();
+  th_rb.join();
+  {
+    const uint64_t* pts[5] = {mx[3], mx[4], sA, rB1, pre->nrsd1};
+    int infs[5] = {msm_inf[3], msm_inf[4], inf_sA, inf_rB1, pre->inf_nrsd1};
+    const uint64_t* sc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     host_lincomb(curve, 1, 5, pts, infs, sc, out_c, &infC);
   }
-  th_b2.join();
   memcpy(out_a, A, g1);
   out_inf[0] = infA;
   out_inf[1] = infB2;
@@ -566,6 +645,7 @@ int zkb_groth16_prove_dev(zkb_groth16_pk* pk, const void* d_a, const void* d_b, 
   if (!pk) return set_error(ZKB_ERR_ARG, "null proving key");
   if (pk->len != pk->n || pk->klen != pk->n_kdelta || pk->wworld != 1)
     return set_error(ZKB_ERR_ARG, "this proving key holds one slice only: use zkb_groth16_partial + zkb_groth16_assemble");
+  pre_start(pk, r, s);   // host multiples of delta under the GPU work
   const size_t bytes = pk->n * 32;
   char* w = pk->work;
   void *d_u = w + 3 * bytes, *d_v = w + 4 * bytes, *d_w = w + 5 * bytes, *d_h = w + 6 * bytes;
@@ -739,6 +819,7 @@ int zkb_groth16_prove_witness(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const uint64_t
   if ((rc = prove_witness_checks(pk, r1cs, n_public))) return rc;
   if (pk->len != pk->n || pk->klen != pk->n_kdelta || pk->wworld != 1)
     return set_error(ZKB_ERR_ARG, "this proving key holds one slice only: use zkb_groth16_partial + zkb_groth16_assemble");
+  pre_start(pk, r, s);   // host multiples of delta under the GPU work
   if ((rc = r1cs_load_witness(r1cs, witness, 0))) return rc;
   if ((rc = partial_from_resident_witness(pk, r1cs, n_public))) return rc;
   return zkb_groth16_assemble(pk, &pk->msm_xy[0][0], pk->msm_inf, r, s, out_a, out_b, out_c, out_inf);
@@ -752,6 +833,7 @@ int zkb_groth16_prove_witness_dev(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const void
   if ((rc = prove_witness_checks(pk, r1cs, n_public))) return rc;
   if (pk->len != pk->n || pk->klen != pk->n_kdelta || pk->wworld != 1)
     return set_error(ZKB_ERR_ARG, "this proving key holds one slice only: use zkb_groth16_partial + zkb_groth16_assemble");
+  pre_start(pk, r, s);   // host multiples of delta under the GPU work
   if ((rc = r1cs_load_witness(r1cs, d_witness, 1))) return rc;
   if ((rc = partial_from_resident_witness(pk, r1cs, n_public))) return rc;
   return zkb_groth16_assemble(pk, &pk->msm_xy[0][0], pk->msm_inf, r, s, out_a, out_b, out_c, out_inf);

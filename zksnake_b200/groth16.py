@@ -313,6 +313,7 @@ class Groth16:
                 keep = dist.upload_sharded(witness_limbs)
                 wptr, on_dev = keep.data_ptr(), True
             # every rank: witness polynomials + the five MSMs over its key slice; one all-gather; identical assembly everywhere
+            nat.check(nat.lib.zkb_groth16_precompute(self._pk_handle, nat.ptr(rr), nat.ptr(ss)))   # host threads, under the GPU work
             xy = np.zeros((dist.MSM_SLOTS, dist.SLOT_LIMBS), dtype=np.uint64)
             flags = np.zeros(dist.MSM_SLOTS, dtype=np.int32)
             nat.check(nat.lib.zkb_groth16_partial(self._pk_handle, self._r1cs_handle, wptr, int(on_dev), self.n_public,

@@ -169,17 +169,25 @@ class CpuProver:
         self.csr = chain_csr(n)
         self.witness = chain_witness(n, self.r)
         self.m = n + 2
-        self.threads = cport.threads()
-        g1 = lambda k0, cnt: cport.chain_points(curve, 1, k0, cnt)  # noqa: E731
+        # every host core this process may use, passed explicitly: torchrun exports OMP_NUM_THREADS=1, which would otherwise
+        # turn the "all host threads" arm into a single-threaded one
+        try:
+            self.threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            self.threads = os.cpu_count() or 1
+        nt = self.threads
+        g1 = lambda k0, cnt: cport.chain_points(curve, 1, k0, cnt, nt)  # noqa: E731
+        g2 = lambda k0, cnt: cport.chain_points(curve, 2, k0, cnt, nt)  # noqa: E731
         self.key = {
-            "tau1": g1(1, n), "tau2": cport.chain_points(curve, 2, 1, n), "target1": g1(7, n), "kdelta1": g1(11, self.m - 2),
-            "alpha1": g1(3, 1)[0], "beta1": g1(5, 1)[0], "beta2": cport.chain_points(curve, 2, 5, 1)[0],
-            "delta1": g1(9, 1)[0], "delta2": cport.chain_points(curve, 2, 9, 1)[0],
+            "tau1": g1(1, n), "tau2": g2(1, n), "target1": g1(7, n), "kdelta1": g1(11, self.m - 2),
+            "alpha1": g1(3, 1)[0], "beta1": g1(5, 1)[0], "beta2": g2(5, 1)[0],
+            "delta1": g1(9, 1)[0], "delta2": g2(9, 1)[0],
         }
 
     def prove(self):
         t0 = time.perf_counter()
-        out = self.cport.groth16_prove(self.curve, self.log_n, self.csr, self.m, 2, self.witness, self.key, 12345, 67890)
+        out = self.cport.groth16_prove(self.curve, self.log_n, self.csr, self.m, 2, self.witness, self.key, 12345, 67890,
+                                       nthreads=self.threads)
         return (time.perf_counter() - t0) * 1e3, out
 
 

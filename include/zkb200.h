@@ -143,8 +143,10 @@ int zkb_points_download(int curve, int group, const void* d_pts, size_t n, uint6
  *   zkb_compressed_bytes: 32 / 64 (BN254 G1 / G2), 48 / 96 (BLS12-381).
  *   zkb_points_compress:   n device points -> n encodings in host memory.
  *   zkb_points_decompress: n encodings in host memory -> n device points.  validate != 0 adds the prime-order subgroup check
- *     (ark's Validate::Yes, what from_bytes does); flags, x < q, "infinity has x = 0" and "x^3 + b is a square" are always
- *     checked.  On an invalid encoding returns ZKB_ERR_POINT with *bad_index = the first offending point and *reason =
+ *     (ark's Validate::Yes, what from_bytes does): 1 = by the endomorphism criteria in G2 (psi(P) = [x]P on BLS12-381,
+ *     [x+1]P + psi([x]P) + psi^2([x]P) = psi^3([2x]P) on BN254; r * P = infinity in G1), 2 = r * P = infinity everywhere --
+ *     the same accept set, about three times the work in G2.  Flags, x < q, "infinity has x = 0" and "x^3 + b is a square"
+ *     are always checked.  On an invalid encoding returns ZKB_ERR_POINT with *bad_index = the first offending point and *reason =
  *     1 flags | 2 coordinate not in field | 3 non-zero infinity | 4 not on curve | 5 not in the subgroup (both optional). */
 size_t zkb_compressed_bytes(int curve, int group);
 int zkb_points_compress(int curve, int group, const void* d_pts, size_t n, uint8_t* out);

@@ -267,3 +267,48 @@ def test_groth16_from_circom_file(gpu, tmp_path):
         proofs.append(prove_seeded(gm, g, pub, priv, 1234567 % r, 7654321 % r).to_bytes())
         assert g.verify(gm.Proof.from_bytes(proofs[-1]), pub)
     assert proofs[0] == proofs[1]
+
+
+@pytest.mark.parametrize("curve_name", ["BN254", "BLS12_381"])
+def test_g2_subgroup_criteria_agree_with_the_definition(gpu, curve_name):
+    """validate=1 (endomorphism criterion) and validate=2 (r * P = infinity) against the oracle's r * P on members, random
+    non-members of E'(Fq2), pure cofactor-torsion points and member + torsion sums."""
+    cid = curve_id(curve_name)
+    E = _ec(curve_name)
+    G = group(cid, True)
+    F, q, r = G.F, PARAMS[cid].q, PARAMS[cid].r
+    rnd = random.Random(4242)
+    pts, member = [], []
+    while len(pts) < 36:
+        x = (rnd.randint(0, q - 1), rnd.randint(0, q - 1))
+        y = F.sqrt(F.add(F.mul(F.mul(x, x), x), G.b))
+        if y is None:
+            continue
+        p0 = (x, y)
+        t = G.mul_raw(p0, r)                         # the cofactor-torsion part of a random curve point
+        cands = [p0, t, G.add(t, G.mul(G.gen, rnd.randint(1, r - 1))) if t is not None else None,
+                 G.mul(G.gen, rnd.randint(1, r - 1))]
+        for c in cands:
+            if c is None:
+                continue
+            pts.append(c)
+            member.append(G.mul_raw(c, r) is None)
+    assert sum(member) >= 8 and sum(1 for m in member if not m) >= 20
+    encs = [G.to_bytes(p) for p in pts]
+    size = len(encs[0])
+    for mode in (1, 2):
+        # one at a time: the kernel's verdict per point
+        for enc, ok in zip(encs, member):
+            if ok:
+                assert E.curve.PointVector.from_bytes(cid, 2, enc, validate=mode).to_bytes() == enc
+            else:
+                with pytest.raises(ValueError, match="not in the prime-order subgroup"):
+                    E.curve.PointVector.from_bytes(cid, 2, enc, validate=mode)
+        # all members in one vector pass; the first non-member of the whole list is the one reported
+        good = b"".join(e for e, ok in zip(encs, member) if ok)
+        assert E.curve.PointVector.from_bytes(cid, 2, good, validate=mode).to_bytes() == good
+        first_bad = member.index(False)
+        with pytest.raises(ValueError, match=rf"\(index {first_bad}\)"):
+            E.curve.PointVector.from_bytes(cid, 2, b"".join(encs), validate=mode)
+    assert E.curve.PointVector.from_bytes(cid, 2, b"".join(encs), validate=0).to_bytes() == b"".join(encs)
+    assert len(encs) * size == len(b"".join(encs))

@@ -1,0 +1,110 @@
+"""Groundwork for the endomorphism subgroup test of the G2 key decoder: pins the constants of
+psi (untwist-Frobenius-twist) numerically -- psi(P) = [p mod r] P on G2 -- and checks the two published membership criteria
+against the definition r * P = infinity with the oracle's curve arithmetic, on members, random non-members of E'(Fq2), pure
+cofactor-torsion points and member + torsion sums:
+  BN254      [x+1]P + psi([x]P) + psi^2([x]P) = psi^3([2x]P),  x = 4965661367192848881   (eprint 2022/352, section 4.3)
+  BLS12-381  psi(P) = [x]P,                                    x = -0xd201000000010000    (Scott, eprint 2021/1130)
+CPU only, about two minutes.  Nothing in the library uses this yet: zkb_points_decompress still checks r * P = infinity."""
+import os
+import random
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle.curve import group
+from oracle.fields import PARAMS
+for cid, xi, X in ((0, (9,1), 4965661367192848881), (1, (1,1), 0xd201000000010000)):
+    G = group(cid, True); F = G.F; q = PARAMS[cid].q; r = PARAMS[cid].r
+    def fpow(a, e):
+        res = (1, 0); base = a
+        while e:
+            if e & 1: res = F.mul(res, base)
+            base = F.mul(base, base); e >>= 1
+        return res
+    conj = lambda a: (a[0], (-a[1]) % q)
+    g3 = fpow(xi, (q - 1) // 3); g2 = fpow(xi, (q - 1) // 2)
+    cands = {"xi": (g3, g2), "inv": (F.inv(g3), F.inv(g2))}
+    P = G.mul(G.gen, 123456789)
+    target = G.mul(P, q % r)
+    for name, (cx, cy) in cands.items():
+        psi = lambda pt: None if pt is None else (F.mul(conj(pt[0]), cx), F.mul(conj(pt[1]), cy))
+        ok = psi(P) == target
+        print(cid, name, "psi(P)==[p]P:", ok, "on curve:", G.on_curve(psi(P)))
+        if ok:
+            print("  cx =", [hex(v) for v in cx]); print("  cy =", [hex(v) for v in cy])
+
+print("---- membership criteria ----")
+consts = {}
+for cid, xi, X in ((0, (9,1), 4965661367192848881), (1, (1,1), 0xd201000000010000)):
+    G = group(cid, True); F = G.F; q = PARAMS[cid].q; r = PARAMS[cid].r
+    def fpow(a, e):
+        res = (1, 0); base = a
+        while e:
+            if e & 1: res = F.mul(res, base)
+            base = F.mul(base, base); e >>= 1
+        return res
+    conj = lambda a: (a[0], (-a[1]) % q)
+    g3 = fpow(xi, (q - 1) // 3); g2 = fpow(xi, (q - 1) // 2)
+    cx, cy = (g3, g2) if cid == 0 else (F.inv(g3), F.inv(g2))
+    psi = lambda pt: None if pt is None else (F.mul(conj(pt[0]), cx), F.mul(conj(pt[1]), cy))
+    def member_fast(P):
+        if P is None: return True
+        xP = G.mul_raw(P, X)
+        if cid == 0:
+            a = G.add(xP, P)                    # [x+1]P
+            b = psi(xP); c = psi(b)             # psi([x]P), psi^2([x]P)
+            lhs = G.add(G.add(a, b), c)
+            rhs = psi(psi(psi(G.add(xP, xP))))  # psi^3([2x]P)
+            return lhs == rhs
+        return G.add(psi(P), xP) is None        # psi(P) = [x]P with x = -X
+    rnd = random.Random(5)
+    n_in = n_out = 0
+    for _ in range(12):
+        P = G.mul(G.gen, rnd.randint(1, r - 1))
+        assert member_fast(P) and G.mul_raw(P, r) is None
+        n_in += 1
+    k = 1
+    while n_out < 40:
+        x = (rnd.randint(0, q - 1), rnd.randint(0, q - 1))
+        y = F.sqrt(F.add(F.mul(F.mul(x, x), x), G.b))
+        if y is None: continue
+        P = (x, y)
+        slow = G.mul_raw(P, r) is None
+        fast = member_fast(P)
+        assert slow == fast, (cid, P)
+        n_out += (not slow)
+    # points of small-cofactor order: h2 * r / small... also r*P' style: cofactor-cleared must be members
+    print(cid, "members ok:", n_in, "non-members rejected:", n_out)
+
+print("---- structured non-members (cofactor torsion) ----")
+for cid, xi, X in ((0, (9,1), 4965661367192848881), (1, (1,1), 0xd201000000010000)):
+    G = group(cid, True); F = G.F; q = PARAMS[cid].q; r = PARAMS[cid].r
+    def fpow(a, e):
+        res = (1, 0); base = a
+        while e:
+            if e & 1: res = F.mul(res, base)
+            base = F.mul(base, base); e >>= 1
+        return res
+    conj = lambda a: (a[0], (-a[1]) % q)
+    g3 = fpow(xi, (q - 1) // 3); g2 = fpow(xi, (q - 1) // 2)
+    cx, cy = (g3, g2) if cid == 0 else (F.inv(g3), F.inv(g2))
+    psi = lambda pt: None if pt is None else (F.mul(conj(pt[0]), cx), F.mul(conj(pt[1]), cy))
+    def member_fast(P):
+        if P is None: return True
+        xP = G.mul_raw(P, X)
+        if cid == 0:
+            a = G.add(xP, P); b = psi(xP); c = psi(b)
+            return G.add(G.add(a, b), c) == psi(psi(psi(G.add(xP, xP))))
+        return G.add(psi(P), xP) is None
+    rnd = random.Random(9)
+    cnt = 0
+    while cnt < 12:
+        x = (rnd.randint(0, q - 1), rnd.randint(0, q - 1))
+        y = F.sqrt(F.add(F.mul(F.mul(x, x), x), G.b))
+        if y is None: continue
+        T = G.mul_raw((x, y), r)            # torsion part only
+        if T is None: continue
+        assert not member_fast(T)
+        M = G.add(T, G.mul(G.gen, rnd.randint(1, r - 1)))
+        assert not member_fast(M) and G.mul_raw(M, r) is not None
+        cnt += 1
+    print(cid, "torsion and mixed points rejected:", cnt)

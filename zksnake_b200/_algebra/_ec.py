@@ -114,7 +114,9 @@ class PointVector:
     @classmethod
     def from_bytes(cls, curve, group, data, validate=True):
         """Inverse of to_bytes with the checks of from_bytes per point (flags, x < q, on the curve, in the subgroup); raises
-        ValueError("Cannot deserialize point: ...") naming the first offending index (ecc.py:128-142)."""
+        ValueError("Cannot deserialize point: ...") naming the first offending index (ecc.py:128-142).  validate: True / 1 =
+        subgroup membership by the endomorphism criteria in G2 (r * P in G1), 2 = r * P = infinity everywhere (the definition;
+        same accept set, 3x slower in G2), False / 0 = no subgroup check."""
         nat.ensure_init()
         size = nat.lib.zkb_compressed_bytes(curve, group)
         if len(data) % size:
@@ -123,7 +125,7 @@ class PointVector:
         vec = cls(curve, group, n)
         if n:
             raw = np.frombuffer(bytes(data), dtype=np.uint8)
-            nat.check(nat.lib.zkb_points_decompress(curve, group, raw.ctypes.data, n, 1 if validate else 0, vec.ptr, None, None))
+            nat.check(nat.lib.zkb_points_decompress(curve, group, raw.ctypes.data, n, int(validate), vec.ptr, None, None))
         return vec
 
     def download(self):

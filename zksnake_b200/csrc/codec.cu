@@ -173,8 +173,71 @@ struct Wire2 {
 
 template <class F>
 struct CurveB {
-  F b;   // Montgomery form
+  F b;             // Montgomery form
+  F psi_x, psi_y;  // G2 only: psi(x, y) = (conj(x) psi_x, conj(y) psi_y), the untwist-Frobenius-twist endomorphism
 };
+
+// ------------------------------------------------------------------------------------------------ subgroup membership
+// Definition: r * P = infinity.  mode 2 computes exactly that (255 doublings).  mode 1 uses, in G2, the endomorphism criteria
+// that replace the 254-bit scalar by the 63/64-bit curve parameter x (psi acts on G2 as multiplication by p):
+//   BN254      [x+1]P + psi([x]P) + psi^2([x]P) = psi^3([2x]P)      (El Housni, Guillevic, Piellard, eprint 2022/352, section 4.3)
+//   BLS12-381  psi(P) = [x]P, x < 0                                (Scott, eprint 2021/1130)
+// Both are proven equivalent to the definition for points of E'(Fq2); tools/psi_subgroup_check.py pins the constants and checks
+// them against r * P on members, random non-members, cofactor-torsion points and mixtures; tests/test_gpu_codec.py checks
+// the kernel against the oracle's r * P on the same kinds of points.
+template <class P>
+__device__ Fp2<P> conj2(const Fp2<P>& a) {
+  Fp2<P> r;
+  r.c0 = a.c0;
+  r.c1 = neg(a.c1);
+  return r;
+}
+template <class P>
+__device__ Affine<Fp2<P>> psi(const Affine<Fp2<P>>& p, const CurveB<Fp2<P>>& cb) {
+  if (p.is_inf()) return p;
+  Affine<Fp2<P>> r;
+  r.x = conj2(p.x) * cb.psi_x;
+  r.y = conj2(p.y) * cb.psi_y;
+  return r;
+}
+template <class P>
+__device__ XYZZ<Fp2<P>> psi(const XYZZ<Fp2<P>>& p, const CurveB<Fp2<P>>& cb) {
+  XYZZ<Fp2<P>> r;   // x = X / ZZ, y = Y / ZZZ and conjugation is a field automorphism
+  r.X = conj2(p.X) * cb.psi_x;
+  r.Y = conj2(p.Y) * cb.psi_y;
+  r.ZZ = conj2(p.ZZ);
+  r.ZZZ = conj2(p.ZZZ);
+  return r;
+}
+
+template <class F>
+__device__ bool in_subgroup(const Affine<F>& p, const CurveB<F>&, const uint32_t* order, int) {
+  uint32_t k[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) k[j] = order[j];
+  return scalar_mul(p, k, 8).is_inf();
+}
+__device__ bool in_subgroup(const Affine<Fp2<FqBN254>>& p, const CurveB<Fp2<FqBN254>>& cb, const uint32_t* order, int mode) {
+  typedef Fp2<FqBN254> F;
+  if (mode == 2) return in_subgroup<F>(p, cb, order, 0);
+  const uint32_t x[2] = {0x4A6909F1u, 0x44E992B4u};   // 4965661367192848881
+  XYZZ<F> xp = scalar_mul(p, x, 2);
+  XYZZ<F> a = xp;
+  madd(a, p);                        // [x+1]P
+  XYZZ<F> b = psi(xp, cb);           // psi([x]P)
+  XYZZ<F> c = psi(b, cb);            // psi^2([x]P)
+  XYZZ<F> lhs = add(add(a, b), c);
+  XYZZ<F> rhs = psi(psi(psi(dbl(xp), cb), cb), cb);
+  return add(lhs, neg(rhs)).is_inf();
+}
+__device__ bool in_subgroup(const Affine<Fp2<FqBLS381>>& p, const CurveB<Fp2<FqBLS381>>& cb, const uint32_t* order, int mode) {
+  typedef Fp2<FqBLS381> F;
+  if (mode == 2) return in_subgroup<F>(p, cb, order, 0);
+  const uint32_t x[2] = {0x00010000u, 0xd2010000u};   // |x| = 0xd201000000010000, x = -|x|
+  XYZZ<F> xp = scalar_mul(p, x, 2);
+  madd(xp, psi(p, cb));              // [|x|]P + psi(P) = 0  <=>  psi(P) = [x]P
+  return xp.is_inf();
+}
 
 // ------------------------------------------------------------------------------------------------ kernels
 template <class W, class P, bool BE>
@@ -198,7 +261,7 @@ __global__ void __launch_bounds__(128) compress_kernel(unsigned long long n, con
 }
 
 // status: atomicMin of (index << 8 | reason) over the offending points
-template <class W, class P, bool BE, bool SUBGROUP>
+template <class W, class P, bool BE, int SUBGROUP>   // SUBGROUP: 0 none, 1 fast criterion (G2) / r*P (G1), 2 r*P
 __global__ void __launch_bounds__(128) decompress_kernel(unsigned long long n, const uint32_t* __restrict__ in,
                                                          CurveB<typename W::F> cb, const uint32_t* __restrict__ order,
                                                          Affine<typename W::F>* __restrict__ pts,
@@ -236,11 +299,7 @@ __global__ void __launch_bounds__(128) decompress_kernel(unsigned long long n, c
         p.x = xm;
         p.y = y;
         if (SUBGROUP) {
-          uint32_t k[8];
-#pragma unroll
-          for (int j = 0; j < 8; j++) k[j] = order[j];
-          XYZZ<F> t = scalar_mul(p, k, 8);
-          if (!t.is_inf()) bad = CODEC_SUBGROUP;
+          if (!in_subgroup(p, cb, order, SUBGROUP)) bad = CODEC_SUBGROUP;
         }
       }
     }
@@ -267,7 +326,7 @@ static Fp<P> host_to_mont(const uint64_t* limbs) {
   return to_mont(a);
 }
 
-template <class W, class P, bool BE, bool SUBGROUP>
+template <class W, class P, bool BE, int SUBGROUP>
 static int decompress_run(size_t n, const void* d_in, const CurveB<typename W::F>& cb, const uint32_t* d_order, void* d_pts,
                           unsigned long long* d_status) {
   decompress_kernel<W, P, BE, SUBGROUP><<<(unsigned)((n + 127) / 128), 128, 0, S()>>>(
@@ -285,6 +344,10 @@ static const uint64_t B_BLS_G1[6] = {4, 0, 0, 0, 0, 0};
 static const uint64_t ORDER[2][4] = {{0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull},
                                      {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull, 0x73eda753299d7d48ull}};
 
+static const uint64_t PSI_BN[4][4] = {{0x99e39557176f553dull, 0xb78cc310c2c3330cull, 0x4c0bec3cf559b143ull, 0x2fb347984f7911f7ull}, {0x1665d51c640fcba2ull, 0x32ae2a1d0b7c9dceull, 0x4ba4cc8bd75a0794ull, 0x16c9e55061ebae20ull},
+    {0xdc54014671a0135aull, 0xdbaae0eda9c95998ull, 0xdc5ec698b6e2f9b9ull, 0x063cf305489af5dcull}, {0x82d37f632623b0e3ull, 0x21807dc98fa25bd2ull, 0x0704b5a7ec796f2bull, 0x07c03cbcac41049aull}};   // psi_x.c0, psi_x.c1, psi_y.c0, psi_y.c1
+static const uint64_t PSI_BLS[4][6] = {{0x0000000000000000ull, 0x0000000000000000ull, 0x0000000000000000ull, 0x0000000000000000ull, 0x0000000000000000ull, 0x0000000000000000ull}, {0x8bfd00000000aaadull, 0x409427eb4f49fffdull, 0x897d29650fb85f9bull, 0xaa0d857d89759ad4ull, 0xec02408663d4de85ull, 0x1a0111ea397fe699ull},
+    {0xf1ee7b04121bdea2ull, 0x304466cf3e67fa0aull, 0xef396489f61eb45eull, 0x1c3dedd930b1cf60ull, 0xe2e9c448d77a2cd9ull, 0x135203e60180a68eull}, {0xc81084fbede3cc09ull, 0xee67992f72ec05f4ull, 0x77f76e17009241c5ull, 0x48395dabc2d3435eull, 0x6831e36d6bd17ffeull, 0x06af0e0437ff400bull}};   // psi_x.c0, psi_x.c1, psi_y.c0, psi_y.c1
 static uint32_t* g_order = nullptr;               // device copy of the two group orders (8 limbs each)
 static unsigned long long* g_status = nullptr;    // device status word
 
@@ -317,30 +380,46 @@ int points_decompress_dev(int curve, int group, const void* d_in, size_t n, int 
   if (rc) return rc;
   ZKB_CUDA(cudaMemsetAsync(g_status, 0xff, sizeof(unsigned long long), S()));
   const uint32_t* d_order = g_order + 8 * (curve == ZKB_BN254 ? 0 : 1);
+  // validate: 0 = no subgroup check, 1 = fast criterion in G2 (r * P in G1), 2 = r * P everywhere
   if (curve == ZKB_BN254) {
     if (group == 1) {
       CurveB<Fp<FqBN254>> cb;
+      memset(&cb, 0, sizeof(cb));
       cb.b = host_to_mont<FqBN254>(B_BN_G1);
-      rc = decompress_run<Wire1<FqBN254, false>, FqBN254, false, false>(n, d_in, cb, d_order, d_pts, g_status);
+      rc = decompress_run<Wire1<FqBN254, false>, FqBN254, false, 0>(n, d_in, cb, d_order, d_pts, g_status);   // cofactor 1
     } else {
       CurveB<Fp2<FqBN254>> cb;
       cb.b.c0 = host_to_mont<FqBN254>(B_BN_G2[0]);
       cb.b.c1 = host_to_mont<FqBN254>(B_BN_G2[1]);
-      rc = validate ? decompress_run<Wire2<FqBN254, false>, FqBN254, false, true>(n, d_in, cb, d_order, d_pts, g_status)
-                    : decompress_run<Wire2<FqBN254, false>, FqBN254, false, false>(n, d_in, cb, d_order, d_pts, g_status);
+      cb.psi_x.c0 = host_to_mont<FqBN254>(PSI_BN[0]);
+      cb.psi_x.c1 = host_to_mont<FqBN254>(PSI_BN[1]);
+      cb.psi_y.c0 = host_to_mont<FqBN254>(PSI_BN[2]);
+      cb.psi_y.c1 = host_to_mont<FqBN254>(PSI_BN[3]);
+      typedef Wire2<FqBN254, false> WW;
+      rc = validate == 1   ? decompress_run<WW, FqBN254, false, 1>(n, d_in, cb, d_order, d_pts, g_status)
+           : validate == 2 ? decompress_run<WW, FqBN254, false, 2>(n, d_in, cb, d_order, d_pts, g_status)
+                           : decompress_run<WW, FqBN254, false, 0>(n, d_in, cb, d_order, d_pts, g_status);
     }
   } else {
     if (group == 1) {
       CurveB<Fp<FqBLS381>> cb;
+      memset(&cb, 0, sizeof(cb));
       cb.b = host_to_mont<FqBLS381>(B_BLS_G1);
-      rc = validate ? decompress_run<Wire1<FqBLS381, true>, FqBLS381, true, true>(n, d_in, cb, d_order, d_pts, g_status)
-                    : decompress_run<Wire1<FqBLS381, true>, FqBLS381, true, false>(n, d_in, cb, d_order, d_pts, g_status);
+      typedef Wire1<FqBLS381, true> WW;
+      rc = validate ? decompress_run<WW, FqBLS381, true, 2>(n, d_in, cb, d_order, d_pts, g_status)
+                    : decompress_run<WW, FqBLS381, true, 0>(n, d_in, cb, d_order, d_pts, g_status);
     } else {
       CurveB<Fp2<FqBLS381>> cb;
       cb.b.c0 = host_to_mont<FqBLS381>(B_BLS_G1);
       cb.b.c1 = cb.b.c0;
-      rc = validate ? decompress_run<Wire2<FqBLS381, true>, FqBLS381, true, true>(n, d_in, cb, d_order, d_pts, g_status)
-                    : decompress_run<Wire2<FqBLS381, true>, FqBLS381, true, false>(n, d_in, cb, d_order, d_pts, g_status);
+      cb.psi_x.c0 = host_to_mont<FqBLS381>(PSI_BLS[0]);
+      cb.psi_x.c1 = host_to_mont<FqBLS381>(PSI_BLS[1]);
+      cb.psi_y.c0 = host_to_mont<FqBLS381>(PSI_BLS[2]);
+      cb.psi_y.c1 = host_to_mont<FqBLS381>(PSI_BLS[3]);
+      typedef Wire2<FqBLS381, true> WW;
+      rc = validate == 1   ? decompress_run<WW, FqBLS381, true, 1>(n, d_in, cb, d_order, d_pts, g_status)
+           : validate == 2 ? decompress_run<WW, FqBLS381, true, 2>(n, d_in, cb, d_order, d_pts, g_status)
+                           : decompress_run<WW, FqBLS381, true, 0>(n, d_in, cb, d_order, d_pts, g_status);
     }
   }
   if (rc) return rc;

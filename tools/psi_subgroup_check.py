@@ -1,10 +1,10 @@
-"""Groundwork for the endomorphism subgroup test of the G2 key decoder: pins the constants of
+"""CPU-side validation of the endomorphism subgroup test used by the G2 key decoder (csrc/codec.cu): pins the constants of
 psi (untwist-Frobenius-twist) numerically -- psi(P) = [p mod r] P on G2 -- and checks the two published membership criteria
 against the definition r * P = infinity with the oracle's curve arithmetic, on members, random non-members of E'(Fq2), pure
 cofactor-torsion points and member + torsion sums:
   BN254      [x+1]P + psi([x]P) + psi^2([x]P) = psi^3([2x]P),  x = 4965661367192848881   (eprint 2022/352, section 4.3)
   BLS12-381  psi(P) = [x]P,                                    x = -0xd201000000010000    (Scott, eprint 2021/1130)
-CPU only, about two minutes.  Nothing in the library uses this yet: zkb_points_decompress still checks r * P = infinity."""
+CPU only, a few seconds.  The constants printed here are the PSI_BN / PSI_BLS tables of csrc/codec.cu."""
 import os
 import random
 import sys

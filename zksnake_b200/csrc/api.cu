@@ -379,6 +379,11 @@ struct Groth16Pre {
   uint64_t r[4], s[4];
   uint64_t rd1[12], sd1[12], nrsd1[12], sd2[24];
   int inf_rd1 = 1, inf_sd1 = 1, inf_nrsd1 = 1, inf_sd2 = 1;
+  // single-GPU provers: A, s*A, B1, r*B1 computed by the host threads that finish the [U] and [V] MSMs, i.e. while the GPU
+  // is still busy with the remaining MSMs (groth16_msms); assemble uses them when `early` is set
+  bool early = false;
+  uint64_t A[12], sA[12], B1[12], rB1[12];
+  int infA = 1, inf_sA = 1, infB1 = 1, inf_rB1 = 1;
 };
 static void pre_join(Groth16Pre* p);
 
@@ -507,13 +512,48 @@ static int groth16_msms(zkb_groth16_pk* pk, const void* d_priv) {
   // the five host recombinations (~0.1-0.2 ms of 64-bit Montgomery arithmetic each) run on five host threads; each waits
   // for its own ticket's event, so they also overlap the reductions still running on the GPU
   int rcs[5] = {0, 0, 0, 0, 0};
+  // whole-key single-GPU proofs: the MSM results are final, so the threads that finish [U] (-> A) and [V] in G1 (-> B1) go on
+  // to s*A and r*B1, the two scalar multiplications of the assembly that depend on MSM results (~0.2 ms each), while the
+  // GPU still runs the later MSMs
+  Groth16Pre* pre = pk->pre;
+  const bool early = pre && pre->valid && pk->wworld == 1 && pk->len == pk->n && pk->klen == pk->n_kdelta;
+  if (pre) pre->early = false;
+  if (early) pre_join(pre);   // r*delta_1, s*delta_1 (started when r, s arrived; long done by now)
+  auto after = [&](int i) {
+    if (!early || rcs[i]) return;
+    const size_t g1 = affine_bytes(curve, 1);
+    if (slot[i] == 0) {
+      const uint64_t* pts[3] = {pk->msm_xy[0], pk->alpha1, pre->rd1};
+      int infs[3] = {pk->msm_inf[0], is_zero_pt(pk->alpha1, g1), pre->inf_rd1};
+      const uint64_t* sc[3] = {nullptr, nullptr, nullptr};
+      host_lincomb(curve, 1, 3, pts, infs, sc, pre->A, &pre->infA);
+      const uint64_t* p1[1] = {pre->A};
+      int i1[1] = {pre->infA};
+      const uint64_t* s1[1] = {pre->s};
+      host_lincomb(curve, 1, 1, p1, i1, s1, pre->sA, &pre->inf_sA);
+    } else if (slot[i] == 1) {
+      const uint64_t* pts[3] = {pk->msm_xy[1], pk->beta1, pre->sd1};
+      int infs[3] = {pk->msm_inf[1], is_zero_pt(pk->beta1, g1), pre->inf_sd1};
+      const uint64_t* sc[3] = {nullptr, nullptr, nullptr};
+      host_lincomb(curve, 1, 3, pts, infs, sc, pre->B1, &pre->infB1);
+      const uint64_t* p1[1] = {pre->B1};
+      int i1[1] = {pre->infB1};
+      const uint64_t* s1[1] = {pre->r};
+      host_lincomb(curve, 1, 1, p1, i1, s1, pre->rB1, &pre->inf_rB1);
+    }
+  };
   std::thread th[4];
   for (int i = 1; i < 5; i++)
-    th[i - 1] = std::thread([&, i]() { rcs[i] = msm_finish(&tk[i], pk->msm_xy[slot[i]], &pk->msm_inf[slot[i]]); });
+    th[i - 1] = std::thread([&, i]() {
+      rcs[i] = msm_finish(&tk[i], pk->msm_xy[slot[i]], &pk->msm_inf[slot[i]]);
+      after(i);
+    });
   rcs[0] = msm_finish(&tk[0], pk->msm_xy[slot[0]], &pk->msm_inf[slot[0]]);
+  after(0);
   for (int i = 0; i < 4; i++) th[i].join();
   for (int i = 0; i < 5; i++)
     if (rcs[i]) return set_error(rcs[i], "msm_finish failed in the Groth16 MSM batch");
+  if (early) pre->early = true;
   return ZKB_OK;
 }
 
@@ -529,6 +569,7 @@ static void pre_start(zkb_groth16_pk* pk, const uint64_t r[4], const uint64_t s[
   if (!pk->pre) pk->pre = new Groth16Pre();
   Groth16Pre* p = pk->pre;
   pre_join(p);
+  p->early = false;   // whatever was derived from an earlier (r, s) is void
   memcpy(p->r, r, 32);
   memcpy(p->s, s, 32);
   const int curve = pk->curve;
@@ -593,38 +634,52 @@ int zkb_groth16_assemble(zkb_groth16_pk* pk, const uint64_t* msm_xy, const int* 
   int inf_alpha = is_zero_pt(pk->alpha1, g1), inf_beta1 = is_zero_pt(pk->beta1, g1), inf_beta2 = is_zero_pt(pk->beta2, g2);
   uint64_t A[12], B1[12], sA[12], rB1[12];
   int infA, infB1, infB2, infC, inf_sA, inf_rB1;
-  {
-    const uint64_t* pts[3] = {mx[0], pk->alpha1, pre->rd1};
-    int infs[3] = {msm_inf[0], inf_alpha, pre->inf_rd1};
-    const uint64_t* sc[3] = {nullptr, nullptr, nullptr};
-    host_lincomb(curve, 1, 3, pts, infs, sc, A, &infA);
+  const bool early = pre->early && msm_xy == &pk->msm_xy[0][0];
+  pre->early = false;
+  std::thread th_sa, th_rb;
+  if (early) {
+    memcpy(A, pre->A, sizeof(A));
+    memcpy(sA, pre->sA, sizeof(sA));
+    memcpy(B1, pre->B1, sizeof(B1));
+    memcpy(rB1, pre->rB1, sizeof(rB1));
+    infA = pre->infA;
+    inf_sA = pre->inf_sA;
+    infB1 = pre->infB1;
+    inf_rB1 = pre->inf_rB1;
+  } else {
+    {
+      const uint64_t* pts[3] = {mx[0], pk->alpha1, pre->rd1};
+      int infs[3] = {msm_inf[0], inf_alpha, pre->inf_rd1};
+      const uint64_t* sc[3] = {nullptr, nullptr, nullptr};
+      host_lincomb(curve, 1, 3, pts, infs, sc, A, &infA);
+    }
+    th_sa = std::thread([&]() {
+      const uint64_t* pts[1] = {A};
+      int infs[1] = {infA};
+      const uint64_t* sc[1] = {s};
+      host_lincomb(curve, 1, 1, pts, infs, sc, sA, &inf_sA);
+    });
+    {
+      const uint64_t* pts[3] = {mx[1], pk->beta1, pre->sd1};
+      int infs[3] = {msm_inf[1], inf_beta1, pre->inf_sd1};
+      const uint64_t* sc[3] = {nullptr, nullptr, nullptr};
+      host_lincomb(curve, 1, 3, pts, infs, sc, B1, &infB1);
+    }
+    th_rb = std::thread([&]() {
+      const uint64_t* pts[1] = {B1};
+      int infs[1] = {infB1};
+      const uint64_t* sc[1] = {r};
+      host_lincomb(curve, 1, 1, pts, infs, sc, rB1, &inf_rB1);
+    });
   }
-  std::thread th_sa([&]() {
-    const uint64_t* pts[1] = {A};
-    int infs[1] = {infA};
-    const uint64_t* sc[1] = {s};
-    host_lincomb(curve, 1, 1, pts, infs, sc, sA, &inf_sA);
-  });
-  {
-    const uint64_t* pts[3] = {mx[1], pk->beta1, pre->sd1};
-    int infs[3] = {msm_inf[1], inf_beta1, pre->inf_sd1};
-    const uint64_t* sc[3] = {nullptr, nullptr, nullptr};
-    host_lincomb(curve, 1, 3, pts, infs, sc, B1, &infB1);
-  }
-  std::thread th_rb([&]() {
-    const uint64_t* pts[1] = {B1};
-    int infs[1] = {infB1};
-    const uint64_t* sc[1] = {r};
-    host_lincomb(curve, 1, 1, pts, infs, sc, rB1, &inf_rB1);
-  });
   {
     const uint64_t* pts[3] = {mx[2], pk->beta2, pre->sd2};
     int infs[3] = {msm_inf[2], inf_beta2, pre->inf_sd2};
     const uint64_t* sc[3] = {nullptr, nullptr, nullptr};
     host_lincomb(curve, 2, 3, pts, infs, sc, out_b, &infB2);
   }
-  th_sa.join();
-  th_rb.join();
+  if (th_sa.joinable()) th_sa.join();
+  if (th_rb.joinable()) th_rb.join();
   {
     const uint64_t* pts[5] = {mx[3], mx[4], sA, rB1, pre->nrsd1};
     int infs[5] = {msm_inf[3], msm_inf[4], inf_sA, inf_rB1, pre->inf_nrsd1};

@@ -88,35 +88,7 @@ def main():
                       "imad_wide_frac": n * ops / (ms * 1e-3) / wide.value})
                 d_s.free()
             d_pts.free()
-    # ---- CPU restatement beside it (oracle/cport: ark-style radix-2 FFT and Pippenger), bounded sizes, 1 thread (what the
-    #      shipped reference wheel does) and all host threads
-    try:
-        import time
-        from oracle import cport
-        cport.build()
-        nthreads = cport.threads()
-        for curve, cname in ((0, "BN254"), (1, "BLS12_381")):
-            for log_n in (16, 20):
-                a = pp.rand_fr(1 << log_n, log_n, curve)
-                for th in (1, nthreads):
-                    cport.fft(curve, a, log_n, nthreads=th)
-                    t0 = time.perf_counter()
-                    cport.fft(curve, a, log_n, nthreads=th)
-                    ms = (time.perf_counter() - t0) * 1e3
-                    emit({"kind": "cpu_ntt", "curve": cname, "log_n": log_n, "threads": th, "ms": ms,
-                          "gelem_s": (1 << log_n) / ms / 1e6, "impl": "oracle/cport (C++ restatement)"})
-            for log_n in (16, 18):
-                n = 1 << log_n
-                pts = cport.chain_points(curve, 1, 7, n)
-                sc = pp.rand_fr(n, 1000 + log_n, curve)
-                for th in (1, nthreads):
-                    t0 = time.perf_counter()
-                    cport.msm(curve, 1, pts, sc, nthreads=th)
-                    ms = (time.perf_counter() - t0) * 1e3
-                    emit({"kind": "cpu_msm_g1", "curve": cname, "log_n": log_n, "threads": th, "ms": ms, "mpts_s": n / ms / 1e3,
-                          "impl": "oracle/cport (C++ restatement)"})
-    except Exception as exc:  # the checker is not the product
-        emit({"kind": "cpu", "unavailable": repr(exc)})
+    # (the CPU restatement beside these numbers is timed by tests/cpu_sweep.py: only tests/ and bench.py's CPU legs run oracle/)
     out.close()
 
 

@@ -182,7 +182,7 @@ struct CurveB {
 // that replace the 254-bit scalar by the 63/64-bit curve parameter x (psi acts on G2 as multiplication by p):
 //   BN254      [x+1]P + psi([x]P) + psi^2([x]P) = psi^3([2x]P)      (El Housni, Guillevic, Piellard, eprint 2022/352, section 4.3)
 //   BLS12-381  psi(P) = [x]P, x < 0                                (Scott, eprint 2021/1130)
-// Both are proven equivalent to the definition for points of E'(Fq2); tools/psi_subgroup_check.py pins the constants and checks
+// Both are proven equivalent to the definition for points of E'(Fq2); tests/test_psi_constants.py pins the constants and checks
 // them against r * P on members, random non-members, cofactor-torsion points and mixtures; tests/test_gpu_codec.py checks
 // the kernel against the oracle's r * P on the same kinds of points.
 template <class P>

@@ -152,6 +152,82 @@ ZKB_HD Fp<P> redc(uint32_t* t) {
   return r;
 }
 
+// ---- dedicated squaring (experimental, unused by the kernels; host-tested through zkb_test_field_op_host op 5) ----
+// a^2 needs each off-diagonal product a_i a_j only once: N(N-1)/2 + N wide multiply-adds instead of N^2, then the same
+// reduction -- 100 + 8 multiplier-pipe instructions instead of 128 + 8 for N = 8.  SASS of a squaring loop (sm_100a, CUDA 12.9,
+// build/sq experiment of round 1): BN254 92 IMAD.WIDE + 34 other multiplier-pipe instructions (IMAD, IMAD.HI, IMAD.MOV,
+// IMAD.X) against 120 + 18 for a * a, i.e. ~436 against ~516 pipe cycles per warp (-15 %); BLS12-381 210 + 41 against
+// 276 + 26 (-20 %); the price is ~85 more alu-pipe instructions (doubling, merging the column chains), which have slack.
+// NOT YET MEASURED on the GPU: 2 of the 10 products of a mixed addition, 3 of the 9 of a doubling and two thirds of a
+// square-root / inversion chain are squarings.
+// t[0..2N) = a^2 : off-diagonal products once (even/odd column chains), doubled, plus the diagonal squares
+template <int N>
+ZKB_HD void sqr_limbs(const uint32_t* a, uint32_t* t) {
+  uint32_t ev[2 * N], od[2 * N];
+#pragma unroll
+  for (int k = 0; k < 2 * N; k++) ev[k] = od[k] = 0;
+  // row i multiplies a_i with a_j, j > i; products landing on even columns (i + j even) and odd columns separately
+#pragma unroll
+  for (int i = 0; i < N - 1; i++) {
+    const uint32_t ai = a[i];
+    {  // j = i + 2, i + 4, ... : column i + j has the parity of 2i = even
+      bool first = true;
+#pragma unroll
+      for (int j = i + 2; j < N; j += 2) {
+        const int c = i + j;
+        if (first) { ev[c] = mad_lo_cc(a[j], ai, ev[c]); first = false; }
+        else ev[c] = madc_lo_cc(a[j], ai, ev[c]);
+        ev[c + 1] = madc_hi_cc(a[j], ai, ev[c + 1]);
+      }
+      if (!first) {
+        // carry out of the chain lands on the next even column pair start: column (i + last j) + 2
+        int last = i + 2 + ((N - 1 - (i + 2)) / 2) * 2;
+        int c = i + last + 2;
+        if (c < 2 * N) ev[c] = addc(ev[c], 0u);
+      }
+    }
+    {  // j = i + 1, i + 3, ... : odd columns
+      bool first = true;
+#pragma unroll
+      for (int j = i + 1; j < N; j += 2) {
+        const int c = i + j;
+        if (first) { od[c] = mad_lo_cc(a[j], ai, od[c]); first = false; }
+        else od[c] = madc_lo_cc(a[j], ai, od[c]);
+        od[c + 1] = madc_hi_cc(a[j], ai, od[c + 1]);
+      }
+      if (!first) {
+        int last = i + 1 + ((N - 1 - (i + 1)) / 2) * 2;
+        int c = i + last + 2;
+        if (c < 2 * N) od[c] = addc(od[c], 0u);
+      }
+    }
+  }
+  // merge, double
+  t[0] = 0;
+  t[1] = add_cc(ev[1], od[1]);
+#pragma unroll
+  for (int k = 2; k < 2 * N - 1; k++) t[k] = addc_cc(ev[k], od[k]);
+  t[2 * N - 1] = addc(ev[2 * N - 1], od[2 * N - 1]);
+  t[1] = add_cc(t[1], t[1]);
+#pragma unroll
+  for (int k = 2; k < 2 * N - 1; k++) t[k] = addc_cc(t[k], t[k]);
+  t[2 * N - 1] = addc(t[2 * N - 1], t[2 * N - 1]);
+  // diagonal
+  t[0] = mad_lo_cc(a[0], a[0], t[0]);
+  t[1] = madc_hi_cc(a[0], a[0], t[1]);
+#pragma unroll
+  for (int i = 1; i < N; i++) {
+    t[2 * i] = madc_lo_cc(a[i], a[i], t[2 * i]);
+    t[2 * i + 1] = madc_hi_cc(a[i], a[i], t[2 * i + 1]);
+  }
+}
+template <class P>
+ZKB_HD Fp<P> mont_sqr_split(const Fp<P>& a) {
+  uint32_t t[2 * P::N];
+  sqr_limbs<P::N>(a.v, t);
+  return redc<P>(t);
+}
+
 template <class P>
 ZKB_HD Fp<P> mont_mul_split(const Fp<P>& a, const Fp<P>& b) {
   uint32_t t[2 * P::N];

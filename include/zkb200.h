@@ -120,6 +120,9 @@ int zkb_fr_scan_dev(int curve, int op, size_t n, const void* d_x, void* d_out);
 int zkb_fr_gather_dev(int curve, size_t n, const void* d_src, size_t stride, size_t offset, void* d_out);  /* src[offset + i*stride] */
 int zkb_fr_gather_index_dev(int curve, size_t n, const void* d_src, const void* d_idx_u32, void* d_out);   /* src[idx[i]] */
 int zkb_fr_eval_dev(int curve, size_t n, const void* d_coeffs, const uint64_t point[4], uint64_t out[4]);   /* sum c_i z^i (sync) */
+/* *len = number of coefficients left after stripping trailing zeros (0 for the zero vector): the DensePolynomial invariant behind
+ * Polynomial.coeffs() / degree() / is_zero() (src/bn254/polynomial.rs:132-160, 440) for a device-resident coefficient vector (sync) */
+int zkb_fr_trim_dev(int curve, size_t n, const void* d_x, size_t* len);
 /* q = p / (X^d - 1) (len - d coefficients, polynomial.rs:466-489); *exact = 0 when the remainder is non-zero (sync) */
 int zkb_fr_div_vanishing_dev(int curve, size_t len, size_t d, const void* d_p, void* d_q, int* exact);
 /* PlonK quotient evaluations on the coset g<w_q> of size q (2n..8n) in one pass (python/zksnake/plonk/protocol.py:240-262, 284-300,

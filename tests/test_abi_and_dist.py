@@ -129,13 +129,25 @@ def _gather_worker(rank, world, port, q):
     from zksnake_b200 import dist
     arr = np.arange(6, dtype=np.uint64).reshape(2, 3) + 100 * rank
     got = dist.all_gather_array(arr)
-    rnd = dist.shared_random(lambda n_max: 12345 + rank)     # each rank would draw something different on its own
-    vals = [rnd(10 ** 30) for _ in range(3)]
+    import random
+    own = random.Random(100 + rank)                          # each rank would draw something different on its own
+    hook = lambda n_max: own.randint(1, n_max)               # noqa: E731
+    vals = dist.shared_draws(hook, 10 ** 30, 3, 2) + [dist.shared_random(hook)(10 ** 30)]
+    try:
+        dist.require_world(0, 3)
+        vals.append("no error")
+    except RuntimeError:
+        pass
+    try:
+        dist.shared_draws(hook, 10, 1, world_size=4)
+        vals.append("no error")
+    except RuntimeError:
+        pass
     q.put((rank, got.tolist(), vals))
     td.destroy_process_group()
 
 
-def test_all_gather_array_and_shared_random_gloo():
+def test_all_gather_array_and_shared_draws_gloo():
     """world-size-2 gloo run of the helpers the multi-GPU provers rely on: every rank sees every rank's array, and the shared
     random stream is identical everywhere (it is derived from rank 0's draw)."""
     import multiprocessing as mp
@@ -150,4 +162,18 @@ def test_all_gather_array_and_shared_random_gloo():
         p.join(timeout=60)
     want = [[[0, 1, 2], [3, 4, 5]], [[100, 101, 102], [103, 104, 105]]]
     assert res[0][1] == want and res[1][1] == want
-    assert res[0][2] == res[1][2] and len(set(res[0][2])) == 3 and all(1 <= v <= 10 ** 30 for v in res[0][2])
+    import random
+    rank0 = random.Random(100)
+    assert res[0][2] == res[1][2] == [rank0.randint(1, 10 ** 30) for _ in range(4)]    # the values ARE rank 0's draws
+
+
+def test_sharded_prover_needs_a_matching_process_group():
+    """an explicit shard=(rank, world) without a torch.distributed world of that size must raise, not prove from one
+    slice with private randomness."""
+    from zksnake_b200 import dist
+    dist.require_world(0, 1)
+    dist.require_world(1, 4, emulate=True)
+    with pytest.raises(RuntimeError, match="torch.distributed world"):
+        dist.require_world(1, 4)
+    with pytest.raises(RuntimeError):
+        dist.shared_draws(lambda n: 1, 10, 2, world_size=2)

@@ -148,7 +148,7 @@ def test_groth16_keys_round_trip_and_prove(gpu, curve_name):
     vk_bytes = g.verifying_key.to_bytes()
     # layout against the oracle's encodings of the closed-form key elements
     G1, G2 = group(cid), group(cid, True)
-    tau, alpha, beta, gamma, delta = g.toxic
+    tau, alpha, beta, gamma, delta = st.tau, st.alpha, st.beta, st.gamma, st.delta
     n = g.n
     head = (G1.to_bytes(G1.mul(G1.gen, alpha)) + G2.to_bytes(G2.mul(G2.gen, beta)) + G2.to_bytes(G2.mul(G2.gen, delta))
             + G1.to_bytes(G1.mul(G1.gen, beta)) + G1.to_bytes(G1.mul(G1.gen, delta)))

@@ -64,6 +64,7 @@ def _load():
         "zkb_fr_gather_dev": (c_int, [c_int, c_sz, c_vp, c_sz, c_sz, c_vp]),
         "zkb_fr_gather_index_dev": (c_int, [c_int, c_sz, c_vp, c_vp, c_vp]),
         "zkb_fr_eval_dev": (c_int, [c_int, c_sz, c_vp, c_vp, c_vp]),
+        "zkb_fr_trim_dev": (c_int, [c_int, c_sz, c_vp, ctypes.POINTER(c_sz)]),
         "zkb_fr_div_vanishing_dev": (c_int, [c_int, c_sz, c_sz, c_vp, c_vp, ctypes.POINTER(c_int)]),
         "zkb_plonk_quotient_dev": (c_int, [c_int, c_sz, c_sz, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "zkb_fr_add_sparse_dev": (c_int, [c_int, c_vp, c_sz, c_vp, c_vp, c_int]),
@@ -154,15 +155,39 @@ def gpu_available():
 
 
 # ---- numpy <-> Python int helpers (little-endian limbs) --------------------------------------------------------
-def ints_to_limbs(values, nbytes=32):
-    """list[int] -> uint64 array of shape (len, nbytes/8).  Values must be in [0, 2^(8 nbytes))."""
-    buf = b"".join(int(v).to_bytes(nbytes, "little") for v in values)
-    return np.frombuffer(buf, dtype=np.uint64).reshape(len(values), nbytes // 8).copy()
+try:
+    from . import _marshal   # CPython extension built next to libzkb200.so (csrc/pymarshal.cpp)
+except ImportError as exc:   # fail loudly: there is no pure-Python marshalling path
+    raise ImportError(f"zksnake_b200._marshal is missing ({exc}): build it with "
+                      "`python -c 'import __graft_entry__ as g; g.build()'`") from exc
+
+
+def ints_to_limbs(values, nbytes=32, modulus=None, out=None, item=-1, allow_negative=True):
+    """list[int] -> uint64 array of shape (len, nbytes/8), read straight from the PyLong digits by host threads
+    (csrc/pymarshal.cpp; the reference does this one BigUint at a time: src/bn254/polynomial.rs:537-540).  Values must be in
+    [0, 2^(8 nbytes)) unless `modulus` is given, in which case negative / oversized values are reduced mod it.  `out`: an
+    existing C-contiguous uint64 array of that shape (e.g. a view of pinned host memory) to fill instead of a new one.
+    item >= 0: the elements are tuples and the integer is element[item] (the (coeff, terms) pairs the reference's Polynomial
+    constructor passes, python/zksnake/polynomial.py:40-43).  allow_negative=False: a negative value raises OverflowError (what
+    pyo3's BigUint extraction does) instead of being reduced."""
+    if not isinstance(values, (list, tuple)):
+        values = list(values)
+    k = nbytes // 8
+    arr = out if out is not None else np.empty((len(values), k), dtype=np.uint64)
+    assert arr.dtype == np.uint64 and arr.flags["C_CONTIGUOUS"] and arr.size == len(values) * k
+    try:
+        _marshal.ints_to_limbs(values, arr.ctypes.data, k, modulus, item, allow_negative)
+    except TypeError:
+        if item >= 0:
+            raise
+        _marshal.ints_to_limbs([int(v) for v in values], arr.ctypes.data, k, modulus, -1, allow_negative)   # numpy integers and other __index__ types
+    return arr
 
 
 def limbs_to_ints(arr, nbytes=32):
-    raw = np.ascontiguousarray(arr).tobytes()
-    return [int.from_bytes(raw[i:i + nbytes], "little") for i in range(0, len(raw), nbytes)]
+    arr = np.ascontiguousarray(arr, dtype=np.uint64)
+    k = nbytes // 8
+    return _marshal.limbs_to_ints(arr.ctypes.data, arr.size // k, k)
 
 
 def ptr(a):

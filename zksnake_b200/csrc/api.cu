@@ -12,7 +12,8 @@ using namespace zkb;
 
 static inline cudaStream_t S() { return (cudaStream_t)ctx_stream(); }
 #define NEED_INIT() \
-  if (!ctx_ready()) return set_error(ZKB_ERR_NOINIT, "zkb_init has not been called (no CUDA context; no CPU fallback)")
+  if (!ctx_ready()) return set_error(ZKB_ERR_NOINIT, "zkb_init has not been called (no CUDA context; no CPU fallback)"); \
+  ZKB_ENTRY_GUARD()
 #define CHECK_CURVE(c) \
   if ((c) != ZKB_BN254 && (c) != ZKB_BLS12_381) return set_error(ZKB_ERR_ARG, "unknown curve id")
 #define CHECK_GROUP(g) \
@@ -722,6 +723,12 @@ int zkb_groth16_prove(zkb_groth16_pk* pk, const uint64_t* a, const uint64_t* b, 
   ZKB_CUDA(ZKB_H2D(w + bytes, b, bytes));
   ZKB_CUDA(ZKB_H2D(w + 2 * bytes, c, bytes));
   if (pk->n_kdelta) ZKB_CUDA(ZKB_H2D(d_priv, priv, pk->n_kdelta * 32));
+  // host values may be any 256-bit integers (header contract: reduced mod r like Fr::from(BigUint)); the signed-digit walk of
+  // the MSM assumes canonical scalars
+  int rc;
+  for (int i = 0; i < 3; i++)
+    if ((rc = fr_reduce_dev(pk->curve, pk->n, w + i * bytes))) return rc;
+  if ((rc = fr_reduce_dev(pk->curve, pk->n_kdelta, d_priv))) return rc;
   return zkb_groth16_prove_dev(pk, w, w + bytes, w + 2 * bytes, d_priv, r, s, out_a, out_b, out_c, out_inf);
 }
 

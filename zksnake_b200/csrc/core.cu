@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <mutex>
+#include <thread>
 #include <vector>
 #include "../../include/zkb200.h"
 #include "zkb_internal.h"
@@ -31,6 +32,22 @@ int cuda_fail(int cuda_err, const char* what, const char* file, int line) {
   snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", cuda_err, cudaGetErrorString((cudaError_t)cuda_err), file,
            line, what);
   return set_error(ZKB_ERR_CUDA, buf);
+}
+static std::mutex g_entry_mutex;
+static std::thread::id g_entry_owner;
+static int g_entry_depth = 0;
+EntryGuard::EntryGuard() {
+  std::lock_guard<std::mutex> lk(g_entry_mutex);
+  ok = g_entry_depth == 0 || g_entry_owner == std::this_thread::get_id();
+  if (ok) {
+    g_entry_owner = std::this_thread::get_id();
+    g_entry_depth++;
+  }
+}
+EntryGuard::~EntryGuard() {
+  if (!ok) return;
+  std::lock_guard<std::mutex> lk(g_entry_mutex);
+  g_entry_depth--;
 }
 void* ctx_stream() { return (void*)g_ctx.stream; }
 void* ctx_side_stream(int i) {
@@ -205,7 +222,8 @@ void zkb_transfer_count(unsigned long long* h2d_bytes, unsigned long long* d2h_b
 }
 
 #define NEED_INIT() \
-  if (!g_ctx.ready) return set_error(ZKB_ERR_NOINIT, "zkb_init has not been called (no CUDA context; no CPU fallback)")
+  if (!g_ctx.ready) return set_error(ZKB_ERR_NOINIT, "zkb_init has not been called (no CUDA context; no CPU fallback)"); \
+  ZKB_ENTRY_GUARD()
 
 int zkb_sync(void) {
   NEED_INIT();

@@ -215,6 +215,23 @@ __global__ void div_vanishing_kernel(unsigned long long len, unsigned long long 
   }
 }
 
+// *out = max(*out, i + 1) over the non-zero x[i]: the length of the vector with trailing zeros stripped (ark's
+// DensePolynomial invariant, /root/reference/src/bn254/polynomial.rs:132-140 `coeffs()` returns the stripped vector)
+template <class F>
+__global__ void trim_kernel(unsigned long long n, const F* __restrict__ x, unsigned long long* out) {
+  unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  unsigned long long best = 0;
+  for (; i < n; i += stride)
+    if (!ntt_ld(x + i).is_zero()) best = i + 1;
+  // warp maximum first: one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long other = __shfl_down_sync(0xffffffffu, best, o);
+    if (other > best) best = other;
+  }
+  if ((threadIdx.x & 31) == 0 && best) atomicMax(out, best);
+}
+
 // v[idx[k]] += / -= vals[k] for up to 8 entries passed BY VALUE (no staging copy, no synchronisation)
 template <class F>
 struct SparseArgs {
@@ -384,6 +401,27 @@ struct FrVecOps {
     memcpy(out, acc.v, 32);
     return ZKB_OK;
   }
+  static int trim(size_t n, const void* x, size_t* len) {
+    *len = 0;
+    if (n == 0) return ZKB_OK;
+    int rc;
+    if ((rc = scratch_reserve(4096))) return rc;
+    scratch_reset();
+    unsigned long long* d_len = (unsigned long long*)scratch_take(256);
+    ZKB_CUDA(cudaMemsetAsync(d_len, 0, sizeof(unsigned long long), S()));
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    prof_begin(PROF_VEC);
+    trim_kernel<F><<<blocks, 256, 0, S()>>>(n, (const F*)x, d_len);
+    prof_end(PROF_VEC);
+    count_launch();
+    ZKB_CUDA(cudaGetLastError());
+    unsigned long long h = 0;
+    ZKB_CUDA(ZKB_D2H(&h, d_len, sizeof(h)));
+    ZKB_CUDA(cudaStreamSynchronize(S()));
+    *len = (size_t)h;
+    return ZKB_OK;
+  }
   static int div_vanishing(size_t len, size_t d, const void* p, void* q, int* exact) {
     *exact = 1;
     if (len <= d) return ZKB_OK;   // quotient is zero, remainder is p itself: exact iff p == 0 (caller's business)
@@ -453,7 +491,8 @@ struct FrVecOps {
 using namespace zkb;
 
 #define NEED_INIT() \
-  if (!ctx_ready()) return set_error(ZKB_ERR_NOINIT, "zkb_init has not been called (no CUDA context; no CPU fallback)")
+  if (!ctx_ready()) return set_error(ZKB_ERR_NOINIT, "zkb_init has not been called (no CUDA context; no CPU fallback)"); \
+  ZKB_ENTRY_GUARD()
 #define BY_CURVE(EXPR_BN, EXPR_BLS)               \
   if (curve == ZKB_BN254) return EXPR_BN;         \
   if (curve == ZKB_BLS12_381) return EXPR_BLS;    \
@@ -492,6 +531,11 @@ int zkb_fr_gather_index_dev(int curve, size_t n, const void* d_src, const void* 
 int zkb_fr_eval_dev(int curve, size_t n, const void* d_coeffs, const uint64_t point[4], uint64_t out[4]) {
   NEED_INIT();
   BY_CURVE(FrVecOps<fr_bn>::eval(n, d_coeffs, point, out), FrVecOps<fr_bls>::eval(n, d_coeffs, point, out))
+}
+int zkb_fr_trim_dev(int curve, size_t n, const void* d_x, size_t* len) {
+  NEED_INIT();
+  if (!len) return set_error(ZKB_ERR_ARG, "trim: null output");
+  BY_CURVE(FrVecOps<fr_bn>::trim(n, d_x, len), FrVecOps<fr_bls>::trim(n, d_x, len))
 }
 int zkb_fr_div_vanishing_dev(int curve, size_t len, size_t d, const void* d_p, void* d_q, int* exact) {
   NEED_INIT();

@@ -100,19 +100,33 @@ int msm_enqueue_batch(int curve, const MsmJob* jobs, int njobs, uint32_t wr, uin
   // job's sort and accumulation (the accumulation is a work-stealing persistent grid, so it tolerates the few CTAs slots the
   // short reduction kernels borrow); join at the end so later library work is ordered after all of them
   static cudaEvent_t fork_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool forked[8] = {false, false, false, false, false, false, false, false};
+  // on a mid-batch failure the reductions already forked keep running on their side streams over the shared scratch arena:
+  // order the library stream after them before handing the error back, so that the caller's next scratch epoch cannot race them
+  auto fail = [&](int code) {
+    for (int j = 0; j < njobs; j++)
+      if (forked[j] && tickets[j].event) cudaStreamWaitEvent(main_st, (cudaEvent_t)tickets[j].event, 0);
+    return code;
+  };
   for (int i = 0; i < njobs; i++) {
     // reuse the digit sort of an earlier job over the same scalars (phase 1 checks that the geometry matches too)
     const MsmTicket* share = nullptr;
     for (int j = 0; j < i && !share; j++)
       if (!tickets[j].empty && jobs[j].scalars == jobs[i].scalars && jobs[j].n == jobs[i].n) share = &tickets[j];
-    if ((rc = msm_phase1(curve, jobs[i], wr, ww, share, &tickets[i]))) return rc;
+    if ((rc = msm_phase1(curve, jobs[i], wr, ww, share, &tickets[i]))) return fail(rc);
     if (tickets[i].empty) continue;
-    if (!fork_ev[i]) ZKB_CUDA(cudaEventCreateWithFlags(&fork_ev[i], cudaEventDisableTiming));
+    cudaError_t ce = cudaSuccess;
+    if (!fork_ev[i]) ce = cudaEventCreateWithFlags(&fork_ev[i], cudaEventDisableTiming);
     cudaStream_t side = (cudaStream_t)ctx_side_stream(i);
-    if (!side) return set_error(ZKB_ERR_CUDA, "msm batch: cannot create a side stream");
-    ZKB_CUDA(cudaEventRecord(fork_ev[i], main_st));
-    ZKB_CUDA(cudaStreamWaitEvent(side, fork_ev[i], 0));
-    if ((rc = msm_phase2(&tickets[i], side))) return rc;
+    if (ce != cudaSuccess || !side) return fail(set_error(ZKB_ERR_CUDA, "msm batch: cannot create a side stream"));
+    if ((ce = cudaEventRecord(fork_ev[i], main_st)) != cudaSuccess || (ce = cudaStreamWaitEvent(side, fork_ev[i], 0)) != cudaSuccess)
+      return fail(cuda_fail((int)ce, "msm batch fork", __FILE__, __LINE__));
+    rc = msm_phase2(&tickets[i], side);
+    forked[i] = true;   // (whatever phase 2 enqueued before failing is on the side stream; its event may not be recorded yet)
+    if (rc) {
+      cudaEventRecord((cudaEvent_t)tickets[i].event, side);
+      return fail(rc);
+    }
   }
   prof_begin(PROF_MSM_REDUCE);   // what is left of the reductions after the last accumulation
   for (int i = 0; i < njobs; i++)

@@ -31,6 +31,18 @@ int cuda_fail(int cuda_err, const char* what, const char* file, int line);
     if (e_ != cudaSuccess) return zkb::cuda_fail((int)e_, #x, __FILE__, __LINE__); \
   } while (0)
 
+// One host thread drives the library (include/zkb200.h, "Conventions"): entry points share one stream, one scratch arena and
+// per-call result tickets.  EntryGuard makes that contract checked instead of assumed: the first thread inside an entry point
+// owns the library until it leaves (nested entry-point calls of the same thread are fine); a second thread gets ZKB_ERR_ARG.
+struct EntryGuard {
+  bool ok;
+  EntryGuard();
+  ~EntryGuard();
+};
+#define ZKB_ENTRY_GUARD()     \
+  zkb::EntryGuard guard_;      \
+  if (!guard_.ok) return zkb::set_error(ZKB_ERR_ARG, "libzkb200 entry points are not re-entrant: another host thread is inside the library")
+
 void* ctx_stream();                 // cudaStream_t
 void* ctx_side_stream(int i);       // cudaStream_t, i < 8 (created on first use); nullptr on failure
 bool ctx_ready();

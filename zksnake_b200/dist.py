@@ -134,22 +134,35 @@ def all_gather_array(arr, device=None):
     return out.cpu().numpy().view(arr.dtype).reshape((ws,) + arr.shape)
 
 
-def shared_random(draw):
-    """Randomness every rank agrees on.  `draw(n_max)` is the module's get_random_int hook (uniform in [1, n_max]).  With one
-    rank this IS `draw`.  With several, rank 0 draws one 256-bit seed, it is all-gathered once, and every rank expands it with
-    blake2b in counter mode -- toxic waste, prover randomness and blinding scalars must be identical everywhere, otherwise the
-    ranks' partial sums belong to different keys / proofs."""
-    import hashlib
+def require_world(rank, world_size, emulate=False):
+    """An explicit shard=(rank, world) must BE the torch.distributed world: the cooperative provers draw shared randomness and
+    exchange partial sums with collectives, and without a process group of that size every rank would silently produce a proof
+    from its own slice and its own randomness.  `emulate=True` (tests that drive zkb_groth16_partial / assemble rank by rank in one
+    process) skips the check; the collectives below then refuse to run."""
+    if world_size == 1 or emulate:
+        return
+    if world() != (rank, world_size):
+        raise RuntimeError(f"shard=({rank}, {world_size}) but the torch.distributed world is {world()}: initialise a process "
+                           "group of that size (torchrun) before constructing a sharded prover")
+
+
+def shared_draws(draw, n_max, count, world_size=None):
+    """`count` values of the randomness hook `draw(n_max)` (uniform in [1, n_max]) that every rank agrees on: rank 0 draws
+    them, one small all-gather hands them to everybody.  Toxic waste, prover randomness and blinding scalars must be identical
+    on every rank, otherwise the partial sums belong to different keys / proofs.  Because the values ARE rank 0's draws, a
+    seeded hook gives the same key and the same proof bytes at every world size (bench.py's `proof_sha`)."""
     rank, ws = world()
+    if world_size is not None and world_size > 1 and ws != world_size:
+        raise RuntimeError(f"shared randomness for {world_size} ranks needs a torch.distributed world of that size (have {ws})")
+    mine = [int(draw(n_max)) for _ in range(count)] if (rank == 0 or ws == 1) else [0] * count
     if ws == 1:
-        return draw
-    seed = np.frombuffer(int(draw((1 << 256) - 1)).to_bytes(32, "little"), dtype=np.uint8).copy()
-    seed = bytes(all_gather_array(seed)[0])
-    state = {"ctr": 0}
+        return mine
+    nbytes = (max(int(n_max).bit_length(), 1) + 7) // 8
+    raw = np.frombuffer(b"".join(v.to_bytes(nbytes, "little") for v in mine), dtype=np.uint8).copy()
+    got = bytes(all_gather_array(raw)[0])
+    return [int.from_bytes(got[i * nbytes:(i + 1) * nbytes], "little") for i in range(count)]
 
-    def shared(n_max):
-        state["ctr"] += 1
-        h = hashlib.blake2b(seed + state["ctr"].to_bytes(8, "little"), digest_size=64).digest()
-        return 1 + int.from_bytes(h, "little") % n_max
 
-    return shared
+def shared_random(draw):
+    """Function form of shared_draws for call sites that draw one value at a time (one collective per draw)."""
+    return lambda n_max: shared_draws(draw, n_max, 1)[0]

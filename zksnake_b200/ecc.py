@@ -1,29 +1,51 @@
-"""`EllipticCurve` facade over the `_algebra` ec modules -- the host-side counterpart of the reference's
-python/zksnake/ecc.py:47-142 (G1/G2 generators, pairing, batch_mul, multiexp, from_hex), same method names and edge-case
-behaviour; the arithmetic behind multiexp / batch_mul runs in libzkb200.so."""
+"""`EllipticCurve`: curve-name front door to the `_algebra` ec modules, with the method names the reference's
+python/zksnake/ecc.py:47-142 offers (G1, G2, pairing, multi_pairing, batch_mul, multiexp, from_hex) so that prover code reads
+the same.  Point vectors may be Python lists (the reference's representation) or device-resident `PointVector`s -- the form the
+B200 provers keep keys and SRS in; multiexp / batch_mul then never build a Python list of points.
+"""
 from ._algebra import ec_bls12_381, ec_bn254
 from ._algebra._ec import PointVector
 
-CURVE_MODULES = {"BN128": ec_bn254, "BN254": ec_bn254, "ALT_BN128": ec_bn254, "BLS12_381": ec_bls12_381}
-POINT_SIZE = {"BN128": 32, "BN254": 32, "ALT_BN128": 32, "BLS12_381": 48}   # CurvePointSize, ecc.py:40-44
+# name -> (module, compressed G1 size in bytes)
+_REGISTRY = {"BN128": (ec_bn254, 32), "BN254": (ec_bn254, 32), "ALT_BN128": (ec_bn254, 32), "BLS12_381": (ec_bls12_381, 48)}
+CURVE_MODULES = {k: v[0] for k, v in _REGISTRY.items()}
+POINT_SIZE = {k: v[1] for k, v in _REGISTRY.items()}     # CurvePointSize, ecc.py:40-44
+
+
+def point_group(x):
+    """1 for a G1 point, 2 for a G2 point (either curve), 0 for anything else."""
+    for mod in (ec_bn254, ec_bls12_381):
+        if isinstance(x, mod.PointG1):
+            return 1
+        if isinstance(x, mod.PointG2):
+            return 2
+    return 0
 
 
 def ispointG1(x):
-    return isinstance(x, (ec_bn254.PointG1, ec_bls12_381.PointG1))
+    return point_group(x) == 1
 
 
 def ispointG2(x):
-    return isinstance(x, (ec_bn254.PointG2, ec_bls12_381.PointG2))
+    return point_group(x) == 2
 
 
 class EllipticCurve:
     def __init__(self, curve="BN254"):
-        if curve not in CURVE_MODULES:
+        if curve not in _REGISTRY:
             raise ValueError(f"Unsupported curve: {curve}")
         self.name = curve
-        self.curve = CURVE_MODULES[curve]
-        self.order = self.curve.ORDER
-        self.field_modulus = self.curve.FIELD_MODULUS
+        self.curve, self._g1_bytes = _REGISTRY[curve]
+        self.order, self.field_modulus = self.curve.ORDER, self.curve.FIELD_MODULUS
+        self._classes = {1: self.curve.PointG1, 2: self.curve.PointG2}
+        self._msm = {1: self.curve.multiscalar_mul_g1, 2: self.curve.multiscalar_mul_g2}
+        self._batch = {1: self.curve.batch_multi_scalar_g1, 2: self.curve.batch_multi_scalar_g2}
+
+    def _group(self, x, what):
+        for grp, cls in self._classes.items():
+            if isinstance(x, cls):
+                return grp
+        raise TypeError(f"Invalid curve type: {what}")
 
     def G1(self):
         return self.curve.g1()
@@ -39,48 +61,39 @@ class EllipticCurve:
         return self.curve.multi_pairing(a, b)
 
     def batch_mul(self, g, s):
-        """ecc.py:88-105: s[i] * g[i], or s[i] * g for a single point."""
-        if not isinstance(g, list):
-            g = [g] * len(s)
-        if len(g) == 0:
+        """[s_i * g_i] (g a list) or [s_i * g] (g one point) as a list of points -- ecc.py:88-105."""
+        bases = g if isinstance(g, list) else [g] * len(s)
+        if not bases:
             return []
-        if isinstance(g[0], self.curve.PointG1):
-            return self.curve.batch_multi_scalar_g1(g, s)
-        if isinstance(g[0], self.curve.PointG2):
-            return self.curve.batch_multi_scalar_g2(g, s)
-        raise TypeError(f"Invalid curve type: {g[0]}")
+        return self._batch[self._group(bases[0], bases[0])](bases, s)
 
     def batch_mul_device(self, g, s, group=1):
-        """The same, left on the GPU as a PointVector (what setup() uses so that a 2^20-point SRS never becomes a Python list)."""
+        """The same products left in HBM as a PointVector: how setup() builds a 2^20-point SRS without 2^20 Python objects."""
         return self.curve.batch_mul_device(g, s, group)
 
     def multiexp(self, g, s):
-        """ecc.py:107-126.  g: list of points or a device-resident PointVector; s: list of ints.  An empty scalar list gives
-        the identity; more points than scalars are trimmed."""
+        """sum_i s_i * g_i -- ecc.py:107-126: no scalars -> the identity; surplus points are ignored."""
         assert len(g) > 0
-        if isinstance(g, PointVector):
-            cls = self.curve.PointG1 if g.group == 1 else self.curve.PointG2
-            if len(s) == 0:
-                return cls.identity()
+        on_device = isinstance(g, PointVector)
+        grp = g.group if on_device else self._group(g[0], type(g[0]))
+        if len(s) == 0:
+            return self._classes[grp].identity()
+        if on_device:
             if len(s) > len(g):
                 raise ValueError("Number of points and scalars mismatch")
-            fn = self.curve.multiscalar_mul_g1 if g.group == 1 else self.curve.multiscalar_mul_g2
-            return fn(g.prefix(len(s)), s)
-        if len(s) == 0:
-            return g[0] * 0
-        if len(s) < len(g):
-            g = g[:len(s)]
-        if isinstance(g[0], self.curve.PointG1):
-            return self.curve.multiscalar_mul_g1(g, s)
-        if isinstance(g[0], self.curve.PointG2):
-            return self.curve.multiscalar_mul_g2(g, s)
-        raise TypeError(f"Invalid curve type: {type(g[0])}")
+            return self._msm[grp](g.prefix(len(s)), s)
+        return self._msm[grp](g[:len(s)] if len(s) < len(g) else g, s)
 
     def from_hex(self, hexstring):
-        b = bytes.fromhex(hexstring)
-        n = POINT_SIZE[self.name] * 2
-        if len(hexstring) == n:
-            return self.curve.PointG1.from_bytes(b)
-        if len(hexstring) == n * 2:
-            return self.curve.PointG2.from_bytes(b)
-        raise ValueError(f"Hexstring size of {n} or {n * 2} expected, got {len(hexstring)}")
+        """compressed point from hex; the length tells G1 from G2 (ecc.py:128-142)"""
+        raw = bytes.fromhex(hexstring)
+        if len(raw) == self._g1_bytes:
+            return self.curve.PointG1.from_bytes(raw)
+        if len(raw) == 2 * self._g1_bytes:
+            return self.curve.PointG2.from_bytes(raw)
+        raise ValueError(f"Hexstring size of {2 * self._g1_bytes} or {4 * self._g1_bytes} expected, got {len(hexstring)}")
+
+    def __call__(self, x, y):
+        if isinstance(x, (tuple, list)) and isinstance(y, (tuple, list)):
+            return self.curve.PointG2(x[0], x[1], y[0], y[1])
+        return self.curve.PointG1(x, y)

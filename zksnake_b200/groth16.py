@@ -130,13 +130,16 @@ class VerifyingKey:
 
 
 class Groth16:
-    def __init__(self, r1cs: R1CS, curve: str = "BN254", shard=None, shard_mode="windows", tables=None):
+    def __init__(self, r1cs: R1CS, curve: str = "BN254", shard=None, shard_mode="windows", tables=None, emulate_shard=False):
         """shard = (rank, world): this process proves cooperatively with the other ranks (zksnake_b200/dist.py).  Default: the
         torch.distributed world, else (0, 1).  shard_mode "windows" (default): every rank holds the whole key and runs the
         scalar windows [W*rank/world, W*(rank+1)/world) of every MSM -- sort, accumulation and bucket reduction all shrink by
         1/world.  "points": every rank keeps only its contiguous 1/world slice of the four key vectors (1/world of the memory;
-        only the accumulation shrinks)."""
+        only the accumulation shrinks).  An explicit shard must match the torch.distributed world (dist.require_world);
+        emulate_shard=True is for tests that drive zkb_groth16_partial / zkb_groth16_assemble rank by rank in ONE process."""
         self.rank, self.world = shard if shard is not None else dist.world()
+        self._emulate = bool(emulate_shard)
+        dist.require_world(self.rank, self.world, self._emulate)
         assert shard_mode in ("windows", "points")
         self.shard_mode = shard_mode
         # fixed-base tables for the four key vectors (zkb_msm_table_create): ~14x the key's memory, ~20 % faster MSMs.
@@ -161,7 +164,8 @@ class Groth16:
         self._pk_handle = None
         self._r1cs_handle = None
         self._bound_key = None
-        self.toxic = None  # (tau, alpha, beta, gamma, delta) kept for closed-form parity checks in tests
+        self._staging = None
+        self._staging_ptr = None
 
     # ------------------------------------------------------------------------------------------------ setup
     def setup(self):
@@ -170,9 +174,9 @@ class Groth16:
         o = self.order
         ec = self.ec
         G1, G2 = ec.g1(), ec.g2()
-        rand = dist.shared_random(get_random_int) if self.world > 1 else get_random_int   # all ranks need the SAME toxic waste
-        tau, alpha, beta, gamma, delta = (rand(o - 1) for _ in range(5))
-        self.toxic = (tau, alpha, beta, gamma, delta)
+        # toxic waste: locals only, as in the reference (protocol.py:38-43) -- never stored on the object.  All ranks need the
+        # SAME values: rank 0 draws, everybody receives (dist.shared_draws)
+        tau, alpha, beta, gamma, delta = self._draws(o - 1, 5)
         inv_gamma, inv_delta = pow(gamma, -1, o), pow(delta, -1, o)
         n, m = self.n, self.m
         # L_i(tau) on the device: one inverse transform of the powers of tau (polynomial.rs:646-652)
@@ -231,6 +235,11 @@ class Groth16:
         self.verifying_key = VerifyingKey(G1 * alpha, G2 * beta, G2 * gamma, G2 * delta, k_gamma_G1)
         self._bind()
 
+    def _draws(self, n_max, count):
+        if self.world == 1 or self._emulate:
+            return [get_random_int(n_max) for _ in range(count)]
+        return dist.shared_draws(get_random_int, n_max, count, self.world)
+
     def _ensure_bound(self):
         """A key assigned from outside (`prover.proving_key = ProvingKey.from_bytes(...)`, the reference's way of reusing a
         stored key) is bound to the device prover on first use."""
@@ -242,13 +251,14 @@ class Groth16:
         assert len(pk.tau_1) == self.n and len(pk.tau_2) == self.n and len(pk.target_1) == self.n, \
             "ProvingKey does not match the constraint system"
         assert len(pk.kdelta_1) == self.m - self.n_public, "Length of kdelta_1 and private_witness must be equal"
-        self._release()
         self._slice = (0, self.n)
         self._kslice = (0, self.m - self.n_public)
         self._bind()
 
     def _bind(self):
-        """Create the device-side prover objects (proving-key handle + CSR R1CS)."""
+        """Create the device-side prover objects (proving-key handle + CSR R1CS); whatever was bound before (an earlier setup(),
+        another key) is released first -- the handle owns the work buffer, the fixed-base tables and the device CSR."""
+        self._release()
         pk = self.proving_key
         flat = lambda pt: np.frombuffer(pt._flat(), dtype=np.uint64).copy()  # noqa: E731
         singles = [flat(pk.alpha_1), flat(pk.beta_1), flat(pk.beta_2), flat(pk.delta_1), flat(pk.delta_2)]
@@ -282,14 +292,30 @@ class Groth16:
         assert self.proving_key, "ProvingKey has not been generated"
         assert self.m - self.n_public == len(private_witness), \
             "Length of kdelta_1 and private_witness must be equal"
-        rand = dist.shared_random(get_random_int) if self.world > 1 else get_random_int
-        r = rand(self.order - 1)
-        s = rand(self.order - 1)
-        w = nat.ints_to_limbs([int(x) % self.order for x in list(public_witness) + list(private_witness)])
+        r, s = self._draws(self.order - 1, 2)
+        # list[int] -> limbs straight into a pinned staging buffer (csrc/pymarshal.cpp: host threads over the PyLong digits; the
+        # reference pays one BigUint conversion per element under the GIL, src/bn254/polynomial.rs:537-540).  Values in
+        # [0, 2^256) go up as they are and are reduced mod r on the device; negatives (legal here: SparseArray.dot reduces at
+        # the end, array.py:43) and wider ints are reduced on the host.
+        w = self._witness_staging()
+        n_pub = len(public_witness)
+        if n_pub + len(private_witness) != self.m:
+            raise ValueError(f"witness has {n_pub + len(private_witness)} entries, the constraint system has {self.m} columns")
+        nat.ints_to_limbs(public_witness, 32, modulus=self.order, out=w[:n_pub])
+        nat.ints_to_limbs(private_witness, 32, modulus=self.order, out=w[n_pub:])
         try:
             return self.prove_packed(w, r, s)
         except ValueError as exc:
             raise ValueError("Failed to evaluate with the given witness") from exc
+
+    def _witness_staging(self):
+        """(m, 4) uint64 view of a pinned host buffer owned by this prover (full-rate H2D, no per-proof allocation)."""
+        if self._staging is None:
+            p = ctypes.c_void_p()
+            nat.check(nat.lib.zkb_host_alloc(max(self.m, 1) * 32, ctypes.byref(p)))
+            self._staging_ptr = p
+            self._staging = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint64)), shape=(self.m, 4))
+        return self._staging
 
     def prove_packed(self, witness_limbs, r, s):
         """witness as a (m, 4) uint64 array (host; pinned for full H2D speed) or a DeviceBuffer holding the same bytes -- the
@@ -369,5 +395,9 @@ class Groth16:
     def __del__(self):
         try:
             self._release()
+            if self._staging_ptr is not None:
+                self._staging = None
+                nat.lib.zkb_host_free(self._staging_ptr)
+                self._staging_ptr = None
         except Exception:
             pass

@@ -37,12 +37,14 @@ from .transcript import FiatShamirTranscript
 
 
 class DevicePlonk(Plonk):
-    def __init__(self, constraints, curve="BN254", shard=None):
+    def __init__(self, constraints, curve="BN254", shard=None, emulate_shard=False):
         """shard = (rank, world): one process per GPU (torch.distributed); every rank runs the whole protocol but only its window
         shard of each commitment MSM, and the partial points are all-gathered and added (zksnake_b200/dist.py) -- every rank ends
         up with the same commitments, the same transcript and the same proof.  Default: the torch.distributed world, else (0, 1)."""
         super().__init__(constraints, curve)
         self.rank, self.world = shard if shard is not None else dist.world()
+        self._emulate = bool(emulate_shard)     # tests: one process plays the ranks through the batch-MSM entry point
+        dist.require_world(self.rank, self.world, self._emulate)
         self.cid = self.E.curve.CURVE_ID
         self.table = None      # fixed-base table of the SRS
         self.timings = {}
@@ -83,6 +85,11 @@ class DevicePlonk(Plonk):
             res.append(P._from_flat(acc, ainf.value))
         return res
 
+    def _draws(self, n_max, count):
+        if self.world == 1 or self._emulate:
+            return [_plonk.get_random_int(n_max) for _ in range(count)]
+        return dist.shared_draws(_plonk.get_random_int, n_max, count, self.world)
+
     def __del__(self):
         try:
             if self.table:
@@ -98,8 +105,7 @@ class DevicePlonk(Plonk):
         p, cs, cid = self.order, self.constraints, self.cid
         n = cs.length
         assert n >= 4, "PlonK needs at least 4 gates (the blinding polynomials have up to 3 coefficients)"
-        tau = (dist.shared_random(_plonk.get_random_int) if self.world > 1 else _plonk.get_random_int)(p - 1)
-        self.tau = tau
+        tau = self._draws(p - 1, 1)[0]          # toxic waste: a local, never stored; identical on every rank
         self.srs_len = n + 6
         # [tau^i]G1: powers on the device, then the fixed-base scalar-multiplication kernel; table for the prover's MSMs
         powers = FrVec.powers(cid, self.srs_len, tau)
@@ -231,7 +237,10 @@ class DevicePlonk(Plonk):
         pk, p, cid = self.proving_key, self.order, self.cid
         n, N4 = pk.n, self.NQ
         omega = self.omega
-        rnd = dist.shared_random(_plonk.get_random_int) if self.world > 1 else _plonk.get_random_int
+        # the 11 blinding scalars of protocol.py:223-234, 280, 362 do not depend on the transcript: drawn up front, in the
+        # reference's call order, with ONE collective when several ranks cooperate
+        blinders = iter(self._draws(p - 1, 11))
+        rnd = lambda n_max: next(blinders)  # noqa: E731
         sel, sig = pk.selector_poly, pk.permutation_poly
         selc, sigc = self.selector_coset, self.sigma_coset
         T = {}

@@ -20,7 +20,7 @@ def Polynomial(coeffs, p, domain_size=None):
         raise TypeError("Coefficients must be in list or dict")   # multivariate dicts are outside the proving path
     if not domain_size:
         domain_size = len(coeffs)
-    return POLY_OBJECT[p].Polynomial(1, [(c, [(0, 0)]) for c in coeffs], domain_size)
+    return POLY_OBJECT[p].Polynomial(1, coeffs, domain_size)   # (the mirror also takes bare ints: no per-coefficient tuple)
 
 
 def get_evaluation_point(domain, i, p):

@@ -51,10 +51,12 @@ class SparseArray:
         cols = np.fromiter((t[1] for t in trip), dtype=np.int64, count=nnz)
         vals = np.zeros((nnz, 4), dtype=np.uint64)
         p = self.p
-        try:
-            vals[:, 0] = np.fromiter((t[2] for t in trip), dtype=np.uint64, count=nnz)     # all values in [0, 2^64)
-        except (OverflowError, ValueError):
-            vals = nat.ints_to_limbs([t[2] % p for t in trip], 32) if nnz else vals
+        # one-limb fast path only when EVERY value is in [0, 2^64) -- decided explicitly, not by numpy's overflow behaviour
+        # (numpy 1.x wraps a -1 to 2^64 - 1 instead of raising)
+        if all(0 <= t[2] < (1 << 64) for t in trip):
+            vals[:, 0] = np.fromiter((t[2] for t in trip), dtype=np.uint64, count=nnz)
+        elif nnz:
+            vals = nat.ints_to_limbs([t[2] % p for t in trip], 32)
         self._arrays_cache = (nnz, (rows, cols, vals))     # (append() only ever grows the list, so the length is the version)
         return rows, cols, vals
 

@@ -1,48 +1,50 @@
-"""Fiat-Shamir transcript with the reference's exact byte conventions (python/zksnake/transcript.py:29-71): blake2b, ints
-appended big-endian with `bit_length()` BYTES (sic -- the reference passes the bit length as the byte length, so an int is
-left-padded with zeros to that many bytes; reproduced because every challenge depends on it), points appended in their
-compressed encoding, and the hasher re-seeded with the digest after every challenge."""
+"""Fiat-Shamir transcript of the PlonK / KZG provers.
+
+Byte conventions are the reference's (python/zksnake/transcript.py:29-71), because every challenge -- hence every proof byte --
+depends on them: blake2b; an int is absorbed big-endian, left-padded to `bit_length()` BYTES (the reference passes the bit length
+where a byte length is meant; reproduced, not fixed); a curve point is absorbed in its compressed encoding; str as UTF-8; a list
+element by element; after a challenge is squeezed the hash restarts from that digest.  The implementation is a small encoder
+(`absorbed_bytes`) in front of hashlib, shared by `append`.
+"""
 import hashlib
 
-from .ecc import ispointG1, ispointG2
+from ._algebra import ec_bls12_381, ec_bn254
+from ._algebra._poly import _R
+
+_POINT_TYPES = (ec_bn254.PointG1, ec_bn254.PointG2, ec_bls12_381.PointG1, ec_bls12_381.PointG2)
+
+
+def absorbed_bytes(item):
+    """The byte string one transcript item contributes."""
+    if isinstance(item, (bytes, bytearray)):
+        return bytes(item)
+    if isinstance(item, str):
+        return item.encode()
+    if isinstance(item, int):
+        return item.to_bytes(item.bit_length(), "big")      # sic: bit length used as the byte count
+    if isinstance(item, _POINT_TYPES):
+        return bytes(item.to_bytes())
+    if isinstance(item, list) and item and isinstance(item[0], (int,) + _POINT_TYPES):
+        return b"".join(absorbed_bytes(x) for x in item)
+    raise TypeError(f"Type of {type(item)} is not supported as transcript")
 
 
 class FiatShamirTranscript:
     def __init__(self, label=b"", field=None, alg="blake2b"):
-        from .polynomial import BN254_SCALAR_FIELD
-        self.alg, self.label = alg, label
-        self.hasher = hashlib.new(alg, label)
-        self.field = field or BN254_SCALAR_FIELD
+        self._alg, self._label = alg, label
+        self.field = field or _R[0]
+        self._state = hashlib.new(alg, label)
 
     def reset(self):
-        self.hasher = hashlib.new(self.alg, self.label)
-
-    @staticmethod
-    def _int_bytes(v):
-        return int.to_bytes(v, v.bit_length(), "big")
+        self._state = hashlib.new(self._alg, self._label)
 
     def append(self, data):
-        if isinstance(data, bytes):
-            self.hasher.update(data)
-        elif isinstance(data, str):
-            self.hasher.update(data.encode())
-        elif isinstance(data, int):
-            self.hasher.update(self._int_bytes(data))
-        elif data and isinstance(data, list) and isinstance(data[0], int):
-            for d in data:
-                self.hasher.update(self._int_bytes(d))
-        elif ispointG1(data) or ispointG2(data):
-            self.hasher.update(bytes(data.to_bytes()))
-        elif data and isinstance(data, list) and (ispointG1(data[0]) or ispointG2(data[0])):
-            for d in data:
-                self.hasher.update(bytes(d.to_bytes()))
-        else:
-            raise TypeError(f"Type of {type(data)} is not supported as transcript")
+        self._state.update(absorbed_bytes(data))
 
     def get_challenge(self):
-        digest = self.hasher.digest()
-        self.hasher = hashlib.new(self.alg, digest)
-        return digest
+        out = self._state.digest()
+        self._state = hashlib.new(self._alg, out)            # ratchet: the next challenge depends on this one
+        return out
 
     def get_challenge_scalar(self):
         return int.from_bytes(self.get_challenge(), "big") % self.field

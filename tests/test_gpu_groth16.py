@@ -82,7 +82,7 @@ def test_prove_matches_oracle_small(gpu, curve_name):
 
 
 @pytest.mark.parametrize("curve_name,n", [("BN254", 1 << 12), ("BLS12_381", 1 << 10), ("BN254", 1 << 16), ("BLS12_381", 1 << 16),
-                                          ("BN254", 1 << 20)])   # the last one is BASELINE.json's full size
+                                          ("BN254", 1 << 20), ("BLS12_381", 1 << 20)])   # the last two: BASELINE.json's full size
 def test_prove_matches_closed_form_large(gpu, curve_name, n):
     from zksnake_b200 import groth16 as gm
     from zksnake_b200 import r1cs as rm
@@ -95,6 +95,42 @@ def test_prove_matches_closed_form_large(gpu, curve_name, n):
     assert proof.to_bytes() == og.proof_bytes(cid, A, B, C)
     if n <= 1 << 12:
         assert g.verify(proof, pub)
+
+
+@pytest.mark.parametrize("curve_name,n", [("BN254", 1 << 12), ("BN254", 1 << 20)])
+def test_prove_dense_random_matches_closed_form(gpu, curve_name, n):
+    """SURVEY.md section 8d config 3, dense-random variant: A.w, B.w uniform in Fr, C.w their product, so U, V, H are full-size
+    random scalars (the realistic MSM digit distribution) and the private witness has 3n columns.  Full size: n = 2^20."""
+    from zksnake_b200 import groth16 as gm
+    from zksnake_b200 import r1cs as rm
+    cid = curve_id(curve_name)
+    r = PARAMS[cid].r
+    g, st, pub, priv = make(gm, rm, rm.dense_random_circuit(n, curve_name), curve_name, seed=7)
+    rr, ss = random.Random(12).randint(1, r - 1), random.Random(13).randint(1, r - 1)
+    proof = prove_seeded(gm, g, pub, priv, rr, ss)
+    A, B, C = og.prove_closed_form(st, pub + priv, rr, ss)
+    assert proof.to_bytes() == og.proof_bytes(cid, A, B, C)
+    if n <= 1 << 12:
+        assert g.verify(proof, pub)
+        # every raw MSM against its discrete log
+        G1, G2 = group(cid, False), group(cid, True)
+        for i, (e, pt) in enumerate(zip(og.msm_exponents(st, pub + priv), g.last_msms())):
+            G = G2 if i == 2 else G1
+            assert as_oracle_point(pt) == G.mul(G.gen, e), i
+
+
+def test_prove_accepts_unreduced_and_negative_witness_values(gpu):
+    """Groth16.prove(list, list) marshals through csrc/pymarshal.cpp: values >= r go up raw and are reduced on the device, negative
+    and > 256-bit values on the host -- the reference reduces them all in SparseArray.dot (array.py:43)."""
+    from zksnake_b200 import groth16 as gm
+    from zksnake_b200 import r1cs as rm
+    r = PARAMS[0].r
+    g, st, pub, priv = make(gm, rm, rm.chain_circuit(37, "BN254"), "BN254")
+    want = prove_seeded(gm, g, pub, priv, 5, 7).to_bytes()
+    shifted = [v + r if i % 3 == 0 else (v - r if i % 3 == 1 else v + (r << 200)) for i, v in enumerate(priv)]
+    assert prove_seeded(gm, g, [pub[0] + r, pub[1] - 2 * r], shifted, 5, 7).to_bytes() == want
+    with pytest.raises(TypeError):
+        g.prove(pub, [1.5] * len(priv))
 
 
 def test_bad_witness_raises(gpu):

@@ -170,6 +170,70 @@ def test_device_prover_2p16_verifies(gpu):
     assert not plonk.verify(proof, {k: (pub[k] + 1) % plonk.order})
 
 
+def test_device_prover_2p20_commitments_match_closed_form(gpu):
+    """BASELINE.json configs[3] at full size: 2^20 gates on BN254.  With tau known, every one of the nine commitments must be
+    [P(tau)]G1 for the polynomial P the prover committed to -- P is downloaded from the device and Horner-evaluated in Python
+    ints, the point comes from the oracle's scalar multiplication: this pins the nine 2^20-point MSMs over the SRS table.  The
+    proof must verify, the six opening values must be the evaluations of those polynomials, and the window-sharded MSMs (two
+    ranks, emulated) must add up to the same commitments."""
+    import ctypes
+
+    import numpy as np
+
+    from zksnake_b200 import _native as nat
+    from zksnake_b200 import plonk as pm
+    from zksnake_b200.plonk_device import DevicePlonk
+    from zksnake_b200.plonkish import chain_gates
+    n = 1 << 20
+    cs, pub, priv = chain_gates(n, "BN254")
+    r = PARAMS[0].r
+    G1 = group(0, False)
+    rnd = random.Random(2020)
+    tau = rnd.randint(1, r - 1)
+    blind = [rnd.randint(1, r - 1) for _ in range(11)]
+    plonk = DevicePlonk(cs, "BN254")
+    plonk.keep_polys = True
+    old = seeded(pm, [tau] + blind)
+    try:
+        plonk.setup()
+        proof = plonk.prove(pub, priv)
+    finally:
+        pm.get_random_int = old
+    assert plonk.verify(proof, pub)
+
+    def horner(coeffs, x):
+        acc = 0
+        for c in reversed(coeffs):
+            acc = (acc * x + c) % r
+        return acc
+
+    names = {"a": "tau_a", "b": "tau_b", "c": "tau_c", "z": "tau_z", "t_lo": "tau_t_lo", "t_mid": "tau_t_mid", "t_hi": "tau_t_hi",
+             "w_zeta": "tau_W_zeta", "w_zeta_omega": "tau_W_zeta_omega"}
+    coeffs = {}
+    for key, attr in names.items():
+        coeffs[key] = plonk.last_polys[key].to_ints()
+        pt = getattr(proof, attr)
+        assert (pt.x, pt.y) == G1.mul(G1.gen, horner(coeffs[key], tau)), key
+    # the opening values are evaluations of the committed polynomials at the transcript's zeta
+    beta, gamma, alpha, zeta, v, u = plonk._challenges(proof, pub)
+    assert proof.zeta_a == horner(coeffs["a"], zeta) and proof.zeta_b == horner(coeffs["b"], zeta)
+    assert proof.zeta_c == horner(coeffs["c"], zeta)
+    assert proof.zeta_omega == horner(coeffs["z"], zeta * plonk.omega % r)
+    # two-rank window shards of the first-round batch add up to the same three commitments
+    vecs = [plonk.last_polys[k] for k in ("a", "b", "c")]
+    limbs = nat.lib.zkb_affine_bytes(0, 1) // 8
+    acc = [plonk.E.curve.PointG1.identity() for _ in vecs]
+    for rank in range(2):
+        ptrs = (ctypes.c_void_p * 3)(*[x.ptr for x in vecs])
+        lens = (ctypes.c_size_t * 3)(*[x.n for x in vecs])
+        xy = np.zeros((3, limbs), dtype=np.uint64)
+        inf = (ctypes.c_int * 3)()
+        nat.check(nat.lib.zkb_msm_table_batch_dev(plonk.table, 3, ptrs, lens, rank, 2, nat.ptr(xy), inf))
+        for i in range(3):
+            acc[i] = acc[i] + plonk.E.curve.PointG1._from_flat(xy[i], inf[i])
+    assert acc == [proof.tau_a, proof.tau_b, proof.tau_c]
+
+
 def test_commitment_window_shards_add_up(gpu):
     """DevicePlonk with shard=(r, W): each "rank" returns its window shard of every commitment; emulated here by calling the
     batch MSM for every shard and adding the partial points -- must equal the single-rank commitments."""

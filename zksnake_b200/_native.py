@@ -5,6 +5,7 @@ entry point raises unless a B200 is present and `ensure_init()` succeeded.  The 
 (zksnake_b200/libzkb200.so, built by `__graft_entry__.build()` / `make -C zksnake_b200/csrc`).
 """
 import ctypes
+import operator
 import os
 
 import numpy as np
@@ -180,7 +181,8 @@ def ints_to_limbs(values, nbytes=32, modulus=None, out=None, item=-1, allow_nega
     except TypeError:
         if item >= 0:
             raise
-        _marshal.ints_to_limbs([int(v) for v in values], arr.ctypes.data, k, modulus, -1, allow_negative)   # numpy integers and other __index__ types
+        # numpy integers and other __index__ types (floats and strings still raise TypeError)
+        _marshal.ints_to_limbs([operator.index(v) for v in values], arr.ctypes.data, k, modulus, -1, allow_negative)
     return arr
 
 

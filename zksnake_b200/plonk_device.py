@@ -48,6 +48,8 @@ class DevicePlonk(Plonk):
         self.cid = self.E.curve.CURVE_ID
         self.table = None      # fixed-base table of the SRS
         self.timings = {}
+        self.keep_polys = False   # tests: keep the nine committed coefficient vectors of the last proof in `last_polys`
+        self.last_polys = {}
 
     # ------------------------------------------------------------------------------------------------------------ helpers
     def _commit(self, vec, count=None):
@@ -388,4 +390,7 @@ class DevicePlonk(Plonk):
         tau_w, tau_ww = self._commit_many([W_zeta, W_zeta_omega])
         lap("round5")
         self.timings = T
+        if self.keep_polys:
+            self.last_polys = {"a": A, "b": B, "c": C, "z": Z, "t_lo": T_lo, "t_mid": T_mid, "t_hi": T_hi, "w_zeta": W_zeta,
+                               "w_zeta_omega": W_zeta_omega}
         return Proof(tau_a, tau_b, tau_c, tau_z, tau_t[0], tau_t[1], tau_t[2], tau_w, tau_ww, za, zb, zc, zs1, zs2, zzw)

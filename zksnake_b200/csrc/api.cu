@@ -739,6 +739,9 @@ struct zkb_r1cs {
   uint32_t* col[3];
   void* val[3];
   void* w;  // witness staging (n_cols)
+  uint32_t* long_rows[3];   // rows with more than SPMV_LONG_ROW non-zeros (summed by whole CTAs, ntt.cuh:spmv_long_kernel)
+  uint32_t n_long[3];
+  void* long_partial;       // max(n_long) * 64 slice sums
 };
 
 void zkb_r1cs_free(zkb_r1cs* r) {
@@ -749,8 +752,10 @@ void zkb_r1cs_free(zkb_r1cs* r) {
       cudaFree(r->row_ptr[i]);
       cudaFree(r->col[i]);
       cudaFree(r->val[i]);
+      cudaFree(r->long_rows[i]);
     }
     cudaFree(r->w);
+    cudaFree(r->long_partial);
   }
   delete r;
 }
@@ -782,6 +787,27 @@ int zkb_r1cs_create(int curve, size_t n_rows, size_t n_cols, const uint64_t* con
       break;
     }
     rc = fr_reduce_dev(curve, nnz, r->val[i]);
+    if (rc) break;
+    std::vector<uint32_t> longs;
+    for (size_t row = 0; row < n_rows; row++)
+      if (row_ptr[i][row + 1] - row_ptr[i][row] > SPMV_LONG_ROW) longs.push_back((uint32_t)row);
+    r->n_long[i] = (uint32_t)longs.size();
+    if (!longs.empty()) {
+      if ((e = cudaMalloc((void**)&r->long_rows[i], longs.size() * 4)) != cudaSuccess ||
+          (e = ZKB_H2D(r->long_rows[i], longs.data(), longs.size() * 4)) != cudaSuccess ||
+          (e = cudaStreamSynchronize(S())) != cudaSuccess) {     // (`longs` dies at the end of this iteration)
+        rc = cuda_fail((int)e, "r1cs long-row list", __FILE__, __LINE__);
+        break;
+      }
+    }
+  }
+  if (rc == ZKB_OK) {
+    uint32_t most = 0;
+    for (int i = 0; i < 3; i++) most = r->n_long[i] > most ? r->n_long[i] : most;
+    if (most) {
+      cudaError_t e = cudaMalloc(&r->long_partial, (size_t)most * 64 * 32);
+      if (e != cudaSuccess) rc = cuda_fail((int)e, "r1cs long-row partial sums", __FILE__, __LINE__);
+    }
   }
   if (rc == ZKB_OK) {
     cudaError_t e = cudaMalloc(&r->w, (n_cols ? n_cols : 1) * 32);
@@ -810,7 +836,9 @@ static int r1cs_spmv3(zkb_r1cs* r, size_t n_out, void* d_a, void* d_b, void* d_c
   void* outs[3] = {d_a, d_b, d_c};
   int rc;
   for (int i = 0; i < 3; i++)
-    if ((rc = spmv_dev(r->curve, n_out, r->n_rows, r->row_ptr[i], r->col[i], r->val[i], r->w, outs[i]))) return rc;
+    if ((rc = spmv_dev(r->curve, n_out, r->n_rows, r->row_ptr[i], r->col[i], r->val[i], r->w, outs[i], r->long_rows[i], r->n_long[i],
+                       r->long_partial)))
+      return rc;
   return ZKB_OK;
 }
 static int r1cs_eval_dev(zkb_r1cs* r, const uint64_t* witness, size_t n_out, void* d_a, void* d_b, void* d_c) {

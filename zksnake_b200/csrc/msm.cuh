@@ -127,6 +127,263 @@ static __global__ void msm_scatter_kernel(MsmPlan pl, const uint32_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Digit sort, two levels, every histogram in shared memory (round 2; replaces one global atomic per reference in each of
+// msm_count_kernel / msm_scatter_kernel: 2 x 14.7 M global atomics per 2^20-point MSM, 0.7 ms).
+//   level 1 partitions the (window, |digit|) keys by their high bits: key >> L selects one of NP partitions;
+//     msm_part_hist_kernel    -- CTA g walks ITS slice of the scalars, histogram of the partitions in shared memory, written to
+//                                cta_hist[partition * G + g] (partition-major, so ONE exclusive scan yields every CTA's write offset
+//                                for every partition and partition p is the contiguous range [scan[p G], scan[(p+1) G]) );
+//     msm_part_scatter_kernel -- the same walk; cursor[partition] (shared memory, seeded with the scanned offsets) hands out the
+//                                slots; element = (low key bits, reference);
+//   level 2: msm_bucket_sort_kernel -- one CTA per partition: histogram of the 2^L low key values in shared memory, exclusive scan
+//     -> cnt[] and start[] of its buckets (start = partition offset + local prefix), second walk scatters the references.
+// Equal keys in a warp (skewed scalars: a 0/1 witness puts every reference of window 0 into ONE bucket) are combined before the
+// shared-memory atomic when the whole warp agrees, which is the case that would otherwise serialise 32-fold.
+// The order of the references inside a bucket is arbitrary; the bucket sum does not depend on it (exact group law).
+// ------------------------------------------------------------------------------------------------------
+struct MsmSortGeom {
+  uint32_t L;        // low key bits resolved by level 2
+  uint32_t np;       // partitions = ceil(nb / 2^L)
+  uint32_t G;        // CTAs of level 1
+  uint32_t per_cta;  // scalars per level-1 CTA
+};
+
+// one warp-wide shared-memory increment; returns the slot each lane got (count-only callers ignore it)
+__device__ __forceinline__ uint32_t smem_take(uint32_t* counters, uint32_t key, bool have) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t k0 = __shfl_sync(0xffffffffu, key, 0);
+  const uint32_t ballot = __ballot_sync(0xffffffffu, have);
+  if (__all_sync(0xffffffffu, !have || key == k0) && __shfl_sync(0xffffffffu, (uint32_t)have, 0)) {
+    // every live lane wants the same counter (and lane 0 is live, so k0 is that counter): one atomic for the warp
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&counters[k0], (uint32_t)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    return base + (uint32_t)__popc(ballot & ((1u << lane) - 1u));
+  }
+  return have ? atomicAdd(&counters[key], 1u) : 0u;
+}
+
+// walks the windows of one scalar; calls f(key, ref) for every non-zero digit of the windows this launch handles
+template <class Fn>
+__device__ __forceinline__ void msm_walk_digits(const MsmPlan& pl, const uint32_t* s, uint32_t index, bool live, Fn f) {
+  uint32_t carry = 0;
+  const uint32_t half = 1u << (pl.c - 1);
+  const uint32_t wend = pl.win0 + pl.nwin;
+  for (uint32_t w = 0; w < wend; w++) {   // the carry has to be walked up from window 0 even when win0 > 0
+    uint32_t d = scalar_bits(s, w * pl.c, pl.c) + carry;
+    carry = d > half;
+    uint32_t mag = carry ? ((1u << pl.c) - d) : d;
+    if (w < pl.win0) continue;   // warp-uniform
+    const bool have = live && mag != 0;
+    const uint32_t key = (pl.table_n ? 0u : (w - pl.win0) * pl.nbuck) + mag - 1;
+    const uint32_t ref = (index + w * pl.table_n) | (carry << 31);
+    f(have, key, ref);
+  }
+}
+
+static __global__ void __launch_bounds__(256) msm_part_hist_kernel(MsmPlan pl, MsmSortGeom sg, const uint32_t* __restrict__ scalars,
+                                                                   uint32_t* __restrict__ cta_hist) {
+  extern __shared__ uint32_t part_smem[];
+  for (uint32_t j = threadIdx.x; j < sg.np; j += blockDim.x) part_smem[j] = 0;
+  __syncthreads();
+  const unsigned long long lo = (unsigned long long)blockIdx.x * sg.per_cta;
+  const unsigned long long hi = lo + sg.per_cta < pl.n ? lo + sg.per_cta : pl.n;
+  for (unsigned long long i0 = lo; i0 < hi; i0 += blockDim.x) {     // (warp-uniform trip count: shuffles inside)
+    const unsigned long long i = i0 + threadIdx.x;
+    const bool live = i < hi;
+    uint32_t s[8];
+    if (live) load_scalar(scalars + i * 8, s);
+    else { for (int j = 0; j < 8; j++) s[j] = 0; }
+    msm_walk_digits(pl, s, (uint32_t)i, live, [&](bool have, uint32_t key, uint32_t) { smem_take(part_smem, key >> sg.L, have); });
+  }
+  __syncthreads();
+  for (uint32_t j = threadIdx.x; j < sg.np; j += blockDim.x) cta_hist[(size_t)j * sg.G + blockIdx.x] = part_smem[j];
+}
+
+static __global__ void __launch_bounds__(256) msm_part_scatter_kernel(MsmPlan pl, MsmSortGeom sg, const uint32_t* __restrict__ scalars,
+                                                                      const uint32_t* __restrict__ cta_offset,
+                                                                      uint2* __restrict__ parts) {
+  extern __shared__ uint32_t part_smem[];
+  for (uint32_t j = threadIdx.x; j < sg.np; j += blockDim.x) part_smem[j] = cta_offset[(size_t)j * sg.G + blockIdx.x];
+  __syncthreads();
+  const unsigned long long lo = (unsigned long long)blockIdx.x * sg.per_cta;
+  const unsigned long long hi = lo + sg.per_cta < pl.n ? lo + sg.per_cta : pl.n;
+  const uint32_t lowmask = (1u << sg.L) - 1u;
+  for (unsigned long long i0 = lo; i0 < hi; i0 += blockDim.x) {
+    const unsigned long long i = i0 + threadIdx.x;
+    const bool live = i < hi;
+    uint32_t s[8];
+    if (live) load_scalar(scalars + i * 8, s);
+    else { for (int j = 0; j < 8; j++) s[j] = 0; }
+    msm_walk_digits(pl, s, (uint32_t)i, live, [&](bool have, uint32_t key, uint32_t ref) {
+      uint32_t pos = smem_take(part_smem, key >> sg.L, have);
+      if (have) parts[pos] = make_uint2(key & lowmask, ref);
+    });
+  }
+}
+
+// level 2.  grid.x = np; partition p = elements [off[p G], off[(p+1) G]) of `parts` (off = the scanned cta_hist, np G + 1 entries).
+// Writes cnt / start of the buckets [p 2^L, (p+1) 2^L) (clipped to nb) and the sorted references; the last CTA also writes start[nb].
+// A partition with more than ZKB_SORT_BIG elements is NOT sorted here: it is appended to big_list (its buckets' cnt zeroed) and
+// the three msm_big_* kernels spread it over the whole grid.  Such partitions are systematic, not exotic: the top window of a
+// 254-bit scalar holds 7 significant bits at c = 19, so ALL N of its digits fall into the first 128 buckets, and a 0/1 witness
+// does the same to window 0.  (One CTA walking 2^20 elements twice took 3.3 ms in the first version of this kernel.)
+#define ZKB_SORT_BIG 24576u
+static __global__ void __launch_bounds__(256) msm_bucket_sort_kernel(MsmSortGeom sg, unsigned long long nb, const uint32_t* __restrict__ off,
+                                                                     const uint2* __restrict__ parts, uint32_t* __restrict__ cnt,
+                                                                     uint32_t* __restrict__ start, uint32_t* __restrict__ refs,
+                                                                     uint32_t* __restrict__ big_count, uint32_t* __restrict__ big_list) {
+  __shared__ uint32_t hist[128];
+  __shared__ uint32_t cursor[128];
+  __shared__ uint32_t warp_tot[8];
+  const uint32_t p = blockIdx.x;
+  const uint32_t nkeys = 1u << sg.L;     // <= 128
+  const uint32_t begin = off[(size_t)p * sg.G], end = off[(size_t)(p + 1) * sg.G];
+  if (p + 1 == gridDim.x && threadIdx.x == 0) start[nb] = end;
+  const uint32_t span = end - begin;
+  if (span > ZKB_SORT_BIG) {
+    const unsigned long long b = (unsigned long long)p * nkeys + threadIdx.x;
+    if (threadIdx.x < nkeys && b < nb) cnt[b] = 0;
+    if (threadIdx.x == 0) big_list[atomicAdd(big_count, 1u)] = p;
+    return;
+  }
+  if (threadIdx.x < 128) hist[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t trips = (span + blockDim.x - 1) / blockDim.x;
+  for (uint32_t it = 0; it < trips; it++) {
+    const uint32_t e = begin + it * blockDim.x + threadIdx.x;
+    const bool have = e < end;
+    uint2 el = have ? parts[e] : make_uint2(0, 0);
+    smem_take(hist, el.x, have);
+  }
+  __syncthreads();
+  // exclusive scan of the (<= 128) counters by the first 128 threads: warp scans + 4 warp totals
+  uint32_t v = 0, incl = 0;
+  if (threadIdx.x < 128) {
+    v = threadIdx.x < nkeys ? hist[threadIdx.x] : 0;
+    incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= (uint32_t)o) incl += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    uint32_t before = 0;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) before += warp_tot[w];
+    const uint32_t excl = before + incl - v;
+    cursor[threadIdx.x] = begin + excl;
+    const unsigned long long b = (unsigned long long)p * nkeys + threadIdx.x;
+    if (threadIdx.x < nkeys && b < nb) {
+      cnt[b] = v;
+      start[b] = begin + excl;
+    }
+  }
+  __syncthreads();
+  for (uint32_t it = 0; it < trips; it++) {
+    const uint32_t e = begin + it * blockDim.x + threadIdx.x;
+    const bool have = e < end;
+    uint2 el = have ? parts[e] : make_uint2(0, 0);
+    uint32_t pos = smem_take(cursor, el.x, have);
+    if (have) refs[pos] = el.y;
+  }
+}
+
+// ---- oversized partitions: every CTA of the grid takes a strided share of each listed partition ---------------------------------
+// element e of partition q belongs to CTA (e - begin) / 256 mod gridDim.x (whole 256-element tiles, the same in count and scatter)
+// count: shared-memory histogram of the CTA's tiles, then ONE global atomic per non-empty bucket
+static __global__ void __launch_bounds__(256) msm_big_count_kernel(MsmSortGeom sg, const uint32_t* __restrict__ off,
+                                                                   const uint2* __restrict__ parts, const uint32_t* __restrict__ big_count,
+                                                                   const uint32_t* __restrict__ big_list, uint32_t* __restrict__ cnt) {
+  __shared__ uint32_t hist[128];
+  const uint32_t nbig = *big_count;
+  const uint32_t nkeys = 1u << sg.L;
+  for (uint32_t q = 0; q < nbig; q++) {
+    const uint32_t p = big_list[q];
+    const uint32_t begin = off[(size_t)p * sg.G], end = off[(size_t)(p + 1) * sg.G];
+    if (threadIdx.x < 128) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t t0 = begin + blockIdx.x * 256u; t0 < end; t0 += gridDim.x * 256u) {
+      const uint32_t e = t0 + threadIdx.x;
+      const bool have = e < end;
+      uint2 el = have ? parts[e] : make_uint2(0, 0);
+      smem_take(hist, el.x, have);
+    }
+    __syncthreads();
+    if (threadIdx.x < nkeys && hist[threadIdx.x]) atomicAdd(&cnt[(size_t)p * nkeys + threadIdx.x], hist[threadIdx.x]);
+    __syncthreads();
+  }
+}
+// scan: one CTA (128 threads) per listed partition: start[] of its buckets, and the global cursors the scatter draws from
+static __global__ void __launch_bounds__(128) msm_big_scan_kernel(MsmSortGeom sg, unsigned long long nb, const uint32_t* __restrict__ off,
+                                                                  const uint32_t* __restrict__ big_count,
+                                                                  const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ cnt,
+                                                                  uint32_t* __restrict__ start, uint32_t* __restrict__ gcursor) {
+  __shared__ uint32_t warp_tot[4];
+  const uint32_t nbig = *big_count;
+  const uint32_t nkeys = 1u << sg.L;
+  for (uint32_t q = blockIdx.x; q < nbig; q += gridDim.x) {
+    const uint32_t p = big_list[q];
+    const uint32_t begin = off[(size_t)p * sg.G];
+    const unsigned long long b = (unsigned long long)p * nkeys + threadIdx.x;
+    const bool live = threadIdx.x < nkeys && b < nb;
+    const uint32_t v = live ? cnt[b] : 0;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= (uint32_t)o) incl += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) before += warp_tot[w];
+    if (live) {
+      start[b] = begin + before + incl - v;
+      gcursor[b] = begin + before + incl - v;
+    }
+    __syncthreads();
+  }
+}
+// scatter: the CTA recounts its tiles, reserves a contiguous range per bucket with ONE global atomic each, fills it
+static __global__ void __launch_bounds__(256) msm_big_scatter_kernel(MsmSortGeom sg, const uint32_t* __restrict__ off,
+                                                                     const uint2* __restrict__ parts, const uint32_t* __restrict__ big_count,
+                                                                     const uint32_t* __restrict__ big_list, uint32_t* __restrict__ gcursor,
+                                                                     uint32_t* __restrict__ refs) {
+  __shared__ uint32_t hist[128];
+  const uint32_t nbig = *big_count;
+  const uint32_t nkeys = 1u << sg.L;
+  for (uint32_t q = 0; q < nbig; q++) {
+    const uint32_t p = big_list[q];
+    const uint32_t begin = off[(size_t)p * sg.G], end = off[(size_t)(p + 1) * sg.G];
+    if (threadIdx.x < 128) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t t0 = begin + blockIdx.x * 256u; t0 < end; t0 += gridDim.x * 256u) {
+      const uint32_t e = t0 + threadIdx.x;
+      const bool have = e < end;
+      uint2 el = have ? parts[e] : make_uint2(0, 0);
+      smem_take(hist, el.x, have);
+    }
+    __syncthreads();
+    if (threadIdx.x < nkeys) {
+      const uint32_t mine = hist[threadIdx.x];
+      hist[threadIdx.x] = mine ? atomicAdd(&gcursor[(size_t)p * nkeys + threadIdx.x], mine) : 0u;   // becomes this CTA's cursor
+    }
+    __syncthreads();
+    for (uint32_t t0 = begin + blockIdx.x * 256u; t0 < end; t0 += gridDim.x * 256u) {
+      const uint32_t e = t0 + threadIdx.x;
+      const bool have = e < end;
+      uint2 el = have ? parts[e] : make_uint2(0, 0);
+      uint32_t pos = smem_take(hist, el.x, have);
+      if (have) refs[pos] = el.y;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // exclusive scan of n u32 into out[0..n] (out[n] = total): per-CTA partial sums, one CTA scans the partials, per-CTA
 // rescan with its offset.  SCAN_TILE elements per CTA.
 // ------------------------------------------------------------------------------------------------------

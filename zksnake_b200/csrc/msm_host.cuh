@@ -121,9 +121,29 @@ static inline void scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_
 }
 
 // Sizes of one MSM launch, derived from the plan only (so the scratch of a whole batch can be reserved up front).
+// level split of the digit sort (msm.cuh: msm_part_*_kernel / msm_bucket_sort_kernel)
+inline MsmSortGeom msm_sort_geometry(size_t n, size_t nb) {
+  MsmSortGeom sg;
+  uint32_t lognb = 0;
+  while (((size_t)1 << lognb) < nb) lognb++;
+  // level 2 resolves L <= 7 bits per CTA; keep at least ~1024 partitions when the key space allows it (one CTA each)
+  int L = (int)lognb - 10;
+  if (L < 3) L = 3;
+  if (L > 7) L = 7;
+  sg.L = (uint32_t)L;
+  sg.np = (uint32_t)((nb + ((size_t)1 << L) - 1) >> L);
+  size_t ctas = (n + 511) / 512;              // >= 512 scalars per level-1 CTA
+  if (ctas > 148 * 8) ctas = 148 * 8;         // (8 CTAs of 256 threads per SM: the walk is latency-bound, occupancy pays)
+  if (ctas < 1) ctas = 1;
+  sg.G = (uint32_t)ctas;
+  sg.per_cta = (uint32_t)((n + ctas - 1) / ctas);
+  return sg;
+}
+
 template <class X>
 struct MsmGeom {
   MsmPlan pl;
+  MsmSortGeom sg;
   size_t nb, nrefs, max_pieces, nparts, max_vhot, lev_elems, out_bytes, need;
   uint32_t m, nbits, njobs, parts[ZKB_MSM_MAXLEV];
   bool skip;   // nothing to do (n == 0, or a window shard beyond the last window)
@@ -151,7 +171,13 @@ inline int msm_geometry(size_t n, uint32_t scalar_bits, uint32_t wrank, uint32_t
   if (table_n && (size_t)pl.nwin_total * table_n >= ((size_t)1 << 31))
     return set_error(ZKB_ERR_ARG, "msm: table index exceeds 31 bits");
   g->max_pieces = pl.max_runs + g->nb + 1;
-  g->nparts = (g->nb + ZKB_SCAN_TILE - 1) / ZKB_SCAN_TILE + 2;
+  g->sg = msm_sort_geometry(n, g->nb);
+  if ((size_t)g->sg.np * 4 > 96 * 1024) return set_error(ZKB_ERR_ARG, "msm: key space too large for the partition histogram");
+  {
+    size_t scan_max = (size_t)g->sg.np * g->sg.G + 1;          // the per-CTA partition histogram is the longest scan input
+    if (scan_max < g->nb) scan_max = g->nb;
+    g->nparts = (scan_max + ZKB_SCAN_TILE - 1) / ZKB_SCAN_TILE + 2;
+  }
   g->max_vhot = pl.max_runs / ZKB_MSM_VHOT + 1;
   for (uint32_t l = 0; l < pl.nlev; l++) g->lev_elems += (size_t)pl.bwin * pl.lsize[l + 1];
   g->m = pl.lsize[pl.nlev];
@@ -166,7 +192,8 @@ inline int msm_geometry(size_t n, uint32_t scalar_bits, uint32_t wrank, uint32_t
   g->out_bytes = (size_t)pl.bwin * g->njobs * sizeof(X);
   g->need = (g->nb + 1) * 4 * 6 + g->nrefs * 4 + (pl.max_runs + 1) * 4 + g->nb * 4 + g->max_vhot * 4 + g->nparts * 4 +
             g->max_pieces * sizeof(X) + 2 * g->lev_elems * sizeof(X) + g->max_vhot * ZKB_MSM_VHOT_SPLIT * sizeof(X) +
-            g->out_bytes + 32 * 256;
+            g->out_bytes + 32 * 256 +
+            ((size_t)g->sg.np * g->sg.G + 2) * 4 * 2 + g->nrefs * 8 + (size_t)g->sg.np * 4 + 2048;   // two-level sort: CTA histograms (+ scanned) and elements
   return ZKB_OK;
 }
 
@@ -254,14 +281,44 @@ int msm_phase1_t(int curve, int group, const void* d_points, const void* d_scala
     ZKB_CUDA(cudaMemcpyAsync(d->counters, sh->counters, 256, cudaMemcpyDeviceToDevice, st));
     ZKB_CUDA(cudaMemsetAsync(d->counters + 1, 0, 4, st));
   } else {
-    ZKB_CUDA(cudaMemsetAsync(cnt, 0, (nb + 1) * 4, st));
     ZKB_CUDA(cudaMemsetAsync(d->counters, 0, 256, st));
-    unsigned pblocks = (unsigned)((n + 255) / 256);
     unsigned bblocks = (unsigned)((nb + 255) / 256);
-    msm_count_kernel<<<pblocks, 256, 0, st>>>(pl, sc, cnt);
-    scan_u32(cnt, start, nb, part, st);
-    ZKB_CUDA(cudaMemcpyAsync(cursor, start, (nb + 1) * 4, cudaMemcpyDeviceToDevice, st));
-    msm_scatter_kernel<<<pblocks, 256, 0, st>>>(pl, sc, cursor, refs);
+    static const bool sort2 = [] { const char* e = getenv("ZKB_MSM_SORT2"); return !e || atoi(e) != 0; }();
+    if (sort2) {
+      // two-level sort, all histograms in shared memory (msm.cuh)
+      const MsmSortGeom& sg = g.sg;
+      const size_t hist_len = (size_t)sg.np * sg.G;
+      uint32_t* cta_hist = (uint32_t*)scratch_take((hist_len + 2) * 4);
+      uint32_t* cta_off = (uint32_t*)scratch_take((hist_len + 2) * 4);
+      uint2* elems = (uint2*)scratch_take(g.nrefs * 8);
+      if (!cta_hist || !cta_off || !elems) return set_error(ZKB_ERR_CUDA, "msm: scratch exhausted");
+      static bool sort_attr = false;
+      if (!sort_attr) {
+        ZKB_CUDA(cudaFuncSetAttribute(msm_part_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        ZKB_CUDA(cudaFuncSetAttribute(msm_part_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        sort_attr = true;
+      }
+      const size_t hsm = (size_t)sg.np * 4;
+      msm_part_hist_kernel<<<sg.G, 256, hsm, st>>>(pl, sg, sc, cta_hist);
+      scan_u32(cta_hist, cta_off, hist_len, part, st);
+      msm_part_scatter_kernel<<<sg.G, 256, hsm, st>>>(pl, sg, sc, cta_off, elems);
+      // oversized partitions (top window, skewed witnesses) are listed by the level-2 kernel and spread over the grid
+      uint32_t* big_count = (uint32_t*)scratch_take(256);
+      uint32_t* big_list = (uint32_t*)scratch_take((size_t)sg.np * 4);
+      if (!big_count || !big_list) return set_error(ZKB_ERR_CUDA, "msm: scratch exhausted");
+      ZKB_CUDA(cudaMemsetAsync(big_count, 0, 4, st));
+      msm_bucket_sort_kernel<<<sg.np, 256, 0, st>>>(sg, (unsigned long long)nb, cta_off, elems, cnt, start, refs, big_count, big_list);
+      msm_big_count_kernel<<<148 * 2, 256, 0, st>>>(sg, cta_off, elems, big_count, big_list, cnt);
+      msm_big_scan_kernel<<<32, 128, 0, st>>>(sg, (unsigned long long)nb, cta_off, big_count, big_list, cnt, start, cursor);
+      msm_big_scatter_kernel<<<148 * 2, 256, 0, st>>>(sg, cta_off, elems, big_count, big_list, cursor, refs);
+    } else {
+      ZKB_CUDA(cudaMemsetAsync(cnt, 0, (nb + 1) * 4, st));
+      unsigned pblocks = (unsigned)((n + 255) / 256);
+      msm_count_kernel<<<pblocks, 256, 0, st>>>(pl, sc, cnt);
+      scan_u32(cnt, start, nb, part, st);
+      ZKB_CUDA(cudaMemcpyAsync(cursor, start, (nb + 1) * 4, cudaMemcpyDeviceToDevice, st));
+      msm_scatter_kernel<<<pblocks, 256, 0, st>>>(pl, sc, cursor, refs);
+    }
     msm_piece_plan_kernel<<<bblocks, 256, 0, st>>>(pl, cnt, start, npieces, d->np_eff, run_bucket, d->hot_list, d->vhot_list,
                                                    d->counters);
     scan_u32(npieces, d->pstart, nb, part, st);

@@ -288,6 +288,9 @@ __global__ void check_abc_kernel(unsigned long long n, const F* __restrict__ a, 
 // out[row] = sum_k val[k] * w[col[k]] over the CSR row -- SparseArray.dot of /root/reference/python/zksnake/array.py:36-43
 // (the A.w, B.w, C.w products of qap.py:53-55).  Rows past n_rows_csr (domain padding) are zero.  Canonical in and out:
 // the raw Montgomery products val*w/R are summed and one multiplication by R^2 restores the scale.
+#define ZKB_SPMV_LONG 64u      // rows with more non-zeros than this are summed by whole CTAs (spmv_long_kernel)
+#define ZKB_SPMV_SPLIT 64u     // CTAs per long row
+
 template <class F>
 __global__ void spmv_kernel(unsigned long long n_out, unsigned long long n_rows_csr, const unsigned long long* __restrict__ row_ptr,
                             const uint32_t* __restrict__ col, const F* __restrict__ val, const F* __restrict__ w,
@@ -297,10 +300,63 @@ __global__ void spmv_kernel(unsigned long long n_out, unsigned long long n_rows_
   F acc = F::zero();
   if (row < n_rows_csr) {
     unsigned long long lo = row_ptr[row], hi = row_ptr[row + 1];
+    if (hi - lo > ZKB_SPMV_LONG) return;     // a long row: spmv_long_kernel / spmv_long_finish_kernel write it
     for (unsigned long long k = lo; k < hi; k++) acc = acc + ntt_ldg(val + k) * ntt_ld(w + col[k]);
     acc = acc * F::r2();
   }
   ntt_st(out + row, acc);
+}
+
+// Skewed matrices: one column of a circuit that feeds every constraint (the `inp` wire of the chain circuit: a 2^20-entry row of
+// B^T in Groth16.setup's L/R/O products, /root/reference/python/zksnake/groth16/protocol.py:64-77) would keep ONE thread busy
+// for 2^20 products (270 ms per launch in round 1).  The rows longer than ZKB_SPMV_LONG are listed when the matrix is
+// created; CTA (j, r) sums slice j of long row r (raw Montgomery products, block tree), a warp adds the ZKB_SPMV_SPLIT slices.
+template <class F>
+__global__ void __launch_bounds__(256) spmv_long_kernel(const uint32_t* __restrict__ long_rows,
+                                                        const unsigned long long* __restrict__ row_ptr,
+                                                        const uint32_t* __restrict__ col, const F* __restrict__ val,
+                                                        const F* __restrict__ w, F* __restrict__ partial) {
+  __shared__ uint4 sh0[256], sh1[256];
+  const uint32_t row = long_rows[blockIdx.y];
+  const unsigned long long lo = row_ptr[row], hi = row_ptr[row + 1];
+  const unsigned long long per = (hi - lo + ZKB_SPMV_SPLIT - 1) / ZKB_SPMV_SPLIT;
+  unsigned long long a = lo + blockIdx.x * per, b = a + per;
+  if (b > hi) b = hi;
+  F acc = F::zero();
+  for (unsigned long long k = a + threadIdx.x; k < b; k += blockDim.x) acc = acc + ntt_ldg(val + k) * ntt_ld(w + col[k]);
+  const uint32_t t = threadIdx.x;
+  sh0[t] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+  sh1[t] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+  __syncthreads();
+  for (uint32_t off = 128; off > 0; off >>= 1) {
+    if (t < off) {
+      uint4 p = sh0[t + off], q = sh1[t + off];
+      F o;
+      o.v[0] = p.x; o.v[1] = p.y; o.v[2] = p.z; o.v[3] = p.w;
+      o.v[4] = q.x; o.v[5] = q.y; o.v[6] = q.z; o.v[7] = q.w;
+      acc = acc + o;
+      sh0[t] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+      sh1[t] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+    }
+    __syncthreads();
+  }
+  if (t == 0) ntt_st(partial + (unsigned long long)blockIdx.y * ZKB_SPMV_SPLIT + blockIdx.x, acc);
+}
+// one warp per long row: sum of its slice sums, scale restored, written to out[row]
+template <class F>
+__global__ void __launch_bounds__(128) spmv_long_finish_kernel(uint32_t n_long, const uint32_t* __restrict__ long_rows,
+                                                               const F* __restrict__ partial, F* __restrict__ out) {
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_long) return;
+  F acc = F::zero();
+  for (uint32_t j = lane; j < ZKB_SPMV_SPLIT; j += 32) acc = acc + ntt_ld(partial + (unsigned long long)warp * ZKB_SPMV_SPLIT + j);
+  for (uint32_t off = 16; off > 0; off >>= 1) {
+    F o;
+#pragma unroll
+    for (int i = 0; i < F::N; i++) o.v[i] = __shfl_down_sync(0xffffffffu, acc.v[i], off);
+    acc = acc + o;
+  }
+  if (lane == 0) ntt_st(out + long_rows[warp], acc * F::r2());
 }
 
 }  // namespace zkb

@@ -4,6 +4,7 @@
 #include <map>
 #include <vector>
 #include "ntt.cuh"
+#include "ntt_warp.cuh"
 #include "zkb_internal.h"
 
 namespace zkb {
@@ -168,6 +169,99 @@ static size_t pass_smem(uint32_t k, uint32_t log_c) {
 
 size_t ntt_scratch_bytes(uint32_t log_n) { return ((size_t)32 << log_n) + 256; }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// register-resident passes (ntt_warp.cuh): used from 2^11 up; below that one shared-memory pass of ntt_pass_kernel does it
+// ------------------------------------------------------------------------------------------------------------------------
+// A lane holds 2^2 elements: a warp transforms columns of up to 2^7 elements (no spills at 128 registers).  Measured on a B200
+// (profiles/R2_ntt_probe.md): for ONE transform the register-resident passes tie with the shared-memory passes at 2^20 (0.256 vs
+// 0.262 ms) and lose from 2^21 up (an extra pass over the data: 1.11 vs 1.00 ms at 2^22), so zkb_ntt_dev keeps the shared-memory
+// kernel; for the BATCHED transforms of the Groth16 quotient (three columns' worth of work per launch, 9 launches instead of 18)
+// they win at every size (2^12: 0.116 vs 0.161 ms, 2^16: 0.206 vs 0.222, 2^20: 1.98 vs 2.06), so groth16_h_t uses them.
+static inline bool use_warp_ntt(uint32_t log_n) { return log_n >= 11 && log_n <= 28 && env_int("ZKB_NTT_WARP", 1) != 0; }
+static inline int warp_ntt_el(uint32_t) { return 2; }
+
+static Plan make_warp_plan(uint32_t log_n, int el) {
+  Plan p;
+  const uint32_t kmax = (uint32_t)el + 5;
+  uint32_t npass = (log_n + kmax - 1) / kmax;
+  uint32_t rem = log_n;
+  for (uint32_t i = 0; i < npass; i++) {
+    uint32_t k = (rem + (npass - i) - 1) / (npass - i);
+    p.k.push_back(k);
+    p.log_c.push_back(0);
+    rem -= k;
+  }
+  return p;
+}
+
+extern template int ntt_warp_launch_el<fr_bn, 2>(const fr_bn*, fr_bn*, const NttPass&, uint32_t, size_t, size_t, const PowTable<fr_bn>&,
+                                                 const PreTables<fr_bn>&, const PowTable<fr_bn>&, const fr_bn&, void*);
+extern template int ntt_warp_launch_el<fr_bls, 2>(const fr_bls*, fr_bls*, const NttPass&, uint32_t, size_t, size_t,
+                                                  const PowTable<fr_bls>&, const PreTables<fr_bls>&, const PowTable<fr_bls>&,
+                                                  const fr_bls&, void*);
+// `batch` transforms of the same size and direction, member b at in + b * stride / out + b * stride (stride in elements);
+// pre[b]: first-pass scaling table of member b (nullptr: none); tmp holds batch * 2^log_n elements.
+template <class F>
+static int ntt_exec_warp(const F* in, size_t in_len, F* out, uint32_t log_n, uint32_t batch, size_t stride, const PowTable<F>& tw,
+                         const PowTable<F>* const* pre, const PowTable<F>* post, const F* post_const, F* tmp) {
+  if (batch == 0 || batch > ZKB_NTT_MAX_BATCH) return set_error(ZKB_ERR_ARG, "ntt: batch out of range");
+  const int el = warp_ntt_el(log_n);
+  Plan plan = make_warp_plan(log_n, el);
+  const uint32_t P = (uint32_t)plan.k.size();
+  if (P < 2 || P > 4) return set_error(ZKB_ERR_ARG, "ntt: unsupported size for the register-resident path");
+  size_t n = (size_t)1 << log_n;
+  if (in_len > n) in_len = n;
+  PowTable<F> none;
+  none.lo = none.hi = nullptr;
+  none.h = 0;
+  none.direct = 0;
+  PreTables<F> pres;
+  bool any_pre = false;
+  for (uint32_t b = 0; b < ZKB_NTT_MAX_BATCH; b++) {
+    pres.t[b] = (pre && b < batch && pre[b]) ? *pre[b] : none;
+    any_pre |= pre && b < batch && pre[b];
+  }
+  if (any_pre)
+    for (uint32_t b = 0; b < batch; b++)
+      if (!pre[b]) return set_error(ZKB_ERR_ARG, "ntt: a batch mixes scaled and unscaled members");
+  uint32_t log_b = 0, log_m = log_n;
+  prof_begin(PROF_NTT);
+  for (uint32_t p = 0; p < P; p++) {
+    NttPass pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.log_n = log_n;
+    pp.k = plan.k[p];
+    pp.log_c = 0;
+    log_m -= pp.k;
+    pp.log_m = log_m;
+    pp.log_b = log_b;
+    pp.last = (p + 1 == P);
+    pp.k1 = plan.k[0];
+    pp.nmid = P - 2;
+    pp.kmid[0] = P > 2 ? plan.k[1] : 0;
+    pp.kmid[1] = P > 3 ? plan.k[2] : 0;
+    pp.pre = (p == 0 && any_pre) ? 1 : 0;
+    pp.post = 0;
+    if (pp.last) pp.post = post ? 1 : (post_const ? 2 : 0);
+    pp.in_len = (p == 0) ? in_len : n;
+    const F* src = (p == 0) ? in : tmp;
+    F* dst = pp.last ? out : tmp;
+    const size_t src_stride = (p == 0) ? stride : n, dst_stride = pp.last ? stride : n;
+    const PowTable<F>& postv = post ? *post : none;
+    const F pc = post_const ? *post_const : F::zero();
+    int lrc = ntt_warp_launch_el<F, 2>(src, dst, pp, batch, src_stride, dst_stride, tw, pres, postv, pc, (void*)S());
+    if (lrc) {
+      prof_end(PROF_NTT);
+      return set_error(ZKB_ERR_ARG, "ntt: pass radix outside the instantiated range");
+    }
+    count_launch();
+    log_b += pp.k;
+  }
+  prof_end(PROF_NTT);
+  ZKB_CUDA(cudaGetLastError());
+  return ZKB_OK;
+}
+
 template <class F>
 static int ntt_exec(const F* in, size_t in_len, F* out, uint32_t log_n, const PowTable<F>& tw, const PowTable<F>* pre,
                     const PowTable<F>* post, const F* post_const, F* tmp) {
@@ -175,6 +269,10 @@ static int ntt_exec(const F* in, size_t in_len, F* out, uint32_t log_n, const Po
   if (!attr_set) {
     ZKB_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
+  }
+  if (use_warp_ntt(log_n) && (log_n == 11 || env_int("ZKB_NTT_WARP_SINGLE", 0))) {   // (2^11: 0.029 vs 0.045 ms)
+    const PowTable<F>* pres[1] = {pre};
+    return ntt_exec_warp<F>(in, in_len, out, log_n, 1, (size_t)1 << log_n, tw, pre ? pres : nullptr, post, post_const, tmp);
   }
   Plan plan = make_plan(log_n);
   const uint32_t P = (uint32_t)plan.k.size();
@@ -330,14 +428,15 @@ static int groth16_h_t(uint32_t log_n, const void* d_a, const void* d_b, const v
   Domain<F>* d;
   int rc = get_domain<F>(log_n, true, &d);
   if (rc) return rc;
-  size_t need = 3 * ((size_t)32 << log_n) + 4096;
+  size_t need = 6 * ((size_t)32 << log_n) + 8192;
   if ((rc = scratch_reserve(need))) return rc;
   scratch_reset();
-  F* tmp = (F*)scratch_take(n * sizeof(F));
-  F* ea = (F*)scratch_take(n * sizeof(F));
-  F* eb = (F*)scratch_take(n * sizeof(F));
+  F* tmp = (F*)scratch_take(3 * n * sizeof(F));     // pass-to-pass buffer of up to three batched transforms
+  F* ea = (F*)scratch_take(3 * n * sizeof(F));      // coset evaluations of U, V, W (contiguous: one batched transform)
   int* flag = (int*)scratch_take(256);
-  if (!tmp || !ea || !eb || !flag) return set_error(ZKB_ERR_CUDA, "scratch exhausted");
+  if (!tmp || !ea || !flag) return set_error(ZKB_ERR_CUDA, "scratch exhausted");
+  F* eb = ea + n;
+  F* ec = eb + n;
   if (check) {
     ZKB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), S()));
     unsigned blocks = (unsigned)((n + 255) / 256);
@@ -350,13 +449,22 @@ static int groth16_h_t(uint32_t log_n, const void* d_a, const void* d_b, const v
   PowTable<F> fwd = d->fwd.view(), inv_t = d->inv.view();
   PowTable<F> gpre = d->gen_pre.view(), gpre_r = d->gen_pre_r.view(), gpost = d->gen_post.view();
   F* U = (F*)d_u; F* V = (F*)d_v; F* W = (F*)d_w; F* H = (F*)d_h;
-  if ((rc = ntt_exec<F>((const F*)d_a, n, U, log_n, inv_t, nullptr, nullptr, &d->n_inv, tmp))) return rc;
-  if ((rc = ntt_exec<F>((const F*)d_b, n, V, log_n, inv_t, nullptr, nullptr, &d->n_inv, tmp))) return rc;
-  if ((rc = ntt_exec<F>((const F*)d_c, n, W, log_n, inv_t, nullptr, nullptr, &d->n_inv, tmp))) return rc;
-  if ((rc = ntt_exec<F>(U, n, ea, log_n, fwd, &gpre, nullptr, nullptr, tmp))) return rc;
-  if ((rc = ntt_exec<F>(V, n, eb, log_n, fwd, &gpre, nullptr, nullptr, tmp))) return rc;
-  if ((rc = ntt_exec<F>(W, n, H, log_n, fwd, &gpre_r, nullptr, nullptr, tmp))) return rc;   // W(g w^i) / R
-  if ((rc = vec_op_t<F>(VEC_MULSUB_RAW, n, ea, n, eb, n, H, ea))) return rc;                 // (U V - W)/R on the coset
+  const bool contiguous = (const F*)d_b == (const F*)d_a + n && (const F*)d_c == (const F*)d_b + n && V == U + n && W == V + n;
+  if (use_warp_ntt(log_n) && contiguous) {
+    // the three interpolations as ONE batched transform per pass, then the three coset evaluations likewise: 9 launches instead
+    // of 18, and three times the columns per launch to fill the waves (W goes through g^j / R, see vec_op_kernel)
+    if ((rc = ntt_exec_warp<F>((const F*)d_a, n, U, log_n, 3, n, inv_t, nullptr, nullptr, &d->n_inv, tmp))) return rc;
+    const PowTable<F>* pres[3] = {&gpre, &gpre, &gpre_r};
+    if ((rc = ntt_exec_warp<F>(U, n, ea, log_n, 3, n, fwd, pres, nullptr, nullptr, tmp))) return rc;
+  } else {
+    if ((rc = ntt_exec<F>((const F*)d_a, n, U, log_n, inv_t, nullptr, nullptr, &d->n_inv, tmp))) return rc;
+    if ((rc = ntt_exec<F>((const F*)d_b, n, V, log_n, inv_t, nullptr, nullptr, &d->n_inv, tmp))) return rc;
+    if ((rc = ntt_exec<F>((const F*)d_c, n, W, log_n, inv_t, nullptr, nullptr, &d->n_inv, tmp))) return rc;
+    if ((rc = ntt_exec<F>(U, n, ea, log_n, fwd, &gpre, nullptr, nullptr, tmp))) return rc;
+    if ((rc = ntt_exec<F>(V, n, eb, log_n, fwd, &gpre, nullptr, nullptr, tmp))) return rc;
+    if ((rc = ntt_exec<F>(W, n, ec, log_n, fwd, &gpre_r, nullptr, nullptr, tmp))) return rc;   // W(g w^i) / R
+  }
+  if ((rc = vec_op_t<F>(VEC_MULSUB_RAW, n, ea, n, eb, n, ec, ea))) return rc;                  // (U V - W)/R on the coset
   if ((rc = ntt_exec<F>(ea, n, H, log_n, inv_t, nullptr, &gpost, nullptr, tmp))) return rc;
   if (check) {
     int hflag = 0;
@@ -374,20 +482,29 @@ int groth16_h_dev(int curve, uint32_t log_n, const void* d_a, const void* d_b, c
 }
 
 template <class F>
-static int spmv_t(size_t n_out, size_t n_rows, const void* row_ptr, const void* col, const void* val, const void* w, void* out) {
+static int spmv_t(size_t n_out, size_t n_rows, const void* row_ptr, const void* col, const void* val, const void* w, void* out,
+                  const uint32_t* long_rows, uint32_t n_long, void* long_partial) {
   if (n_out == 0) return ZKB_OK;
   prof_begin(PROF_SPMV);
   spmv_kernel<F><<<(unsigned)((n_out + 127) / 128), 128, 0, S()>>>(n_out, n_rows, (const unsigned long long*)row_ptr,
                                                                    (const uint32_t*)col, (const F*)val, (const F*)w, (F*)out);
-  prof_end(PROF_SPMV);
   count_launch();
+  if (n_long) {
+    spmv_long_kernel<F><<<dim3(ZKB_SPMV_SPLIT, n_long), 256, 0, S()>>>(long_rows, (const unsigned long long*)row_ptr,
+                                                                       (const uint32_t*)col, (const F*)val, (const F*)w,
+                                                                       (F*)long_partial);
+    spmv_long_finish_kernel<F><<<(n_long * 32 + 127) / 128, 128, 0, S()>>>(n_long, long_rows, (const F*)long_partial, (F*)out);
+    count_launch(2);
+  }
+  prof_end(PROF_SPMV);
   ZKB_CUDA(cudaGetLastError());
   return ZKB_OK;
 }
 int spmv_dev(int curve, size_t n_out, size_t n_rows, const void* row_ptr, const void* col, const void* val, const void* w,
-             void* out) {
-  if (curve == ZKB_BN254) return spmv_t<fr_bn>(n_out, n_rows, row_ptr, col, val, w, out);
-  if (curve == ZKB_BLS12_381) return spmv_t<fr_bls>(n_out, n_rows, row_ptr, col, val, w, out);
+             void* out, const uint32_t* long_rows, uint32_t n_long, void* long_partial) {
+  if (n_long > 65535) return set_error(ZKB_ERR_ARG, "r1cs: too many long rows");
+  if (curve == ZKB_BN254) return spmv_t<fr_bn>(n_out, n_rows, row_ptr, col, val, w, out, long_rows, n_long, long_partial);
+  if (curve == ZKB_BLS12_381) return spmv_t<fr_bls>(n_out, n_rows, row_ptr, col, val, w, out, long_rows, n_long, long_partial);
   return set_error(ZKB_ERR_ARG, "unknown curve id");
 }
 

@@ -75,8 +75,11 @@ int fr_powers_dev(int curve, const uint64_t* base, const uint64_t* scale, size_t
 int groth16_h_dev(int curve, uint32_t log_n, const void* d_a, const void* d_b, const void* d_c, void* d_u, void* d_v,
                   void* d_w, void* d_h, int check);
 size_t ntt_scratch_bytes(uint32_t log_n);
+// long_rows: the n_long rows with more than SPMV_LONG_ROW non-zeros (device array, listed when the matrix is created); they are
+// summed by whole CTAs into long_partial (n_long * 64 elements) instead of by one thread each
+#define SPMV_LONG_ROW 64
 int spmv_dev(int curve, size_t n_out, size_t n_rows, const void* row_ptr, const void* col, const void* val, const void* w,
-             void* out);
+             void* out, const uint32_t* long_rows, uint32_t n_long, void* long_partial);
 
 // window size / window count the plain (table-less) MSM heuristic picks for n points (msm_common.cu)
 void msm_plan_info(size_t n, uint32_t scalar_bits, uint32_t wworld, uint32_t* c, uint32_t* W);

@@ -89,6 +89,9 @@ int zkb_dev_free(void* p);
 int zkb_host_alloc(size_t bytes, void** out);   /* pinned */
 int zkb_host_free(void* p);
 int zkb_h2d(void* dst, const void* src, size_t bytes);
+/* the same without the synchronisation: enqueued on the library stream; `src` must stay untouched until the stream has passed the
+ * copy (pinned memory from zkb_host_alloc makes it a true asynchronous DMA transfer) */
+int zkb_h2d_async(void* dst, const void* src, size_t bytes);
 int zkb_d2h(void* dst, const void* src, size_t bytes);
 int zkb_d2d(void* dst, const void* src, size_t bytes);
 int zkb_memset(void* dst, int value, size_t bytes);
@@ -262,6 +265,10 @@ int zkb_groth16_partial(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const void* witness,
                         uint64_t* msm_xy, int* msm_inf);
 int zkb_groth16_assemble(zkb_groth16_pk* pk, const uint64_t* msm_xy, const int* msm_inf, const uint64_t r[4],
                          const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c, int out_inf[3]);
+/* The last two steps in one call: all_xy = world x 5 x 24 uint64 (every rank's msm_xy, rank-major), all_inf = world x 5 flags; the
+ * slot sums over the ranks are formed on host threads and assembled (protocol.py:133-165). */
+int zkb_groth16_assemble_partials(zkb_groth16_pk* pk, int world, const uint64_t* all_xy, const int* all_inf, const uint64_t r[4],
+                                  const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c, int out_inf[3]);
 /* intermediate results of the last prove on this key, for parity tests: which = 0 U, 1 V, 2 H (n coefficients each) */
 int zkb_groth16_last_poly(zkb_groth16_pk* pk, int which, uint64_t* out);
 /* the five raw MSM results of the last prove (A, B1, B2, HZ, KW) as affine canonical points + infinity flags */

@@ -143,6 +143,17 @@ def _gather_worker(rank, world, port, q):
         vals.append("no error")
     except RuntimeError:
         pass
+    # the node-local shared-memory mailbox that carries the partial MSM sums (several rounds: the two buffers alternate)
+    hx = dist.host_exchange()
+    rounds = []
+    for k in range(5):
+        xy = (np.arange(dist.MSM_SLOTS * dist.SLOT_LIMBS, dtype=np.uint64).reshape(dist.MSM_SLOTS, dist.SLOT_LIMBS) + 1000 * rank + k)
+        inf = np.array([rank, k, 0, 1, rank ^ 1], dtype=np.int32)
+        all_xy, all_inf = dist.all_gather_partials(xy, inf)
+        rounds.append((all_xy[:, 0, 0].tolist(), all_xy[:, 4, 23].tolist(), all_inf.tolist()))
+    vals.append(("hx", hx is not None, rounds))
+    if hx is not None:
+        hx.close()
     q.put((rank, got.tolist(), vals))
     td.destroy_process_group()
 
@@ -164,7 +175,13 @@ def test_all_gather_array_and_shared_draws_gloo():
     assert res[0][1] == want and res[1][1] == want
     import random
     rank0 = random.Random(100)
-    assert res[0][2] == res[1][2] == [rank0.randint(1, 10 ** 30) for _ in range(4)]    # the values ARE rank 0's draws
+    assert res[0][2][:4] == res[1][2][:4] == [rank0.randint(1, 10 ** 30) for _ in range(4)]    # the values ARE rank 0's draws
+    for r in (0, 1):
+        tag, have, rounds = res[r][2][4]
+        assert tag == "hx" and have
+        for k, (first, last, inf) in enumerate(rounds):
+            assert first == [k, 1000 + k] and last == [4 * 24 + 23 + k, 1000 + 4 * 24 + 23 + k]
+            assert inf == [[0, k, 0, 1, 1], [1, k, 0, 1, 0]]
 
 
 def test_sharded_prover_needs_a_matching_process_group():

@@ -127,7 +127,7 @@ def test_device_prover_matches_oracle(gpu, curve_name, n_gates):
         pm.get_random_int = old
     assert proof.to_bytes() == want
     assert plonk.verify(proof, pub)
-    assert set(plonk.timings) == {"round1", "round2", "round3", "round4", "round5"}
+    assert {"round1", "round2", "round3", "round4", "round5"} <= set(plonk.timings)
 
 
 def test_device_prover_large_and_bad_witness(gpu):

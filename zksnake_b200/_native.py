@@ -48,6 +48,7 @@ def _load():
         "zkb_host_alloc": (c_int, [c_sz, ctypes.POINTER(c_vp)]),
         "zkb_host_free": (c_int, [c_vp]),
         "zkb_h2d": (c_int, [c_vp, c_vp, c_sz]),
+        "zkb_h2d_async": (c_int, [c_vp, c_vp, c_sz]),
         "zkb_d2h": (c_int, [c_vp, c_vp, c_sz]),
         "zkb_d2d": (c_int, [c_vp, c_vp, c_sz]),
         "zkb_memset": (c_int, [c_vp, c_int, c_sz]),
@@ -106,6 +107,7 @@ def _load():
         "zkb_groth16_prove_witness_dev": (c_int, [c_vp, c_vp, c_vp, c_sz, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "zkb_groth16_partial": (c_int, [c_vp, c_vp, c_vp, c_int, c_sz, c_vp, c_vp]),
         "zkb_groth16_assemble": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+        "zkb_groth16_assemble_partials": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "zkb_groth16_last_poly": (c_int, [c_vp, c_int, c_vp]),
         "zkb_groth16_last_msm": (c_int, [c_vp, c_int, c_vp, ctypes.POINTER(c_int)]),
         "zkb_test_field_op_host": (c_int, [c_int, c_int, c_sz, c_vp, c_vp, c_vp]),

@@ -694,6 +694,31 @@ int zkb_groth16_assemble(zkb_groth16_pk* pk, const uint64_t* msm_xy, const int* 
   return ZKB_OK;
 }
 
+int zkb_groth16_assemble_partials(zkb_groth16_pk* pk, int world, const uint64_t* all_xy, const int* all_inf, const uint64_t r[4],
+                                  const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c, int out_inf[3]) {
+  if (!pk || world < 1 || !all_xy || !all_inf) return set_error(ZKB_ERR_ARG, "bad argument");
+  // slot sums over the ranks (exact host group law), the five slots side by side on host threads, then the assembly
+  uint64_t sum_xy[5][24];
+  int sum_inf[5];
+  memset(sum_xy, 0, sizeof(sum_xy));
+  const int curve = pk->curve;
+  auto add_slot = [&](int slot) {
+    const int grp = slot == 2 ? 2 : 1;
+    std::vector<const uint64_t*> pts(world), sc(world, nullptr);
+    std::vector<int> infs(world);
+    for (int k = 0; k < world; k++) {
+      pts[k] = all_xy + ((size_t)k * 5 + slot) * 24;
+      infs[k] = all_inf[k * 5 + slot];
+    }
+    host_lincomb(curve, grp, world, pts.data(), infs.data(), sc.data(), sum_xy[slot], &sum_inf[slot]);
+  };
+  std::thread th[4];
+  for (int slot = 1; slot < 5; slot++) th[slot - 1] = std::thread(add_slot, slot);
+  add_slot(0);
+  for (int i = 0; i < 4; i++) th[i].join();
+  return zkb_groth16_assemble(pk, &sum_xy[0][0], sum_inf, r, s, out_a, out_b, out_c, out_inf);
+}
+
 int zkb_groth16_prove_dev(zkb_groth16_pk* pk, const void* d_a, const void* d_b, const void* d_c, const void* d_priv,
                           const uint64_t r[4], const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c,
                           int out_inf[3]) {

@@ -258,6 +258,12 @@ int zkb_h2d(void* dst, const void* src, size_t bytes) {
   ZKB_CUDA(cudaStreamSynchronize(g_ctx.stream));
   return ZKB_OK;
 }
+int zkb_h2d_async(void* dst, const void* src, size_t bytes) {
+  NEED_INIT();
+  count_h2d(bytes);
+  ZKB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_ctx.stream));
+  return ZKB_OK;
+}
 int zkb_d2h(void* dst, const void* src, size_t bytes) {
   NEED_INIT();
   count_d2h(bytes);

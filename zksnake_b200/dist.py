@@ -48,49 +48,166 @@ def nccl_ready():
         return False
 
 
+_lib_stream = None
+_upload_bufs = {}
+
+
+def library_stream():
+    """torch view of the library's CUDA stream (zkb_stream): torch copies and NCCL collectives issued under
+    `torch.cuda.stream(library_stream())` are ORDERED with the library's kernels -- no host synchronisation between a
+    collective and the kernels that consume it (ProcessGroupNCCL makes the current stream wait for its own NCCL stream)."""
+    global _lib_stream
+    import torch
+    if _lib_stream is None:
+        nat.ensure_init()
+        _lib_stream = torch.cuda.ExternalStream(nat.lib.zkb_stream())
+    return _lib_stream
+
+
 def upload_sharded(arr):
     """A host array that every rank holds (the witness) -> a device copy on every rank, moving only 1/world of it over each
     rank's PCIe link: every rank uploads its own slice and one NCCL all-gather over NVLink completes the vector.  With N
     ranks uploading the whole 32 MiB witness at once the host side is the bottleneck (measured: +1.0 ms at 4 GPUs against
-    +0.4 ms at 1).  Returns a torch uint8 CUDA tensor (keep it alive while the library reads `data_ptr()`)."""
+    +0.4 ms at 1).  Both steps are enqueued on the library stream and the buffers persist across proofs: the call returns
+    without synchronising.  Returns a torch uint8 CUDA tensor (valid until the next call with the same size)."""
     import torch
     import torch.distributed as td
     rank, ws = world()
     flat = np.ascontiguousarray(arr).reshape(-1).view(np.uint8)
     nbytes = flat.size
     per = -(-nbytes // (ws * 256)) * 256                      # slice size, 256-byte aligned
-    full = torch.empty(per * ws, dtype=torch.uint8, device="cuda")
-    mine = torch.empty(per, dtype=torch.uint8, device="cuda")
+    bufs = _upload_bufs.get((nbytes, ws))
+    if bufs is None:     # one pair per distinct size, kept for the life of the process (the library stream may still be reading them)
+        with torch.cuda.stream(library_stream()):
+            bufs = (torch.empty(per * ws, dtype=torch.uint8, device="cuda"), torch.empty(per, dtype=torch.uint8, device="cuda"))
+        _upload_bufs[(nbytes, ws)] = bufs
+    full, mine = bufs
     lo = min(rank * per, nbytes)
     hi = min(lo + per, nbytes)
-    if hi > lo:
-        mine[:hi - lo].copy_(torch.from_numpy(flat[lo:hi]), non_blocking=True)
-        TRANSFER["h2d"] += hi - lo
-    td.all_gather_into_tensor(full, mine)
-    torch.cuda.current_stream().synchronize()                 # the library reads it on its own stream
+    with torch.cuda.stream(library_stream()):
+        if hi > lo:
+            # (the source is cudaHostAlloc'ed by the caller when it wants full PCIe rate; the driver recognises it by address)
+            # counted by the library (zkb_transfer_count), not in TRANSFER
+            nat.check(nat.lib.zkb_h2d_async(ctypes.c_void_p(mine.data_ptr()), ctypes.c_void_p(flat[lo:hi].ctypes.data), hi - lo))
+        td.all_gather_into_tensor(full, mine)
     return full
+
+
+# ---- host-side exchange of small payloads between the ranks of ONE node -----------------------------------------------------
+class HostExchange:
+    """All-gather of a few hundred bytes per rank through a POSIX shared-memory mailbox.
+
+    The per-rank partial MSM results are BORN ON THE HOST: the per-window sums of every MSM come back from the GPU and are
+    recombined by host threads (csrc/host_math.cpp: a serial chain of ~100 group operations is ~100x faster on a CPU core than in
+    one GPU thread).  Sending those 5 points through NCCL means host -> device -> NVLink -> device -> host with two stream
+    synchronisations (round 1: ~0.3 ms of the 8 ms proof at 8 GPUs); all ranks of the bench are processes of one node
+    (`torchrun --nnodes=1`), so they are exchanged where they are: every rank owns one slot of a shared segment, publishes
+    (payload, sequence number) and spins until every other slot shows the same sequence number -- a few microseconds.  Two
+    alternating buffers per slot make the protocol safe without a second barrier (a rank can be at most one round ahead).
+    NCCL carries the data-path traffic (the witness all-gather); multi-node jobs fall back to the torch collective."""
+    SLOT = 2048
+
+    def __init__(self):
+        import atexit
+        from multiprocessing import shared_memory
+        import torch.distributed as td
+        self.rank, self.ws = world()
+        name = [None]
+        if self.rank == 0:
+            import os
+            name[0] = f"zkb200_{os.getpid()}_{int.from_bytes(os.urandom(4), 'little')}"
+            self.shm = shared_memory.SharedMemory(name=name[0], create=True, size=self.ws * 2 * (self.SLOT + 64))
+            self.shm.buf[:] = bytes(len(self.shm.buf))
+        td.broadcast_object_list(name, src=0)
+        if self.rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+        td.barrier()
+        self._owner = self.rank == 0
+        stride = self.SLOT + 64
+        raw = np.frombuffer(self.shm.buf, dtype=np.uint8, count=self.ws * 2 * stride)
+        self._seq = [[raw[(r * 2 + b) * stride:(r * 2 + b) * stride + 8].view(np.uint64) for b in range(2)] for r in range(self.ws)]
+        self._data = [[raw[(r * 2 + b) * stride + 64:(r * 2 + b + 1) * stride] for b in range(2)] for r in range(self.ws)]
+        self._raw = raw
+        self.round = 0
+        atexit.register(self.close)
+
+    def close(self):
+        shm, self.shm = getattr(self, "shm", None), None
+        if shm is None:
+            return
+        self._seq = self._data = self._raw = None
+        try:
+            shm.close()
+            if self._owner:
+                shm.unlink()
+        except Exception:
+            pass
+
+    def all_gather(self, payload):
+        """payload: uint8 array of at most SLOT bytes, same length on every rank -> (world, len) uint8 array"""
+        import time
+        n = payload.size
+        assert n <= self.SLOT
+        self.round += 1
+        b = self.round & 1
+        self._data[self.rank][b][:n] = payload
+        self._seq[self.rank][b][0] = self.round            # published after the payload (x86 keeps the store order)
+        out = np.empty((self.ws, n), dtype=np.uint8)
+        deadline = time.monotonic() + 120.0
+        for r in range(self.ws):
+            seq = self._seq[r][b]
+            spins = 0
+            while seq[0] != self.round:
+                spins += 1
+                if spins & 0xFFFF == 0 and time.monotonic() > deadline:
+                    raise RuntimeError(f"rank {self.rank}: no partial sums from rank {r} after 120 s")
+            out[r] = self._data[r][b][:n]
+        return out
+
+
+_host_exchange = None
+
+
+def host_exchange():
+    """The node-local mailbox, created on first use (None when the job spans several nodes or shared memory is unavailable)."""
+    global _host_exchange
+    import os
+    if _host_exchange is None:
+        local = int(os.environ.get("LOCAL_WORLD_SIZE", "0") or 0)
+        rank, ws = world()
+        if os.environ.get("ZKB_HOST_EXCHANGE", "1") == "0" or (local and local != ws):
+            _host_exchange = False
+        else:
+            try:
+                _host_exchange = HostExchange()
+            except Exception:
+                _host_exchange = False
+    return _host_exchange or None
 
 
 def all_gather_partials(msm_xy, msm_inf, device=None):
     """Exchange the per-rank partial MSM results.  msm_xy: (5, 24) uint64, msm_inf: (5,) int32.
     Returns (world, 5, 24) uint64 and (world, 5) int32 arrays, identical on every rank."""
-    import torch
-    import torch.distributed as td
     rank, ws = world()
     if ws == 1:
         return msm_xy[None].copy(), msm_inf[None].copy()
     payload = np.zeros(MSM_SLOTS * SLOT_LIMBS + MSM_SLOTS, dtype=np.int64)
     payload[:MSM_SLOTS * SLOT_LIMBS] = msm_xy.reshape(-1).view(np.int64)
     payload[MSM_SLOTS * SLOT_LIMBS:] = msm_inf
-    t = torch.from_numpy(payload)
-    on_gpu = td.get_backend() == "nccl"
-    if on_gpu:
-        t = t.cuda(device) if device is not None else t.cuda()
-        TRANSFER["h2d"] += payload.nbytes
-        TRANSFER["d2h"] += ws * payload.nbytes
-    out = torch.empty(ws * t.numel(), dtype=torch.int64, device=t.device)
-    td.all_gather_into_tensor(out, t)
-    arr = out.cpu().numpy().reshape(ws, -1)
+    hx = host_exchange()
+    if hx is not None:
+        arr = hx.all_gather(payload.view(np.uint8)).view(np.int64).reshape(ws, -1)
+    else:
+        import torch
+        import torch.distributed as td
+        t = torch.from_numpy(payload)
+        if td.get_backend() == "nccl":
+            t = t.cuda(device) if device is not None else t.cuda()
+            TRANSFER["h2d"] += payload.nbytes
+            TRANSFER["d2h"] += ws * payload.nbytes
+        out = torch.empty(ws * t.numel(), dtype=torch.int64, device=t.device)
+        td.all_gather_into_tensor(out, t)
+        arr = out.cpu().numpy().reshape(ws, -1)
     xy = arr[:, :MSM_SLOTS * SLOT_LIMBS].copy().view(np.uint64).reshape(ws, MSM_SLOTS, SLOT_LIMBS)
     inf = arr[:, MSM_SLOTS * SLOT_LIMBS:].astype(np.int32)
     return xy, inf
@@ -126,6 +243,8 @@ def all_gather_array(arr, device=None):
     if ws == 1:
         return arr[None].copy()
     flat = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+    if _host_exchange and flat.size <= HostExchange.SLOT:     # small host payloads go through the node-local mailbox once it exists
+        return _host_exchange.all_gather(flat).view(arr.dtype).reshape((ws,) + arr.shape)
     t = torch.from_numpy(flat.copy())
     if td.get_backend() == "nccl":
         t = t.cuda(device) if device is not None else t.cuda()

@@ -345,9 +345,10 @@ class Groth16:
             nat.check(nat.lib.zkb_groth16_partial(self._pk_handle, self._r1cs_handle, wptr, int(on_dev), self.n_public,
                                                   nat.ptr(xy), nat.ptr(flags)))
             all_xy, all_inf = dist.all_gather_partials(xy, flags)
-            sxy, sinf = dist.add_partials(self.curve, all_xy, all_inf)
-            nat.check(nat.lib.zkb_groth16_assemble(self._pk_handle, nat.ptr(sxy), nat.ptr(sinf), nat.ptr(rr), nat.ptr(ss),
-                                                   nat.ptr(oa), nat.ptr(ob), nat.ptr(oc), inf))
+            all_xy = np.ascontiguousarray(all_xy)
+            all_inf = np.ascontiguousarray(all_inf, dtype=np.int32)
+            nat.check(nat.lib.zkb_groth16_assemble_partials(self._pk_handle, self.world, nat.ptr(all_xy), nat.ptr(all_inf), nat.ptr(rr),
+                                                            nat.ptr(ss), nat.ptr(oa), nat.ptr(ob), nat.ptr(oc), inf))
         ec = self.ec
         return Proof(ec.PointG1._from_flat(oa, inf[0]), ec.PointG2._from_flat(ob, inf[1]), ec.PointG1._from_flat(oc, inf[2]))
 

@@ -72,6 +72,7 @@ class DevicePlonk(Plonk):
             return [P._from_flat(xy[i], inf[i]) for i in range(k)]
         out[:, :limbs] = xy
         out[:, limbs] = [inf[i] for i in range(k)]
+        dist.host_exchange()                                 # (node-local mailbox for the few hundred bytes per rank)
         parts = dist.all_gather_array(out)                   # (world, k, limbs + 1)
         res = []
         ws = self.world
@@ -239,6 +240,7 @@ class DevicePlonk(Plonk):
         pk, p, cid = self.proving_key, self.order, self.cid
         n, N4 = pk.n, self.NQ
         omega = self.omega
+        t_entry = time.perf_counter()
         # the 11 blinding scalars of protocol.py:223-234, 280, 362 do not depend on the transcript: drawn up front, in the
         # reference's call order, with ONE collective when several ranks cooperate
         blinders = iter(self._draws(p - 1, 11))
@@ -247,6 +249,7 @@ class DevicePlonk(Plonk):
         selc, sigc = self.selector_coset, self.sigma_coset
         T = {}
         t0 = time.perf_counter()
+        T["draws"] = (t0 - t_entry) * 1e3
 
         def lap(name):
             nonlocal t0
@@ -389,6 +392,7 @@ class DevicePlonk(Plonk):
         assert rem == 0
         tau_w, tau_ww = self._commit_many([W_zeta, W_zeta_omega])
         lap("round5")
+        T["total"] = (time.perf_counter() - t_entry) * 1e3
         self.timings = T
         if self.keep_polys:
             self.last_polys = {"a": A, "b": B, "c": C, "z": Z, "t_lo": T_lo, "t_mid": T_mid, "t_hi": T_hi, "w_zeta": W_zeta,

@@ -3,10 +3,11 @@
 //   2. the carry-chained (mad.lo.cc / madc.hi.cc) rows the Montgomery multiplier is made of,
 //   3. Montgomery multiplications per second (Fq BN254, Fq BLS12-381), inline vs out-of-line, 1/2/4 independent streams,
 //   4. XYZZ mixed additions per second in isolation (no gather), inline vs out-of-line multiplier.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I../zksnake_b200/csrc -o build/ffbench ffbench.cu
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I. -I../zksnake_b200/csrc -o build/ffbench ffbench.cu
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#define ZKB_EXPERIMENTAL_WIDE   // pulls tools/ff_wide.cuh into ff.cuh (build with -I tools -I zksnake_b200/csrc)
 #include "ec.cuh"
 
 using namespace zkb;

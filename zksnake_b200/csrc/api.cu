@@ -981,8 +981,6 @@ __host__ __device__ F field_op(int op, const F& a, const F& b) {
   else if (op == 1) r = x + y;
   else if (op == 2) r = x - y;
   else if (op == 3) r = inv(x);
-  else if (op == 5) r = mont_sqr_split(x);        // experimental multipliers of ff_wide.cuh (used by no kernel)
-  else if (op == 6) r = mont_mul_split(x, y);
   else r = neg(x);
   return from_mont(r);
 }

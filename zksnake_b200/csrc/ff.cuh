@@ -265,7 +265,7 @@ ZKB_HD Fp<P> mont_mul(const Fp<P>& A, const Fp<P>& B) {
   return r;
 }
 
-// split multiplier (ff_wide.cuh, included at the end of this file): Karatsuba product + separate reduction
+// hook for the experimental split multiplier of tools/ff_wide.cuh (measured slower; no product kernel opts in)
 template <class P>
 ZKB_HD Fp<P> mont_mul_split(const Fp<P>& a, const Fp<P>& b);
 // a parameter struct opts in with `static constexpr bool SPLIT_MUL = true;`
@@ -296,8 +296,19 @@ ZKB_HD Fp<P> operator*(const Fp<P>& a, const Fp<P>& b) {
 #endif
 }
 
+// hook for the experimental dedicated squaring of tools/ff_wide.cuh (measured: no gain in the accumulation kernels, DESIGN.md
+// section 3); a parameter struct would opt in with `static constexpr bool SPLIT_SQR = true;` -- none does
 template <class P>
-ZKB_HD Fp<P> sqr(const Fp<P>& a) { return a * a; }
+ZKB_HD Fp<P> mont_sqr_split(const Fp<P>& a);
+template <class P, class = void>
+struct uses_split_sqr { static constexpr bool value = false; };
+template <class P>
+struct uses_split_sqr<P, decltype((void)P::SPLIT_SQR)> { static constexpr bool value = P::SPLIT_SQR; };
+template <class P>
+ZKB_HD Fp<P> sqr(const Fp<P>& a) {
+  if constexpr (uses_split_sqr<P>::value) return mont_sqr_split(a);
+  else return a * a;
+}
 
 // canonical <-> Montgomery
 template <class P>
@@ -420,4 +431,6 @@ typedef Fp2<FqBLS381> fq2_bls;
 
 }  // namespace zkb
 
+#ifdef ZKB_EXPERIMENTAL_WIDE   // tools/ffbench.cu only: the measured-and-rejected split multiplier / dedicated squaring (tools/ff_wide.cuh)
 #include "ff_wide.cuh"
+#endif

@@ -527,7 +527,7 @@ def main_own(args):
         msm_all_ms = sum(prof[k][0] for k in ("msm_sort", "msm_accum_g1", "msm_accum_g2", "msm_reduce")) / args.steps
         # executed additions of ALL FIVE MSMs (the G2 mixed addition is 8 Fq2 products + 2 Fq2 squarings = 28 Fq products)
         # over all MSM kernels of the proof, sorts and reductions included
-        ops_step = pts_per_launch * win_w * mul_ops * (4 * 10 + 28)
+        ops_step = pts_per_launch * win_w * mul_ops * (4 * 10 + 28)   # (28: the one-thread Karatsuba count, kept as the work unit)
         roofline["whole_msm_frac"] = ops_step / (msm_all_ms * 1e-3) / imad_wide.value if msm_all_ms else None
     roofline_g2 = None
     g2_ms, g2_cnt = prof["msm_accum_g2"]
@@ -535,11 +535,18 @@ def main_own(args):
         c2_c, c2_w = ctypes.c_uint32(), ctypes.c_uint32()
         nat.check(nat.lib.zkb_groth16_pk_msm_info(prover._pk_handle, 1, ctypes.byref(c2_c), ctypes.byref(c2_w)))
         per2 = g2_ms / g2_cnt
-        ex2 = pts_per_launch * int(c2_w.value) * 28 * mul_ops / (per2 * 1e-3) / 1e12
-        roofline_g2 = {"kernel": "msm_accumulate_kernel<G2>", "bound": "int32-pipe", "achieved": ex2, "peak": peak_t,
+        lanes, ctas = ctypes.c_int(), ctypes.c_int()
+        nat.check(nat.lib.zkb_msm_kernel_info(curve, 2, ctypes.byref(lanes), ctypes.byref(ctas)))
+        # one thread per point: 8 Fq2 products + 2 Fq2 squarings = 28 reduced Fq products (Karatsuba); two lanes per point
+        # (msm_pair.cuh): per lane 8 lazy dot products of 3L^2+L multiply-adds + 2 plain products
+        add_ops = 28 * mul_ops if lanes.value == 1 else 2 * (8 * (3 * L * L + L) + 2 * mul_ops)
+        ex2 = pts_per_launch * int(c2_w.value) * add_ops / (per2 * 1e-3) / 1e12
+        roofline_g2 = {"kernel": "msm_accumulate_kernel<G2>" if lanes.value == 1 else "msm_accumulate_pair_kernel<G2>",
+                       "bound": "int32-pipe", "achieved": ex2, "peak": peak_t,
                        "unit": "T 32x32->64 multiply-add lane-ops/s (IMAD.WIDE)", "frac": ex2 / peak_t,
-                       "window_bits": int(c2_c.value), "windows": int(c2_w.value),
-                       "executed_ops_per_point": int(c2_w.value) * 28 * mul_ops, "launch_ms": per2, "launches": g2_cnt,
+                       "window_bits": int(c2_c.value), "windows": int(c2_w.value), "lanes_per_point": lanes.value,
+                       "ctas_per_sm": ctas.value, "executed_ops_per_addition": add_ops,
+                       "executed_ops_per_point": int(c2_w.value) * add_ops, "launch_ms": per2, "launches": g2_cnt,
                        "share_of_step": g2_ms / args.steps / dev_ms}
     ntt_ms, ntt_cnt = prof["ntt"]
     roofline_ntt = None

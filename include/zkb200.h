@@ -82,6 +82,10 @@ int zkb_prof_read(int tag, float* total_ms, unsigned long long* count);
 /* Integer-pipe microbenchmark: sustained 32-bit multiply-add lane-operations per second of this GPU (the MSM roofline
  * denominator).  which: 0 = IMAD (mad.lo.u32), 1 = IMAD.WIDE (mad.wide.u32 counted as one op). */
 int zkb_imad_peak(int which, double* ops_per_s);
+/* Shape of the bucket-accumulation kernel compiled for (curve, group): lanes that share one point (1: one thread per point,
+ * msm_accumulate_kernel; 2: an Fp2 half per lane, msm_accumulate_pair_kernel) and resident CTAs per SM.  bench.py derives the
+ * executed multiply-add count of its roofline lines from it. */
+int zkb_msm_kernel_info(int curve, int group, int* lanes_per_point, int* ctas_per_sm);
 
 /* ---- raw memory ------------------------------------------------------------------------------------------- */
 int zkb_dev_alloc(size_t bytes, void** out);

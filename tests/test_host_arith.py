@@ -29,7 +29,8 @@ def test_field_ops_host(native, field):
     B[:8] = [0, p - 1, p - 1, 1, 5, (p + 1) // 2, 1, p - 2]
     a, b = _pack(A, nl), _pack(B, nl)
     ops = [lambda x, y: x * y % p, lambda x, y: (x + y) % p, lambda x, y: (x - y) % p,
-           lambda x, y: pow(x, p - 2, p), lambda x, y: (-x) % p]
+           lambda x, y: pow(x, p - 2, p), lambda x, y: (-x) % p,
+           lambda x, y: (x * y + (x + y) * (x - y)) % p, lambda x, y: x * y % p]   # 5, 6: mont_dot2 (lazy Fp2 half product)
     for op, fn in enumerate(ops):
         out = np.zeros_like(a)
         rc = native.lib.zkb_test_field_op_host(field, op, n, native.ptr(a), native.ptr(b), native.ptr(out))

@@ -43,6 +43,7 @@ def _load():
         "zkb_prof_enable": (c_int, [c_int]),
         "zkb_prof_read": (c_int, [c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_ulonglong)]),
         "zkb_imad_peak": (c_int, [c_int, ctypes.POINTER(ctypes.c_double)]),
+        "zkb_msm_kernel_info": (c_int, [c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
         "zkb_dev_alloc": (c_int, [c_sz, ctypes.POINTER(c_vp)]),
         "zkb_dev_free": (c_int, [c_vp]),
         "zkb_host_alloc": (c_int, [c_sz, ctypes.POINTER(c_vp)]),

@@ -476,6 +476,16 @@ int zkb_groth16_pk_msm_info(const zkb_groth16_pk* pk, int which, uint32_t* windo
   return ZKB_OK;
 }
 
+int zkb_msm_kernel_info(int curve, int group, int* lanes_per_point, int* ctas_per_sm) {
+  CHECK_CURVE(curve);
+  CHECK_GROUP(group);
+  int lanes = 1, ctas = 0;
+  msm_kernel_info(curve, group, &lanes, &ctas);
+  if (lanes_per_point) *lanes_per_point = lanes;
+  if (ctas_per_sm) *ctas_per_sm = ctas;
+  return ZKB_OK;
+}
+
 int zkb_groth16_pk_set_window_shard(zkb_groth16_pk* pk, uint32_t rank, uint32_t world) {
   if (!pk || world == 0 || rank >= world) return set_error(ZKB_ERR_ARG, "bad window shard");
   pk->wrank = rank;
@@ -489,25 +499,33 @@ static bool is_zero_pt(const uint64_t* p, size_t bytes) {
   return true;
 }
 
-// the five MSMs of protocol.py:133-155 over this key's slice; scalars are the full-length U, V, H in pk->work and d_priv
-static int groth16_msms(zkb_groth16_pk* pk, const void* d_priv) {
-  const int curve = pk->curve;
+// The five MSMs of protocol.py:133-155 as one batch: sort + accumulate back to back on the library stream, every reduction
+// (latency-bound) on a side stream as soon as its accumulation is done.  The G2 MSM goes first: its reduction chain is the
+// longest (an Fp2 addition is ~40 dependent Fq products) and so hides behind the four G1 accumulations.
+// Scalars: the full-length U, V, H in pk->work and d_priv.  Batch positions: B2 (G2, V), A (U), B1 (V), HZ (H), KW (priv).
+static MsmTicket g16_tk[5];
+static void groth16_jobs(const zkb_groth16_pk* pk, const void* d_priv, MsmJob job[5]) {
   const size_t bytes = pk->n * 32;
-  char* w = pk->work;
+  const char* w = pk->work;
   const char *d_u = w + 3 * bytes + pk->off * 32, *d_v = w + 4 * bytes + pk->off * 32, *d_h = w + 6 * bytes + pk->off * 32;
-  // The five MSMs as one batch: sort + accumulate back to back on the library stream, every reduction (latency-bound) on a
-  // side stream as soon as its accumulation is done.  The G2 MSM goes first: its reduction chain is the longest (an Fp2
-  // addition is ~40 dependent Fq products) and so hides behind the four G1 accumulations.
-  static MsmTicket tk[5];
-  static const int slot[5] = {2, 0, 1, 3, 4};   // batch position -> index in msm_xy (A, B1, B2, HZ, KW)
   auto mk = [&](int group, int which, const void* pts, const void* sc, size_t n) {
     const zkb_msm_table* t = pk->tab[which];
     if (t) return MsmJob{group, t->d_table, sc, n, t->c, t->n};
     return MsmJob{group, pts, sc, n, 0, 0};
   };
-  MsmJob job[5] = {mk(2, 1, pk->tau2, d_v, pk->len), mk(1, 0, pk->tau1, d_u, pk->len), mk(1, 0, pk->tau1, d_v, pk->len),
-                   mk(1, 2, pk->target1, d_h, pk->len),
-                   mk(1, 3, pk->kdelta1, (const char*)d_priv + pk->koff * 32, pk->klen)};
+  job[0] = mk(2, 1, pk->tau2, d_v, pk->len);
+  job[1] = mk(1, 0, pk->tau1, d_u, pk->len);
+  job[2] = mk(1, 0, pk->tau1, d_v, pk->len);
+  job[3] = mk(1, 2, pk->target1, d_h, pk->len);
+  job[4] = mk(1, 3, pk->kdelta1, (const char*)d_priv + pk->koff * 32, pk->klen);
+}
+
+static int groth16_msms(zkb_groth16_pk* pk, const void* d_priv) {
+  const int curve = pk->curve;
+  MsmTicket* tk = g16_tk;
+  static const int slot[5] = {2, 0, 1, 3, 4};   // batch position -> index in msm_xy (A, B1, B2, HZ, KW)
+  MsmJob job[5];
+  groth16_jobs(pk, d_priv, job);
   int rc;
   if ((rc = msm_enqueue_batch(curve, job, 5, pk->wrank, pk->wworld, tk))) return rc;
   // the five host recombinations (~0.1-0.2 ms of 64-bit Montgomery arithmetic each) run on five host threads; each waits
@@ -903,15 +921,67 @@ static int prove_witness_checks(zkb_groth16_pk* pk, zkb_r1cs* r1cs, size_t n_pub
 }
 
 // witness already canonical and resident in r1cs->w: SpMV x3 -> quotient -> the slice's five MSMs
+// Digit sorts under the transforms: the sort of an MSM needs its scalars and nothing else, and the scalars of three of the four
+// sorts of a proof exist long before the MSM batch starts -- the private witness from the beginning, U and V once the three
+// interpolations are done (four more transforms follow).  Those sorts are enqueued on a side stream at these points and run under
+// the SpMV / NTT pipeline (both sides are latency-bound and leave each other room); the batch then starts accumulating at once and
+// only H is sorted on the critical path.  One held arena epoch carries the transforms' and all MSM scratch.
+struct PresortCtx {
+  zkb_groth16_pk* pk;
+  MsmJob job[5];
+  cudaStream_t sort_st;
+  cudaEvent_t ev;
+  int rc;
+};
+static void presort_uv(void* arg) {   // called by groth16_h_dev when U and V are final on the library stream
+  PresortCtx* c = (PresortCtx*)arg;
+  if (cudaEventRecord(c->ev, S()) != cudaSuccess || cudaStreamWaitEvent(c->sort_st, c->ev, 0) != cudaSuccess) {
+    c->rc = set_error(ZKB_ERR_CUDA, "presort fork failed");
+    return;
+  }
+  c->rc = msm_presort(c->pk->curve, c->job[0], c->pk->wrank, c->pk->wworld, &g16_tk[0], c->sort_st);        // V (shared by B1, B2)
+  if (!c->rc) c->rc = msm_presort(c->pk->curve, c->job[1], c->pk->wrank, c->pk->wworld, &g16_tk[1], c->sort_st);   // U
+}
 static int partial_from_resident_witness(zkb_groth16_pk* pk, zkb_r1cs* r1cs, size_t n_public) {
   const size_t bytes = pk->n * 32;
   char* w = pk->work;
+  const void* d_priv = (char*)r1cs->w + n_public * 32;
   int rc;
-  if ((rc = r1cs_spmv3(r1cs, pk->n, w, w + bytes, w + 2 * bytes))) return rc;
+  static const bool presort_on = [] { const char* e = getenv("ZKB_PRESORT"); return !e || atoi(e) != 0; }();
+  if (!presort_on || pk->log_n < 12) {
+    if ((rc = r1cs_spmv3(r1cs, pk->n, w, w + bytes, w + 2 * bytes))) return rc;
+    if ((rc = groth16_h_dev(pk->curve, pk->log_n, w, w + bytes, w + 2 * bytes, w + 3 * bytes, w + 4 * bytes, w + 5 * bytes,
+                            w + 6 * bytes, 1)))
+      return rc;
+    return groth16_msms(pk, d_priv);
+  }
+  static cudaEvent_t ev = nullptr;
+  if (!ev) ZKB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  PresortCtx ctx;
+  ctx.pk = pk;
+  ctx.sort_st = (cudaStream_t)ctx_side_stream(7);
+  ctx.ev = ev;
+  ctx.rc = ZKB_OK;
+  if (!ctx.sort_st) return set_error(ZKB_ERR_CUDA, "cannot create the sort stream");
+  groth16_jobs(pk, d_priv, ctx.job);
+  size_t need_msm = 0;
+  if ((rc = msm_batch_need(pk->curve, ctx.job, 5, pk->wrank, pk->wworld, &need_msm))) return rc;
+  if ((rc = scratch_hold_begin(need_msm + 6 * ((size_t)32 << pk->log_n) + (1 << 20)))) return rc;
+  auto done = [&](int code) {
+    for (int i = 0; i < 5; i++) msm_presort_cancel(&g16_tk[i]);   // (no-op for tickets the batch consumed)
+    scratch_hold_end();
+    return code;
+  };
+  // the witness is reduced and resident (r1cs_load_witness, library stream): its sort can start here
+  if (cudaEventRecord(ev, S()) != cudaSuccess || cudaStreamWaitEvent(ctx.sort_st, ev, 0) != cudaSuccess)
+    return done(set_error(ZKB_ERR_CUDA, "presort fork failed"));
+  if ((rc = msm_presort(pk->curve, ctx.job[4], pk->wrank, pk->wworld, &g16_tk[4], ctx.sort_st))) return done(rc);
+  if ((rc = r1cs_spmv3(r1cs, pk->n, w, w + bytes, w + 2 * bytes))) return done(rc);
   if ((rc = groth16_h_dev(pk->curve, pk->log_n, w, w + bytes, w + 2 * bytes, w + 3 * bytes, w + 4 * bytes, w + 5 * bytes,
-                          w + 6 * bytes, 1)))
-    return rc;
-  return groth16_msms(pk, (char*)r1cs->w + n_public * 32);
+                          w + 6 * bytes, 1, presort_uv, &ctx)))
+    return done(rc);
+  if (ctx.rc) return done(ctx.rc);
+  return done(groth16_msms(pk, d_priv));
 }
 
 int zkb_groth16_partial(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const void* witness, int witness_on_device, size_t n_public,
@@ -981,6 +1051,15 @@ __host__ __device__ F field_op(int op, const F& a, const F& b) {
   else if (op == 1) r = x + y;
   else if (op == 2) r = x - y;
   else if (op == 3) r = inv(x);
+  else if (op == 5 || op == 6) {
+    // lazy dot product (the pair kernels' Fp2 multiplier): op 5 = x y + (x + y)(x - y); op 6 feeds the unreduced operand p
+    if constexpr ((F::Params::MOD(F::N - 1) >> 30) == 0) {
+      if (op == 5) r = mont_dot2(x, y, x + y, x - y);
+      else r = mont_dot2(x, y, neg_lazy(F::zero()), neg_lazy(y));   // x y + p (p - y) = x y  (mod p)
+    } else {
+      r = op == 5 ? x * y + (x + y) * (x - y) : x * y;
+    }
+  }
   else r = neg(x);
   return from_mont(r);
 }

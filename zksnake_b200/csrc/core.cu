@@ -99,7 +99,25 @@ static void prof_clear() {
   g_prof.clear();
 }
 
+// A HELD arena (scratch_hold_begin .. scratch_hold_end) is one allocation epoch shared by several stages that would each start
+// their own: their scratch_reserve only checks that the request still fits behind what has been taken, their scratch_reset does
+// nothing.  Groth16 prove uses it so that digit sorts enqueued on a side stream keep their buffers while the transforms and the
+// later MSM stages take theirs.
+static bool g_arena_held = false;
+int scratch_hold_begin(size_t total) {
+  g_arena_held = false;
+  int rc = scratch_reserve(total);
+  if (rc) return rc;
+  scratch_reset();
+  g_arena_held = true;
+  return ZKB_OK;
+}
+void scratch_hold_end() { g_arena_held = false; }
 int scratch_reserve(size_t bytes) {
+  if (g_arena_held) {
+    if (((g_ctx.arena_off + 255) & ~(size_t)255) + bytes > g_ctx.arena_cap) return set_error(ZKB_ERR_CUDA, "held scratch arena too small");
+    return ZKB_OK;
+  }
   if (bytes <= g_ctx.arena_cap) return ZKB_OK;
   ZKB_CUDA(cudaStreamSynchronize(g_ctx.stream));
   if (g_ctx.arena) ZKB_CUDA(cudaFree(g_ctx.arena));
@@ -111,7 +129,9 @@ int scratch_reserve(size_t bytes) {
   g_ctx.arena_off = 0;
   return ZKB_OK;
 }
-void scratch_reset() { g_ctx.arena_off = 0; }
+void scratch_reset() {
+  if (!g_arena_held) g_ctx.arena_off = 0;
+}
 void* scratch_take(size_t bytes) {
   size_t off = (g_ctx.arena_off + 255) & ~(size_t)255;
   if (off + bytes > g_ctx.arena_cap) return nullptr;

@@ -265,6 +265,149 @@ ZKB_HD Fp<P> mont_mul(const Fp<P>& A, const Fp<P>& B) {
   return r;
 }
 
+// (a*u + b*v) * R^-1 mod p with ONE interleaved reduction: the "lazy" half of an Fp2 product (c0 = a0 b0 + (p - a1) b1,
+// c1 = a0 b1 + a1 b0).  3 N^2 + N wide multiply-adds instead of 2 (2 N^2 + N) for two products, and no separate field
+// addition.  Same even/odd column accumulators as mont_mul with a third product chain per row.
+// Operands may be anything <= p (p itself is allowed, so the caller may negate without a zero test).  Needs p < 2^(32N-2):
+// then every running sum T + a u_i + b v_i + m p < 3p (2^32 + 2) fits the two N-limb accumulators (no carry leaves the top
+// limb), and the result (a u + b v + M p) / R < p (2p / R + 1) < 2p is reduced by one conditional subtraction.
+// (the limbs u_i, v_i are asked for row by row -- rows(i, ui, vi) -- so that a caller which has to fetch them from another lane
+// keeps only one limb of each alive; mont_dot2 below is the plain-operand form)
+template <class P, class Rows>
+ZKB_HD Fp<P> mont_dot2_rows(const Fp<P>& A, const Fp<P>& B, Rows rows) {
+  constexpr int N = P::N;
+  static_assert(N % 2 == 0, "even limb count required");
+  static_assert((P::MOD(N - 1) >> 30) == 0, "mont_dot2 needs two spare bits in the top limb");
+  const uint32_t* a = A.v;
+  const uint32_t* b = B.v;
+  uint32_t e[N], o[N];
+  // ---- row 0: T = a * u[0] + b * v[0]
+  {
+    uint32_t ui, vi;
+    rows(0, ui, vi);
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      e[j] = mul_lo(a[j], ui);
+      e[j + 1] = mul_hi(a[j], ui);
+      o[j] = mul_lo(a[j + 1], ui);
+      o[j + 1] = mul_hi(a[j + 1], ui);
+    }
+    e[0] = mad_lo_cc(b[0], vi, e[0]);
+    e[1] = madc_hi_cc(b[0], vi, e[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      e[j] = madc_lo_cc(b[j], vi, e[j]);
+      e[j + 1] = madc_hi_cc(b[j], vi, e[j + 1]);
+    }
+    o[N - 1] = addc(o[N - 1], 0u);
+    o[0] = mad_lo_cc(b[1], vi, o[0]);
+    o[1] = madc_hi_cc(b[1], vi, o[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      o[j] = madc_lo_cc(b[j + 1], vi, o[j]);
+      o[j + 1] = madc_hi_cc(b[j + 1], vi, o[j + 1]);
+    }
+    uint32_t m = mul_lo(e[0], P::INV);
+    e[0] = mad_lo_cc(P::MOD(0), m, e[0]);
+    e[1] = madc_hi_cc(P::MOD(0), m, e[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      e[j] = madc_lo_cc(P::MOD(j), m, e[j]);
+      e[j + 1] = madc_hi_cc(P::MOD(j), m, e[j + 1]);
+    }
+    o[N - 1] = addc(o[N - 1], 0u);
+    o[0] = mad_lo_cc(P::MOD(1), m, o[0]);
+    o[1] = madc_hi_cc(P::MOD(1), m, o[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      o[j] = madc_lo_cc(P::MOD(j + 1), m, o[j]);
+      o[j + 1] = madc_hi_cc(P::MOD(j + 1), m, o[j + 1]);
+    }
+  }
+  // ---- rows 1..N-1
+#pragma unroll
+  for (int i = 1; i < N; i++) {
+    uint32_t ui, vi;
+    rows(i, ui, vi);
+    uint32_t E[N], O[N];
+    // T / 2^32 (see mont_mul), then += a * u[i]
+    E[0] = add_cc(o[0], e[1]);
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      O[j] = madc_lo_cc(a[j + 1], ui, (j + 2 < N) ? e[j + 2] : 0u);
+      O[j + 1] = madc_hi_cc(a[j + 1], ui, (j + 3 < N) ? e[j + 3] : 0u);
+    }
+    E[0] = mad_lo_cc(a[0], ui, E[0]);
+    E[1] = madc_hi_cc(a[0], ui, o[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      E[j] = madc_lo_cc(a[j], ui, o[j]);
+      E[j + 1] = madc_hi_cc(a[j], ui, o[j + 1]);
+    }
+    O[N - 1] = addc(O[N - 1], 0u);
+    // += b * v[i]
+    E[0] = mad_lo_cc(b[0], vi, E[0]);
+    E[1] = madc_hi_cc(b[0], vi, E[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      E[j] = madc_lo_cc(b[j], vi, E[j]);
+      E[j + 1] = madc_hi_cc(b[j], vi, E[j + 1]);
+    }
+    O[N - 1] = addc(O[N - 1], 0u);
+    O[0] = mad_lo_cc(b[1], vi, O[0]);
+    O[1] = madc_hi_cc(b[1], vi, O[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      O[j] = madc_lo_cc(b[j + 1], vi, O[j]);
+      O[j + 1] = madc_hi_cc(b[j + 1], vi, O[j + 1]);
+    }
+    // reduction row
+    uint32_t m = mul_lo(E[0], P::INV);
+    E[0] = mad_lo_cc(P::MOD(0), m, E[0]);
+    E[1] = madc_hi_cc(P::MOD(0), m, E[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      E[j] = madc_lo_cc(P::MOD(j), m, E[j]);
+      E[j + 1] = madc_hi_cc(P::MOD(j), m, E[j + 1]);
+    }
+    O[N - 1] = addc(O[N - 1], 0u);
+    O[0] = mad_lo_cc(P::MOD(1), m, O[0]);
+    O[1] = madc_hi_cc(P::MOD(1), m, O[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      O[j] = madc_lo_cc(P::MOD(j + 1), m, O[j]);
+      O[j + 1] = madc_hi_cc(P::MOD(j + 1), m, O[j + 1]);
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      e[j] = E[j];
+      o[j] = O[j];
+    }
+  }
+  Fp<P> r;
+  r.v[0] = add_cc(o[0], e[1]);
+#pragma unroll
+  for (int j = 1; j < N - 1; j++) r.v[j] = addc_cc(o[j], e[j + 1]);
+  r.v[N - 1] = addc(o[N - 1], 0u);
+  final_sub<P>(r.v);
+  return r;
+}
+template <class P>
+ZKB_HD Fp<P> mont_dot2(const Fp<P>& A, const Fp<P>& U, const Fp<P>& B, const Fp<P>& V) {
+  return mont_dot2_rows<P>(A, B, [&](int i, uint32_t& ui, uint32_t& vi) { ui = U.v[i]; vi = V.v[i]; });
+}
+// p - a without reducing (a <= p; a = 0 gives p): the negated operand of mont_dot2
+template <class P>
+ZKB_HD Fp<P> neg_lazy(const Fp<P>& a) {
+  constexpr int N = P::N;
+  Fp<P> r;
+  r.v[0] = sub_cc(P::MOD(0), a.v[0]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.v[i] = subc_cc(P::MOD(i), a.v[i]);
+  r.v[N - 1] = subc(P::MOD(N - 1), a.v[N - 1]);
+  return r;
+}
+
 // hook for the experimental split multiplier of tools/ff_wide.cuh (measured slower; no product kernel opts in)
 template <class P>
 ZKB_HD Fp<P> mont_mul_split(const Fp<P>& a, const Fp<P>& b);

@@ -5,6 +5,7 @@
 #include <string.h>
 #include <vector>
 #include "msm.cuh"
+#include "msm_pair.cuh"
 #include "zkb_internal.h"
 
 namespace zkb {
@@ -15,11 +16,39 @@ static inline cudaStream_t MS() { return (cudaStream_t)ctx_stream(); }
 
 // the inline-multiplier twin of a stored field (identical layout; only the device code generation differs)
 template <class P> struct InlineMul : P { static constexpr bool NOINLINE_MUL = false; };
-template <class F> struct AccumField { typedef F type; static constexpr int MINB = 2; };
+// PAIR: two lanes per point (msm_pair.cuh) -- the accumulation grid then runs 148 x MINB x 64 runs at a time
+template <class F> struct AccumField { typedef F type; static constexpr int MINB = 2; static constexpr bool PAIR = false; };
 // G1: the fully inlined XYZZ addition is ~9-15 % faster than calling the multiplier out of line (tools/ffbench.cu);
 // G2 (Fp2 Karatsuba, ~30 multiplier bodies per addition) is faster out of line.
-template <> struct AccumField<Fp<FqBN254>> { typedef Fp<InlineMul<FqBN254>> type; static constexpr int MINB = 4; };
-template <> struct AccumField<Fp<FqBLS381>> { typedef Fp<InlineMul<FqBLS381>> type; static constexpr int MINB = 3; };
+template <> struct AccumField<Fp<FqBN254>> { typedef Fp<InlineMul<FqBN254>> type; static constexpr int MINB = 4; static constexpr bool PAIR = false; };
+template <> struct AccumField<Fp<FqBLS381>> { typedef Fp<InlineMul<FqBLS381>> type; static constexpr int MINB = 3; static constexpr bool PAIR = false; };
+// G2: lane pairs over the base field (PairBase = the multiplier flavour the pair kernel is generated with)
+#ifndef ZKB_G2_PAIR
+#define ZKB_G2_PAIR 1
+#endif
+#ifndef ZKB_G2_PAIR_BASE_BN
+#define ZKB_G2_PAIR_BASE_BN FqBN254
+#endif
+#ifndef ZKB_G2_PAIR_BASE_BLS
+#define ZKB_G2_PAIR_BASE_BLS FqBLS381
+#endif
+#ifndef ZKB_G2_PAIR_MINB_BN
+#define ZKB_G2_PAIR_MINB_BN 4
+#endif
+#ifndef ZKB_G2_PAIR_MINB_BLS
+#define ZKB_G2_PAIR_MINB_BLS 3
+#endif
+#if ZKB_G2_PAIR
+template <> struct AccumField<Fp2<FqBN254>> {
+  typedef Fp2<FqBN254> type; typedef ZKB_G2_PAIR_BASE_BN PairBase;
+  static constexpr int MINB = ZKB_G2_PAIR_MINB_BN; static constexpr bool PAIR = true;
+};
+template <> struct AccumField<Fp2<FqBLS381>> {
+  typedef Fp2<FqBLS381> type; typedef ZKB_G2_PAIR_BASE_BLS PairBase;
+  static constexpr int MINB = ZKB_G2_PAIR_MINB_BLS; static constexpr bool PAIR = true;
+};
+#endif
+template <class F> constexpr uint32_t accum_run_threads() { return 148u * AccumField<F>::MINB * (AccumField<F>::PAIR ? 64u : 128u); }
 
 // wrank/wworld: this launch handles the windows [W*wrank/wworld, W*(wrank+1)/wworld) of every scalar (multi-GPU window
 // sharding); 0/1 = all windows.
@@ -150,7 +179,7 @@ struct MsmGeom {
 };
 template <class X>
 inline int msm_geometry(size_t n, uint32_t scalar_bits, uint32_t wrank, uint32_t wworld, uint32_t table_c, size_t table_n,
-                        MsmGeom<X>* g) {
+                        uint32_t run_threads, MsmGeom<X>* g) {
   memset(g, 0, sizeof(*g));
   if (wworld == 0 || wrank >= wworld) return set_error(ZKB_ERR_ARG, "msm: bad window shard");
   if (n >= ((size_t)1 << 31)) return set_error(ZKB_ERR_ARG, "msm: more than 2^31-1 points");
@@ -159,7 +188,7 @@ inline int msm_geometry(size_t n, uint32_t scalar_bits, uint32_t wrank, uint32_t
     return ZKB_OK;
   }
   if (table_n && n > table_n) return set_error(ZKB_ERR_ARG, "msm: more scalars than table points");
-  g->pl = msm_make_plan(n, scalar_bits, wrank, wworld, table_c, table_n, 148u * (sizeof(X) >= 256 ? 2u : (sizeof(X) > 128 ? 3u : 4u)) * 128u);
+  g->pl = msm_make_plan(n, scalar_bits, wrank, wworld, table_c, table_n, run_threads);
   const MsmPlan& pl = g->pl;
   if (pl.nwin == 0) {   // more ranks than windows
     g->skip = true;
@@ -209,16 +238,18 @@ template <class F, int SCALAR_BITS>
 int msm_need_t(size_t n, uint32_t wrank, uint32_t wworld, uint32_t table_c, size_t table_n, size_t* need) {
   typedef XYZZ<typename AccumField<F>::type> X;
   MsmGeom<X> g;
-  int rc = msm_geometry<X>(n, SCALAR_BITS, wrank, wworld, table_c, table_n, &g);
+  int rc = msm_geometry<X>(n, SCALAR_BITS, wrank, wworld, table_c, table_n, accum_run_threads<F>(), &g);
   *need = g.need + 4096;
   return rc;
 }
 
-// Phase 1 on the library stream: digit sort and bucket accumulation.  Takes its scratch from the arena WITHOUT resetting it
-// (the caller reserved and reset once for the whole batch), so several MSMs can be between phase 1 and phase 2 at once.
+// Phase 1 = digit sort (msm_sort_t, on stream `st`) + bucket accumulation (msm_accum_t, on the library stream).  Both take their
+// scratch from the arena WITHOUT resetting it (the caller reserved and reset once for the whole batch), so several MSMs can be
+// between their stages at once; a batch may run the sorts of its later jobs on a side stream under an earlier accumulation
+// (msm_common.cu:msm_enqueue_batch).
 template <class F, int SCALAR_BITS>
-int msm_phase1_t(int curve, int group, const void* d_points, const void* d_scalars, size_t n, uint32_t wrank, uint32_t wworld,
-                 uint32_t table_c, size_t table_n, const MsmTicket* share, MsmTicket* tk) {
+int msm_sort_t(int curve, int group, const void* d_scalars, size_t n, uint32_t wrank, uint32_t wworld,
+               uint32_t table_c, size_t table_n, const MsmTicket* share, MsmTicket* tk, cudaStream_t st) {
   typedef typename AccumField<F>::type FA;   // G1: inline-multiplier twin (same layout); G2: F itself
   typedef XYZZ<FA> X;
   static_assert(sizeof(FA) == sizeof(F), "inline twin must share the layout");
@@ -227,7 +258,7 @@ int msm_phase1_t(int curve, int group, const void* d_points, const void* d_scala
   tk->group = group;
   MsmDev<X>* d = reinterpret_cast<MsmDev<X>*>(tk->dev);
   int rc;
-  if ((rc = msm_geometry<X>(n, SCALAR_BITS, wrank, wworld, table_c, table_n, &d->g))) return rc;
+  if ((rc = msm_geometry<X>(n, SCALAR_BITS, wrank, wworld, table_c, table_n, accum_run_threads<F>(), &d->g))) return rc;
   tk->empty = d->g.skip;
   if (d->g.skip) return ZKB_OK;
   const MsmGeom<X>& g = d->g;
@@ -272,9 +303,9 @@ int msm_phase1_t(int curve, int group, const void* d_points, const void* d_scala
       !d->hot_list || !d->vhot_list || !d->counters || !d->pieces || !d->lev_t || !d->lev_r || !d->side || !d->sums)
     return set_error(ZKB_ERR_CUDA, "msm: scratch exhausted");
 
-  cudaStream_t st = MS();
+  const bool timed = st == MS();   // the per-family timers bracket the library stream only
   const uint32_t* sc = (const uint32_t*)d_scalars;
-  prof_begin(PROF_MSM_SORT);
+  if (timed) prof_begin(PROF_MSM_SORT);
   if (sh) {
     // own copies of what the folds rewrite (np_eff) and of the counters (hot counts kept, work counter cleared)
     ZKB_CUDA(cudaMemcpyAsync(d->np_eff, npieces, (nb + 1) * 4, cudaMemcpyDeviceToDevice, st));
@@ -324,18 +355,62 @@ int msm_phase1_t(int curve, int group, const void* d_points, const void* d_scala
     scan_u32(npieces, d->pstart, nb, part, st);
     count_launch(10);
   }
-  prof_end(PROF_MSM_SORT);
+  if (timed) prof_end(PROF_MSM_SORT);
   tk->sorted = MsmSorted{d_scalars, n, table_c, table_n, wrank, wworld, nb, pl.krun, start, d->pstart, npieces, refs, run_bucket,
                          d->hot_list, d->vhot_list, d->counters};
-  const int acc_tag = group == 2 ? PROF_MSM_ACCUM_G2 : PROF_MSM_ACCUM_G1;
+  ZKB_CUDA(cudaGetLastError());
+  return ZKB_OK;
+}
+
+// Bucket accumulation of a sorted job on the library stream.  leave_room (experiment, off unless ZKB_G2_ROOM_CTAS is set): run
+// the pair kernel with fewer CTAs per SM than fit, pinned with dynamic shared memory, so that sort kernels of later jobs find room
+// on every SM while it runs.  Measured on 2^20 BN254: the accumulation goes 7.25 -> 7.84 ms at 3 CTAs and the proof gains
+// nothing (profiles/R2p_*), so the default leaves the grid alone.
+template <class F, int SCALAR_BITS>
+int msm_accum_t(const void* d_points, MsmTicket* tk, bool leave_room) {
+  typedef typename AccumField<F>::type FA;
+  typedef XYZZ<FA> X;
+  if (tk->empty) return ZKB_OK;
+  MsmDev<X>* d = reinterpret_cast<MsmDev<X>*>(tk->dev);
+  const MsmPlan& pl = d->g.pl;
+  const MsmSorted& so = tk->sorted;
+  cudaStream_t st = MS();
+  const int acc_tag = tk->group == 2 ? PROF_MSM_ACCUM_G2 : PROF_MSM_ACCUM_G1;
   prof_begin(acc_tag);
   constexpr int MINB = AccumField<F>::MINB;
-  msm_accumulate_kernel<FA, MINB><<<148 * MINB, 128, 0, st>>>(pl, (const Affine<FA>*)d_points, refs, start, d->pstart, run_bucket,
-                                                              d->pieces, d->counters + 1);
+  if constexpr (AccumField<F>::PAIR) {
+    typedef typename AccumField<F>::PairBase PB;
+    int ctas = MINB;
+    size_t dyn = 0;
+    if (leave_room && MINB > 2) {
+      static const int room_ctas = [] { const char* e = getenv("ZKB_G2_ROOM_CTAS"); return e ? atoi(e) : 0; }();
+      if (room_ctas > 0 && room_ctas < MINB) {
+        ctas = room_ctas;
+        dyn = (size_t)(200 * 1024 / ctas) & ~(size_t)1023;   // ctas CTAs fill ~200 KiB of the SM's 227: no further one fits, a sort CTA does
+        static bool attr = false;
+        if (!attr) {
+          ZKB_CUDA(cudaFuncSetAttribute(msm_accumulate_pair_kernel<PB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          attr = true;
+        }
+      }
+    }
+    msm_accumulate_pair_kernel<PB, MINB><<<148 * ctas, 128, dyn, st>>>(pl, (const Fp<PB>*)d_points, so.refs, so.start, so.pstart,
+                                                                       so.run_bucket, (Fp<PB>*)d->pieces, d->counters + 1);
+  } else {
+    msm_accumulate_kernel<FA, MINB><<<148 * MINB, 128, 0, st>>>(pl, (const Affine<FA>*)d_points, so.refs, so.start, so.pstart,
+                                                                so.run_bucket, d->pieces, d->counters + 1);
+  }
   prof_end(acc_tag);
   count_launch(1);
   ZKB_CUDA(cudaGetLastError());
   return ZKB_OK;
+}
+template <class F, int SCALAR_BITS>
+int msm_phase1_t(int curve, int group, const void* d_points, const void* d_scalars, size_t n, uint32_t wrank, uint32_t wworld,
+                 uint32_t table_c, size_t table_n, const MsmTicket* share, MsmTicket* tk) {
+  int rc = msm_sort_t<F, SCALAR_BITS>(curve, group, d_scalars, n, wrank, wworld, table_c, table_n, share, tk, MS());
+  if (rc) return rc;
+  return msm_accum_t<F, SCALAR_BITS>(d_points, tk, false);
 }
 
 // Phase 2 on stream `st` (the library stream, or a side stream so that the latency-bound reductions of several MSMs overlap):
@@ -456,6 +531,11 @@ int batch_mul_run(const void* d_bases, int single_base, const void* d_scalars, s
                           const MsmTicket* share, MsmTicket* tk) {                                                       \
     return msm_phase1_t<FIELD, BITS>(CURVE, GROUP, p, s, n, wr, ww, tc, tn, share, tk);                                 \
   }                                                                                                                      \
+  int msm_sort_##SUFFIX(const void* s, size_t n, uint32_t wr, uint32_t ww, uint32_t tc, size_t tn, const MsmTicket* share,  \
+                        MsmTicket* tk, void* stream) {                                                                   \
+    return msm_sort_t<FIELD, BITS>(CURVE, GROUP, s, n, wr, ww, tc, tn, share, tk, (cudaStream_t)stream);                \
+  }                                                                                                                      \
+  int msm_accum_##SUFFIX(const void* p, MsmTicket* tk, int leave_room) { return msm_accum_t<FIELD, BITS>(p, tk, leave_room != 0); } \
   int msm_phase2_##SUFFIX(MsmTicket* tk, void* stream) { return msm_phase2_t<FIELD, BITS>(tk, (cudaStream_t)stream); }  \
   int msm_table_##SUFFIX(const void* pts, size_t n, uint32_t world, uint32_t* c, uint32_t* W, void* table) {            \
     return msm_table_run<FIELD, BITS>(pts, n, world, c, W, table);                                                      \

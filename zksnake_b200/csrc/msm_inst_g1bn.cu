@@ -11,4 +11,18 @@ void msm_plan_info(size_t n, uint32_t scalar_bits, uint32_t wworld, uint32_t* c,
   *c = pl.c;
   *W = pl.nwin_total;
 }
+template <class F>
+static void kernel_info_t(int* lanes, int* ctas) {
+  *lanes = AccumField<F>::PAIR ? 2 : 1;
+  *ctas = AccumField<F>::MINB;
+}
+void msm_kernel_info(int curve, int group, int* lanes_per_point, int* ctas_per_sm) {
+  if (curve == ZKB_BN254) {
+    if (group == 2) kernel_info_t<fq2_bn>(lanes_per_point, ctas_per_sm);
+    else kernel_info_t<fq_bn>(lanes_per_point, ctas_per_sm);
+  } else {
+    if (group == 2) kernel_info_t<fq2_bls>(lanes_per_point, ctas_per_sm);
+    else kernel_info_t<fq_bls>(lanes_per_point, ctas_per_sm);
+  }
+}
 }  // namespace zkb

@@ -421,7 +421,7 @@ int fr_powers_dev(int curve, const uint64_t* base, const uint64_t* scale, size_t
 // ------------------------------------------------------------------------------------------------------
 template <class F>
 static int groth16_h_t(uint32_t log_n, const void* d_a, const void* d_b, const void* d_c, void* d_u, void* d_v, void* d_w,
-                       void* d_h, int check) {
+                       void* d_h, int check, void (*after_interp)(void*), void* arg) {
   typedef typename F::Params P;
   if (log_n > (uint32_t)P::TWO_ADICITY || log_n > 30) return set_error(ZKB_ERR_DOMAIN, "Domain size is too large");
   size_t n = (size_t)1 << log_n;
@@ -454,12 +454,14 @@ static int groth16_h_t(uint32_t log_n, const void* d_a, const void* d_b, const v
     // the three interpolations as ONE batched transform per pass, then the three coset evaluations likewise: 9 launches instead
     // of 18, and three times the columns per launch to fill the waves (W goes through g^j / R, see vec_op_kernel)
     if ((rc = ntt_exec_warp<F>((const F*)d_a, n, U, log_n, 3, n, inv_t, nullptr, nullptr, &d->n_inv, tmp))) return rc;
+    if (after_interp) after_interp(arg);
     const PowTable<F>* pres[3] = {&gpre, &gpre, &gpre_r};
     if ((rc = ntt_exec_warp<F>(U, n, ea, log_n, 3, n, fwd, pres, nullptr, nullptr, tmp))) return rc;
   } else {
     if ((rc = ntt_exec<F>((const F*)d_a, n, U, log_n, inv_t, nullptr, nullptr, &d->n_inv, tmp))) return rc;
     if ((rc = ntt_exec<F>((const F*)d_b, n, V, log_n, inv_t, nullptr, nullptr, &d->n_inv, tmp))) return rc;
     if ((rc = ntt_exec<F>((const F*)d_c, n, W, log_n, inv_t, nullptr, nullptr, &d->n_inv, tmp))) return rc;
+    if (after_interp) after_interp(arg);
     if ((rc = ntt_exec<F>(U, n, ea, log_n, fwd, &gpre, nullptr, nullptr, tmp))) return rc;
     if ((rc = ntt_exec<F>(V, n, eb, log_n, fwd, &gpre, nullptr, nullptr, tmp))) return rc;
     if ((rc = ntt_exec<F>(W, n, ec, log_n, fwd, &gpre_r, nullptr, nullptr, tmp))) return rc;   // W(g w^i) / R
@@ -475,9 +477,9 @@ static int groth16_h_t(uint32_t log_n, const void* d_a, const void* d_b, const v
   return ZKB_OK;
 }
 int groth16_h_dev(int curve, uint32_t log_n, const void* d_a, const void* d_b, const void* d_c, void* d_u, void* d_v,
-                  void* d_w, void* d_h, int check) {
-  if (curve == ZKB_BN254) return groth16_h_t<fr_bn>(log_n, d_a, d_b, d_c, d_u, d_v, d_w, d_h, check);
-  if (curve == ZKB_BLS12_381) return groth16_h_t<fr_bls>(log_n, d_a, d_b, d_c, d_u, d_v, d_w, d_h, check);
+                  void* d_w, void* d_h, int check, void (*after_interp)(void*), void* arg) {
+  if (curve == ZKB_BN254) return groth16_h_t<fr_bn>(log_n, d_a, d_b, d_c, d_u, d_v, d_w, d_h, check, after_interp, arg);
+  if (curve == ZKB_BLS12_381) return groth16_h_t<fr_bls>(log_n, d_a, d_b, d_c, d_u, d_v, d_w, d_h, check, after_interp, arg);
   return set_error(ZKB_ERR_ARG, "unknown curve id");
 }
 

@@ -50,6 +50,9 @@ bool ctx_ready();
 int scratch_reserve(size_t bytes);  // make sure the arena holds at least `bytes` (may reallocate; sync)
 void scratch_reset();
 void* scratch_take(size_t bytes);   // 256-byte aligned bump allocation; nullptr when exhausted
+// one epoch shared by several stages: reserve `total`, reset once, then the stages' own reserve / reset calls only check / do nothing
+int scratch_hold_begin(size_t total);
+void scratch_hold_end();
 void count_launch(int n = 1);
 void count_h2d(size_t bytes);   // host<->device traffic issued by the library (zkb_transfer_count)
 void count_d2h(size_t bytes);
@@ -72,8 +75,10 @@ int fr_reduce_dev(int curve, size_t n, void* v);
 int fr_powers_dev(int curve, const uint64_t* base, const uint64_t* scale, size_t n, void* d_out);
 // H = (U*V - W)/Z from the evaluation vectors a,b,c (canonical, n = 2^log_n each, device).  Writes U,V (n coeffs each, the
 // MSM scalars) and H (n coeffs, top one zero).  d_w is scratch for W.  Returns ZKB_ERR_NOT_DIVISIBLE when a.b != c.
+// after_interp(arg), when given, is called once the three interpolations are enqueued: U and V (the MSM scalars) are final on the
+// library stream from there on, while four more transforms follow -- the caller forks the digit sorts of the U / V MSMs there.
 int groth16_h_dev(int curve, uint32_t log_n, const void* d_a, const void* d_b, const void* d_c, void* d_u, void* d_v,
-                  void* d_w, void* d_h, int check);
+                  void* d_w, void* d_h, int check, void (*after_interp)(void*) = nullptr, void* arg = nullptr);
 size_t ntt_scratch_bytes(uint32_t log_n);
 // long_rows: the n_long rows with more than SPMV_LONG_ROW non-zeros (device array, listed when the matrix is created); they are
 // summed by whole CTAs into long_partial (n_long * 64 elements) instead of by one thread each
@@ -83,6 +88,7 @@ int spmv_dev(int curve, size_t n_out, size_t n_rows, const void* row_ptr, const 
 
 // window size / window count the plain (table-less) MSM heuristic picks for n points (msm_common.cu)
 void msm_plan_info(size_t n, uint32_t scalar_bits, uint32_t wworld, uint32_t* c, uint32_t* W);
+void msm_kernel_info(int curve, int group, int* lanes_per_point, int* ctas_per_sm);
 
 // ---- point codec (codec.cu) ----
 size_t compressed_bytes(int curve, int group);
@@ -113,6 +119,8 @@ struct MsmTicket {
   unsigned char* host = nullptr;   // pinned
   size_t host_cap = 0;
   void* event = nullptr;           // cudaEvent_t
+  bool presorted = false;          // msm_presort ran this ticket's digit sort on a side stream; sort_event marks its end
+  void* sort_event = nullptr;      // cudaEvent_t
   alignas(16) unsigned char dev[512];   // MsmDev<X>: plan + device pointers between phase 1 and phase 2
 };
 int ticket_reserve(MsmTicket* tk, size_t bytes);
@@ -126,6 +134,13 @@ struct MsmJob {
   uint32_t table_c;       // window size the table was built for (0 = plain points)
   size_t table_n;         // points per window of the table
 };
+// Scratch bytes a batch of these jobs takes from the arena (what msm_enqueue_batch reserves).
+int msm_batch_need(int curve, const MsmJob* jobs, int njobs, uint32_t wrank, uint32_t wworld, size_t* total);
+// The digit sort of one job of a LATER msm_enqueue_batch call, enqueued on `stream` now (its scalars must be complete there); the
+// arena must be held (scratch_hold_begin) from here to that call.  The batch then only waits for the ticket's sort_event.
+int msm_presort(int curve, const MsmJob& job, uint32_t wrank, uint32_t wworld, MsmTicket* tk, void* stream);
+// Orders the library stream behind a presorted ticket's sort and clears the flag (error paths: the sort may still be running).
+void msm_presort_cancel(MsmTicket* tk);
 // One MSM, both phases on the library stream.
 int msm_enqueue(int curve, const MsmJob& job, uint32_t wrank, uint32_t wworld, MsmTicket* tk);
 // fixed-base table (see msm_host.cuh:msm_table_run)

@@ -268,8 +268,30 @@ def test_msm_g1_discrete_log_full_size(gpu):
 
 @pytest.mark.parametrize("curve", CURVES)
 def test_msm_g2_discrete_log(gpu, curve):
-    for n, kind in ((1 << 12, "uniform"), (1 << 14, "bits"), (1 << 16, "uniform")):
+    # ("same": one hot bucket per window -- whole runs of the two-lanes-per-point kernel inside one bucket, then the folds;
+    #  "pow2": the chain circuit's witness; 1000: ragged last run, lane pairs without a run)
+    for n, kind in ((1 << 12, "uniform"), (1 << 14, "bits"), (1 << 16, "uniform"), (1 << 12, "same"), (1 << 13, "pow2"),
+                    (1000, "uniform")):
         dlog_msm_case(gpu, group(curve, True), n, kind, seed=n + 1)
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_msm_g2_repeated_and_opposite_points(gpu, curve):
+    """The special cases of the group law inside ONE bucket of the G2 accumulation (msm_pair.cuh: selects over pair-uniform flags,
+    the doubling walked by the whole warp): the same point many times (P + P right after the bucket's first point), P and -P
+    alternating (the running sum returns to the identity over and over), identities in between -- against the oracle."""
+    G = group(curve, True)
+    rnd = random.Random(77 + curve)
+    P1, P2 = G.mul(G.gen, rnd.randrange(1, G.r)), G.mul(G.gen, rnd.randrange(1, G.r))
+    s = rnd.randrange(1, G.r)
+    cases = [
+        ([P1] * 40, [s] * 40),
+        ([P1, G.neg(P1)] * 20 + [P2], [s] * 40 + [s]),
+        ([P1, None, P1, None, G.neg(P1), P2, P2, P2], [s] * 8),
+        ([P1, P1, G.neg(P1), G.neg(P1), P1], [3, 3, 3, 3, 3]),
+    ]
+    for pts, sc in cases:
+        assert msm_gpu(gpu, G, pts, sc) == G.msm(pts, sc)
 
 
 @pytest.mark.parametrize("curve", CURVES)

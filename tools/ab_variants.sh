@@ -12,7 +12,7 @@ for spec in "$@"; do   # spec = lib[:ENV=VAL[,ENV=VAL...]]
   envs=""; if [ "$spec" != "$v" ]; then envs=$(echo "${spec#*:}" | tr ',' ' '); fi
   label=$(echo "$spec" | tr -c 'A-Za-z0-9_\n' '_')
   if [ "$v" = main ]; then cp /tmp/libzkb200_main.so zksnake_b200/libzkb200.so; else cp variants/libzkb200_$v.so zksnake_b200/libzkb200.so; fi
-  for curve in BN254 BLS12_381; do
+  for curve in ${CURVES:-BN254 BLS12_381}; do
     env $envs timeout 600 python bench.py --curve $curve $ARGS > gpurun_out/${TAG}_${label}_${curve}.json 2> gpurun_out/${TAG}_${label}_${curve}.err
     echo "$spec $curve rc=$?"
     python - <<PY

@@ -194,3 +194,18 @@ def test_sharded_prover_needs_a_matching_process_group():
         dist.require_world(1, 4)
     with pytest.raises(RuntimeError):
         dist.shared_draws(lambda n: 1, 10, 2, world_size=2)
+
+
+def test_chain_spreading_assignment():
+    """Every transform chain of the Groth16 quotient has exactly one owner at every world size, the masks partition {U, V, W},
+    and with three or more ranks no rank runs more than one chain (zksnake_b200/dist.py)."""
+    from zksnake_b200 import dist
+    for ws in range(1, 10):
+        owners = [dist.chain_owner(c, ws) for c in range(3)]
+        assert all(0 <= o < ws for o in owners)
+        masks = [dist.chain_mask(r, ws) for r in range(ws)]
+        assert sum(masks) == 7 and all(masks[a] & masks[b] == 0 for a in range(ws) for b in range(a))
+        for c in range(3):
+            assert masks[owners[c]] >> c & 1
+        if ws >= 3:
+            assert all(bin(m).count("1") <= 1 for m in masks)

@@ -984,6 +984,100 @@ static int partial_from_resident_witness(zkb_groth16_pk* pk, zkb_r1cs* r1cs, siz
   return done(groth16_msms(pk, d_priv));
 }
 
+// ---- chain spreading (several GPUs): zkb_groth16_spread_begin .. the caller's broadcasts .. zkb_groth16_spread_finish -------
+// What zkb_groth16_partial does in one call, cut where the ranks exchange data.  begin: witness -> A.w, B.w, C.w (every rank: the
+// SpMVs are cheap and the satisfiability check needs all three) -> the chains of `chain_mask` (bit c: 0 U, 1 V, 2 W): coefficients
+// into d_coeffs + c n, coset evaluations into d_evals + c n (caller-owned device buffers of 3 n elements each).  The caller then
+// broadcasts coefficient vectors 0, 1 and evaluation vectors 0, 1, 2 from their owners ON THE LIBRARY STREAM.  finish: U, V ->
+// the key's scalar slots, H from the three evaluation vectors, the five MSMs of this rank's window shard.
+// The scratch arena stays held between the two calls (the private-witness digit sort already runs on the sort stream).
+static struct SpreadState {
+  bool active = false;
+  zkb_groth16_pk* pk = nullptr;
+  int* flag = nullptr;
+  void* tmp = nullptr;
+  cudaEvent_t ev = nullptr;
+} g_spread;
+static void spread_drop() {
+  for (int i = 0; i < 5; i++) msm_presort_cancel(&g16_tk[i]);
+  scratch_hold_end();
+  g_spread.active = false;
+}
+int zkb_groth16_spread_begin(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const void* witness, int witness_on_device, size_t n_public,
+                             unsigned chain_mask, void* d_coeffs, void* d_evals) {
+  NEED_INIT();
+  int rc;
+  if (g_spread.active) spread_drop();
+  if ((rc = prove_witness_checks(pk, r1cs, n_public))) return rc;
+  if (!d_coeffs || !d_evals || chain_mask > 7) return set_error(ZKB_ERR_ARG, "spread: bad argument");
+  if ((rc = r1cs_load_witness(r1cs, witness, witness_on_device))) return rc;
+  const size_t bytes = pk->n * 32;
+  char* w = pk->work;
+  const void* d_priv = (char*)r1cs->w + n_public * 32;
+  if (!g_spread.ev) ZKB_CUDA(cudaEventCreateWithFlags(&g_spread.ev, cudaEventDisableTiming));
+  cudaStream_t sort_st = (cudaStream_t)ctx_side_stream(7);
+  if (!sort_st) return set_error(ZKB_ERR_CUDA, "cannot create the sort stream");
+  MsmJob job[5];
+  groth16_jobs(pk, d_priv, job);
+  size_t need_msm = 0;
+  if ((rc = msm_batch_need(pk->curve, job, 5, pk->wrank, pk->wworld, &need_msm))) return rc;
+  if ((rc = scratch_hold_begin(need_msm + bytes + (1 << 20)))) return rc;
+  g_spread.active = true;
+  g_spread.pk = pk;
+  auto fail = [&](int code) {
+    spread_drop();
+    return code;
+  };
+  if (cudaEventRecord(g_spread.ev, S()) != cudaSuccess || cudaStreamWaitEvent(sort_st, g_spread.ev, 0) != cudaSuccess)
+    return fail(set_error(ZKB_ERR_CUDA, "presort fork failed"));
+  if ((rc = msm_presort(pk->curve, job[4], pk->wrank, pk->wworld, &g16_tk[4], sort_st))) return fail(rc);
+  g_spread.flag = (int*)scratch_take(256);
+  g_spread.tmp = scratch_take(bytes);
+  if (!g_spread.flag || !g_spread.tmp) return fail(set_error(ZKB_ERR_CUDA, "scratch exhausted"));
+  if ((rc = r1cs_spmv3(r1cs, pk->n, w, w + bytes, w + 2 * bytes))) return fail(rc);
+  if ((rc = groth16_check_dev(pk->curve, pk->log_n, w, w + bytes, w + 2 * bytes, g_spread.flag))) return fail(rc);
+  for (int c = 0; c < 3; c++)
+    if (chain_mask >> c & 1)
+      if ((rc = groth16_chain_dev(pk->curve, pk->log_n, c, w + c * bytes, (char*)d_coeffs + c * bytes, (char*)d_evals + c * bytes,
+                                  g_spread.tmp)))
+        return fail(rc);
+  return ZKB_OK;
+}
+int zkb_groth16_spread_finish(zkb_groth16_pk* pk, zkb_r1cs* r1cs, size_t n_public, const void* d_coeffs, void* d_evals,
+                              uint64_t* msm_xy, int* msm_inf) {
+  NEED_INIT();
+  if (!g_spread.active || g_spread.pk != pk || !r1cs) return set_error(ZKB_ERR_ARG, "spread: finish without begin");
+  int rc;
+  const size_t bytes = pk->n * 32;
+  char* w = pk->work;
+  const void* d_priv = (char*)r1cs->w + n_public * 32;
+  auto done = [&](int code) {
+    spread_drop();
+    return code;
+  };
+  // U, V (complete on the library stream behind the caller's broadcasts) become the MSM scalars
+  if (cudaMemcpyAsync(w + 3 * bytes, d_coeffs, 2 * bytes, cudaMemcpyDeviceToDevice, S()) != cudaSuccess)
+    return done(set_error(ZKB_ERR_CUDA, "spread: copy failed"));
+  PresortCtx ctx;
+  ctx.pk = pk;
+  ctx.sort_st = (cudaStream_t)ctx_side_stream(7);
+  ctx.ev = g_spread.ev;
+  ctx.rc = ZKB_OK;
+  groth16_jobs(pk, d_priv, ctx.job);
+  presort_uv(&ctx);
+  if (ctx.rc) return done(ctx.rc);
+  char* e = (char*)d_evals;
+  if ((rc = groth16_hfin_dev(pk->curve, pk->log_n, e, e + bytes, e + 2 * bytes, w + 6 * bytes, g_spread.tmp))) return done(rc);
+  int hflag = 0;
+  if (ZKB_D2H(&hflag, g_spread.flag, sizeof(int)) != cudaSuccess || cudaStreamSynchronize(S()) != cudaSuccess)
+    return done(set_error(ZKB_ERR_CUDA, "spread: flag readback failed"));
+  if (hflag) return done(set_error(ZKB_ERR_NOT_DIVISIBLE, "(U * V - W) did not divided by Z to zero"));
+  if ((rc = groth16_msms(pk, d_priv))) return done(rc);
+  memcpy(msm_xy, pk->msm_xy, sizeof(pk->msm_xy));
+  memcpy(msm_inf, pk->msm_inf, sizeof(pk->msm_inf));
+  return done(ZKB_OK);
+}
+
 int zkb_groth16_partial(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const void* witness, int witness_on_device, size_t n_public,
                         uint64_t* msm_xy, int* msm_inf) {
   NEED_INIT();

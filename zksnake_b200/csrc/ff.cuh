@@ -447,10 +447,26 @@ template <class P, class = void>
 struct uses_split_sqr { static constexpr bool value = false; };
 template <class P>
 struct uses_split_sqr<P, decltype((void)P::SPLIT_SQR)> { static constexpr bool value = P::SPLIT_SQR; };
+// A parameter struct with `static constexpr bool NOINLINE_SQR = true;` keeps its products inline but calls ONE shared body for
+// the squarings: two of the ten multiplier bodies of a mixed addition leave the loop, which brings it under the 32 KB L1.5
+// instruction cache (msm_host.cuh).
+template <class P, class = void>
+struct sqr_out_of_line { static constexpr bool value = false; };
+template <class P>
+struct sqr_out_of_line<P, decltype((void)P::NOINLINE_SQR)> { static constexpr bool value = P::NOINLINE_SQR; };
+#if defined(__CUDA_ARCH__)
+template <class P>
+__device__ __noinline__ Fp<P> mont_sqr_call(Fp<P> a) { return mont_mul(a, a); }
+#endif
 template <class P>
 ZKB_HD Fp<P> sqr(const Fp<P>& a) {
   if constexpr (uses_split_sqr<P>::value) return mont_sqr_split(a);
-  else return a * a;
+  else {
+#if defined(__CUDA_ARCH__)
+    if constexpr (sqr_out_of_line<P>::value) return mont_sqr_call<P>(a);
+#endif
+    return a * a;
+  }
 }
 
 // canonical <-> Montgomery

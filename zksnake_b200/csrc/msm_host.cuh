@@ -16,13 +16,17 @@ static inline cudaStream_t MS() { return (cudaStream_t)ctx_stream(); }
 
 // the inline-multiplier twin of a stored field (identical layout; only the device code generation differs)
 template <class P> struct InlineMul : P { static constexpr bool NOINLINE_MUL = false; };
+template <class P> struct InlineMulCallSqr : P { static constexpr bool NOINLINE_MUL = false; static constexpr bool NOINLINE_SQR = true; };
+#ifndef ZKB_G1_BN_BASE
+#define ZKB_G1_BN_BASE InlineMul<FqBN254>
+#endif
 // PAIR: two lanes per point (msm_pair.cuh) -- the accumulation grid then runs 148 x MINB x 64 runs at a time
 template <class F> struct AccumField { typedef F type; static constexpr int MINB = 2; static constexpr bool PAIR = false; };
 // G1 BN254: the fully inlined XYZZ addition is ~9-15 % faster than calling the multiplier out of line (tools/ffbench.cu).
 // G1 BLS12-381: inlined it is 7.2 K instructions (115 KB, far beyond the 32 KB L1.5 instruction cache) -- out of line at 4 CTAs
 // per SM the 2^20-point launch goes 6.43 -> 6.08 ms and the proof 50.7 -> 48.0 ms (profiles/R2s_*).
 // G2: two lanes per point, multiplier bodies out of line (msm_pair.cuh).
-template <> struct AccumField<Fp<FqBN254>> { typedef Fp<InlineMul<FqBN254>> type; static constexpr int MINB = 4; static constexpr bool PAIR = false; };
+template <> struct AccumField<Fp<FqBN254>> { typedef Fp<ZKB_G1_BN_BASE> type; static constexpr int MINB = 4; static constexpr bool PAIR = false; };
 #ifndef ZKB_G1_BLS_BASE
 #define ZKB_G1_BLS_BASE FqBLS381
 #endif

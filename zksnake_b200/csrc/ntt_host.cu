@@ -476,6 +476,64 @@ static int groth16_h_t(uint32_t log_n, const void* d_a, const void* d_b, const v
   }
   return ZKB_OK;
 }
+// ---- the same pipeline in separable steps: on several GPUs the three interpolation -> coset-evaluation chains run on different
+// ranks and the results are broadcast (zkb_groth16_spread_begin / _finish, api.cu; SURVEY.md section 8e "independent A/B/C NTTs
+// spread across GPUs").  Same kernels and tables as groth16_h_t, so every value is the same field element.
+template <class F>
+static int groth16_check_t(uint32_t log_n, const void* d_a, const void* d_b, const void* d_c, int* d_flag) {
+  const size_t n = (size_t)1 << log_n;
+  ZKB_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), S()));
+  unsigned blocks = (unsigned)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  prof_begin(PROF_VEC);
+  check_abc_kernel<F><<<blocks, 256, 0, S()>>>(n, (const F*)d_a, (const F*)d_b, (const F*)d_c, d_flag);
+  prof_end(PROF_VEC);
+  count_launch();
+  ZKB_CUDA(cudaGetLastError());
+  return ZKB_OK;
+}
+// chain `which` (0 U, 1 V, 2 W): coefficients = iNTT(evaluations on the domain), then their evaluations on the coset g<w>
+// (W's come out divided by R, as the fused (U V - W) kernel expects)
+template <class F>
+static int groth16_chain_t(uint32_t log_n, int which, const void* d_in, void* d_coeff, void* d_eval, void* d_tmp) {
+  typedef typename F::Params P;
+  if (log_n > (uint32_t)P::TWO_ADICITY || log_n > 30) return set_error(ZKB_ERR_DOMAIN, "Domain size is too large");
+  const size_t n = (size_t)1 << log_n;
+  Domain<F>* d;
+  int rc = get_domain<F>(log_n, true, &d);
+  if (rc) return rc;
+  PowTable<F> fwd = d->fwd.view(), inv_t = d->inv.view();
+  PowTable<F> gpre = d->gen_pre.view(), gpre_r = d->gen_pre_r.view();
+  if ((rc = ntt_exec<F>((const F*)d_in, n, (F*)d_coeff, log_n, inv_t, nullptr, nullptr, &d->n_inv, (F*)d_tmp))) return rc;
+  return ntt_exec<F>((const F*)d_coeff, n, (F*)d_eval, log_n, fwd, which == 2 ? &gpre_r : &gpre, nullptr, nullptr, (F*)d_tmp);
+}
+// H from the three coset evaluation vectors (d_eu is overwritten with (U V - W) / R)
+template <class F>
+static int groth16_hfin_t(uint32_t log_n, void* d_eu, const void* d_ev, const void* d_ew, void* d_h, void* d_tmp) {
+  const size_t n = (size_t)1 << log_n;
+  Domain<F>* d;
+  int rc = get_domain<F>(log_n, true, &d);
+  if (rc) return rc;
+  PowTable<F> inv_t = d->inv.view(), gpost = d->gen_post.view();
+  if ((rc = vec_op_t<F>(VEC_MULSUB_RAW, n, d_eu, n, d_ev, n, d_ew, d_eu))) return rc;
+  return ntt_exec<F>((const F*)d_eu, n, (F*)d_h, log_n, inv_t, nullptr, &gpost, nullptr, (F*)d_tmp);
+}
+int groth16_check_dev(int curve, uint32_t log_n, const void* d_a, const void* d_b, const void* d_c, int* d_flag) {
+  if (curve == ZKB_BN254) return groth16_check_t<fr_bn>(log_n, d_a, d_b, d_c, d_flag);
+  if (curve == ZKB_BLS12_381) return groth16_check_t<fr_bls>(log_n, d_a, d_b, d_c, d_flag);
+  return set_error(ZKB_ERR_ARG, "unknown curve id");
+}
+int groth16_chain_dev(int curve, uint32_t log_n, int which, const void* d_in, void* d_coeff, void* d_eval, void* d_tmp) {
+  if (curve == ZKB_BN254) return groth16_chain_t<fr_bn>(log_n, which, d_in, d_coeff, d_eval, d_tmp);
+  if (curve == ZKB_BLS12_381) return groth16_chain_t<fr_bls>(log_n, which, d_in, d_coeff, d_eval, d_tmp);
+  return set_error(ZKB_ERR_ARG, "unknown curve id");
+}
+int groth16_hfin_dev(int curve, uint32_t log_n, void* d_eu, const void* d_ev, const void* d_ew, void* d_h, void* d_tmp) {
+  if (curve == ZKB_BN254) return groth16_hfin_t<fr_bn>(log_n, d_eu, d_ev, d_ew, d_h, d_tmp);
+  if (curve == ZKB_BLS12_381) return groth16_hfin_t<fr_bls>(log_n, d_eu, d_ev, d_ew, d_h, d_tmp);
+  return set_error(ZKB_ERR_ARG, "unknown curve id");
+}
+
 int groth16_h_dev(int curve, uint32_t log_n, const void* d_a, const void* d_b, const void* d_c, void* d_u, void* d_v,
                   void* d_w, void* d_h, int check, void (*after_interp)(void*), void* arg) {
   if (curve == ZKB_BN254) return groth16_h_t<fr_bn>(log_n, d_a, d_b, d_c, d_u, d_v, d_w, d_h, check, after_interp, arg);

@@ -79,6 +79,11 @@ int fr_powers_dev(int curve, const uint64_t* base, const uint64_t* scale, size_t
 // library stream from there on, while four more transforms follow -- the caller forks the digit sorts of the U / V MSMs there.
 int groth16_h_dev(int curve, uint32_t log_n, const void* d_a, const void* d_b, const void* d_c, void* d_u, void* d_v,
                   void* d_w, void* d_h, int check, void (*after_interp)(void*) = nullptr, void* arg = nullptr);
+// the same pipeline step by step (multi-GPU chain spreading): witness check, one interpolation -> coset-evaluation chain
+// (which: 0 U, 1 V, 2 W), and H from the three coset evaluation vectors; d_tmp holds 2^log_n elements
+int groth16_check_dev(int curve, uint32_t log_n, const void* d_a, const void* d_b, const void* d_c, int* d_flag);
+int groth16_chain_dev(int curve, uint32_t log_n, int which, const void* d_in, void* d_coeff, void* d_eval, void* d_tmp);
+int groth16_hfin_dev(int curve, uint32_t log_n, void* d_eu, const void* d_ev, const void* d_ew, void* d_h, void* d_tmp);
 size_t ntt_scratch_bytes(uint32_t log_n);
 // long_rows: the n_long rows with more than SPMV_LONG_ROW non-zeros (device array, listed when the matrix is created); they are
 // summed by whole CTAs into long_partial (n_long * 64 elements) instead of by one thread each

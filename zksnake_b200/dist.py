@@ -93,6 +93,50 @@ def upload_sharded(arr):
     return full
 
 
+# ---- the three interpolation -> coset-evaluation chains of the Groth16 quotient, one per rank ---------------------------------------
+# QAP.evaluate_witness (/root/reference/python/zksnake/groth16/qap.py:57-63) transforms A.w, B.w and C.w independently.  On one GPU
+# they are one batched launch per pass; on several, rank chain_owner(c) runs chain c alone (zkb_groth16_spread_begin) and the five
+# vectors the other ranks need -- U and V (the MSM scalars of every rank's window shard) and the three coset evaluation vectors (for
+# H) -- are broadcast over NVLink on the library stream; every rank then forms H itself (one fused kernel + one inverse transform,
+# zkb_groth16_spread_finish).  Per rank: 2 (or 4, two ranks) + 1 transforms instead of 7.
+_spread_bufs = {}
+
+
+def chain_owner(chain, world_size):
+    """Rank that runs chain 0 (U), 1 (V) or 2 (W).  Three or more ranks: one chain each; two ranks: rank 0 takes U and W."""
+    return chain % world_size if world_size >= 3 else (0, 1 % world_size, 0)[chain]
+
+
+def chain_mask(rank, world_size):
+    return sum(1 << c for c in range(3) if chain_owner(c, world_size) == rank)
+
+
+def spread_buffers(n_elems):
+    """Two persistent device buffers of 3 * n_elems Fr elements (coefficients U|V|W, coset evaluations) as torch uint8 tensors."""
+    import torch
+    bufs = _spread_bufs.get(n_elems)
+    if bufs is None:
+        with torch.cuda.stream(library_stream()):
+            bufs = (torch.empty(3 * n_elems * 32, dtype=torch.uint8, device="cuda"),
+                    torch.empty(3 * n_elems * 32, dtype=torch.uint8, device="cuda"))
+        _spread_bufs[n_elems] = bufs
+    return bufs
+
+
+def broadcast_chains(coeffs, evals, n_elems):
+    """The exchange step between zkb_groth16_spread_begin and _finish: U, V and the three evaluation vectors from their owners to
+    everybody, enqueued on the library stream (no host synchronisation)."""
+    import torch
+    import torch.distributed as td
+    _, ws = world()
+    nb = n_elems * 32
+    with torch.cuda.stream(library_stream()):
+        for c in (0, 1):
+            td.broadcast(coeffs[c * nb:(c + 1) * nb], src=chain_owner(c, ws))
+        for c in (0, 1, 2):
+            td.broadcast(evals[c * nb:(c + 1) * nb], src=chain_owner(c, ws))
+
+
 # ---- host-side exchange of small payloads between the ranks of ONE node -----------------------------------------------------
 class HostExchange:
     """All-gather of a few hundred bytes per rank through a POSIX shared-memory mailbox.

@@ -342,8 +342,19 @@ class Groth16:
             nat.check(nat.lib.zkb_groth16_precompute(self._pk_handle, nat.ptr(rr), nat.ptr(ss)))   # host threads, under the GPU work
             xy = np.zeros((dist.MSM_SLOTS, dist.SLOT_LIMBS), dtype=np.uint64)
             flags = np.zeros(dist.MSM_SLOTS, dtype=np.int32)
-            nat.check(nat.lib.zkb_groth16_partial(self._pk_handle, self._r1cs_handle, wptr, int(on_dev), self.n_public,
-                                                  nat.ptr(xy), nat.ptr(flags)))
+            if self._spread_chains():
+                # the three transform chains on three ranks (two: 2 + 1), results broadcast over NVLink on the library stream
+                coeffs, evals = dist.spread_buffers(self.n)
+                nat.check(nat.lib.zkb_groth16_spread_begin(self._pk_handle, self._r1cs_handle, wptr, int(on_dev), self.n_public,
+                                                           dist.chain_mask(self.rank, self.world),
+                                                           ctypes.c_void_p(coeffs.data_ptr()), ctypes.c_void_p(evals.data_ptr())))
+                dist.broadcast_chains(coeffs, evals, self.n)
+                nat.check(nat.lib.zkb_groth16_spread_finish(self._pk_handle, self._r1cs_handle, self.n_public,
+                                                            ctypes.c_void_p(coeffs.data_ptr()), ctypes.c_void_p(evals.data_ptr()),
+                                                            nat.ptr(xy), nat.ptr(flags)))
+            else:
+                nat.check(nat.lib.zkb_groth16_partial(self._pk_handle, self._r1cs_handle, wptr, int(on_dev), self.n_public,
+                                                      nat.ptr(xy), nat.ptr(flags)))
             all_xy, all_inf = dist.all_gather_partials(xy, flags)
             all_xy = np.ascontiguousarray(all_xy)
             all_inf = np.ascontiguousarray(all_inf, dtype=np.int32)
@@ -351,6 +362,13 @@ class Groth16:
                                                             nat.ptr(ss), nat.ptr(oa), nat.ptr(ob), nat.ptr(oc), inf))
         ec = self.ec
         return Proof(ec.PointG1._from_flat(oa, inf[0]), ec.PointG2._from_flat(ob, inf[1]), ec.PointG1._from_flat(oc, inf[2]))
+
+    def _spread_chains(self):
+        """Run the quotient's three transform chains on different ranks?  Needs the NCCL world this prover shards over, whole key
+        vectors on every rank (window sharding) and a domain large enough for a broadcast to be cheaper than a transform."""
+        if os.environ.get("ZKB_NTT_SPREAD", "1") == "0" or self._emulate or self.shard_mode != "windows":
+            return False
+        return self.world > 1 and dist.nccl_ready() and self.n >= (1 << 16)
 
     def last_polys(self):
         """U, V, H coefficient lists of the last prove (n entries each, unstripped) for parity tests."""

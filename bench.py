@@ -417,12 +417,14 @@ def main_own(args):
     nat.check(nat.lib.zkb_prof_enable(1))
     barrier()
     launches0 = nat.lib.zkb_launch_count()
+    prover.phase_ms.clear()
     t0 = time.perf_counter()
     with nat.Timer() as tm:
         for _ in range(args.steps):
             prover.prove_packed(w_dev, r_rand, s_rand)
     barrier()
     t1 = time.perf_counter()
+    host_phases = {k: round(v / max(prover.phase_ms.get("proofs", 1), 1), 3) for k, v in prover.phase_ms.items() if k != "proofs"}
     launches = nat.lib.zkb_launch_count() - launches0
     dev_ms = tm.ms / args.steps
     wall_ms = (t1 - t0) * 1e3 / args.steps
@@ -470,6 +472,13 @@ def main_own(args):
         lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
         td.all_reduce(lt)
         launches = int(lt.item())
+        # where each rank's host spent the sharded proof: its own work up to the partial sums | waiting for the slowest rank | assembly
+        ph = torch.tensor([host_phases.get(k, 0.0) for k in ("partial", "exchange", "assemble")], dtype=torch.float64, device="cuda")
+        allph = torch.empty(world * 3, dtype=torch.float64, device="cuda")
+        td.all_gather_into_tensor(allph, ph)
+        allph = allph.cpu().reshape(world, 3).tolist()
+        host_phases = {"partial": [round(r[0], 3) for r in allph], "exchange": [round(r[1], 3) for r in allph],
+                       "assemble": [round(r[2], 3) for r in allph], "note": "per rank, mean ms per proof, device-resident leg"}
 
     if rank != 0:
         if td is not None:
@@ -551,11 +560,20 @@ def main_own(args):
     ntt_ms, ntt_cnt = prof["ntt"]
     roofline_ntt = None
     if ntt_cnt:
-        per = ntt_ms / ntt_cnt
+        # The timed brackets are per ENQUEUE CALL: one whole transform (both passes) or a batch of three (the quotient's three
+        # interpolations, then its three coset evaluations, are one batched launch per pass).  Transforms rank 0 runs per proof: all
+        # 7 on one GPU; with the chains spread over the ranks, its own chains x 2 (rank 0 never forms H, zksnake_b200/dist.py).
+        if world > 1 and prover._spread_chains():
+            transforms = 2 * bin(zdist.chain_mask(rank, world)).count("1")
+        else:
+            transforms = 7
+        per = ntt_ms / args.steps / max(transforms, 1)
         ach = 64.0 * n / (per * 1e-3) / 1e9
-        roofline_ntt = {"kernel": "ntt_pass_kernel (all passes of one 2^%d transform)" % args.log_n, "bound": "hbm",
+        roofline_ntt = {"kernel": "ntt_warp_pass_kernel / ntt_pass_kernel (all passes of one 2^%d transform)" % args.log_n, "bound": "hbm",
                         "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": hbm_src,
-                        "algorithmic_bytes": 64 * n, "launch_ms": per, "launches": ntt_cnt,
+                        "algorithmic_bytes": 64 * n, "launch_ms": per, "launches": ntt_cnt, "transforms_per_step": transforms,
+                        "note": "launch_ms = the transforms' device time per proof / transforms_per_step; on one GPU the digit sorts of "
+                                "the witness, U and V MSMs run beside the transforms on a side stream and lengthen them",
                         "traffic": (traffic.get("ntt_pass") or {}).get("dram_bytes"),
                         "traffic_detail": dict(traffic.get("ntt_pass") or {}, note="one PASS of the transform (a 2^20 transform is 2 passes)"),
                         "share_of_step": ntt_ms / args.steps / dev_ms}
@@ -590,8 +608,9 @@ def main_own(args):
             "api": "zksnake_b200.groth16.Groth16.prove(public: list[int], private: list[int]) -> Proof.to_bytes() (the reference's "
                    "signature, protocol.py:115-131): 2^%d Python ints marshalled by csrc/pymarshal.cpp every step" % args.log_n},
         "breakdown_ms": breakdown,
+        "host_phases_ms": host_phases if world > 1 else None,
         "msm_mpts_s": (4 + 1) * pts_per_launch / (msm_ms_total * 1e-3) / 1e6 if msm_ms_total else None,
-        "ntt_gelem_s": n / (ntt_ms / ntt_cnt * 1e-3) / 1e9 if ntt_cnt else None,
+        "ntt_gelem_s": n / (roofline_ntt["launch_ms"] * 1e-3) / 1e9 if roofline_ntt else None,
         "proof_sha": __import__("hashlib").sha256(bytes.fromhex(proof_hex)).hexdigest()[:16],
         "setup_s": setup_s,
     }
@@ -724,6 +743,13 @@ def main_plonk(args):
         lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
         td.all_reduce(lt)
         launches = int(lt.item())
+        # where each rank's host spent the sharded proof: its own work up to the partial sums | waiting for the slowest rank | assembly
+        ph = torch.tensor([host_phases.get(k, 0.0) for k in ("partial", "exchange", "assemble")], dtype=torch.float64, device="cuda")
+        allph = torch.empty(world * 3, dtype=torch.float64, device="cuda")
+        td.all_gather_into_tensor(allph, ph)
+        allph = allph.cpu().reshape(world, 3).tolist()
+        host_phases = {"partial": [round(r[0], 3) for r in allph], "exchange": [round(r[1], 3) for r in allph],
+                       "assemble": [round(r[2], 3) for r in allph], "note": "per rank, mean ms per proof, device-resident leg"}
     if rank != 0:
         if td is not None:
             td.destroy_process_group()

@@ -267,18 +267,30 @@ int zkb_groth16_prove_witness_dev(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const void
  * added with zkb_point_lincomb and turned into the proof by zkb_groth16_assemble (protocol.py:133-165). */
 int zkb_groth16_partial(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const void* witness, int witness_on_device, size_t n_public,
                         uint64_t* msm_xy, int* msm_inf);
-/* zkb_groth16_partial cut in two where the ranks exchange data, so that the three independent interpolation -> coset-evaluation
- * chains of QAP.evaluate_witness (/root/reference/python/zksnake/groth16/qap.py:57-63: the A, B and C transforms) run on DIFFERENT
- * GPUs instead of on every one.  begin: witness -> A.w, B.w, C.w and the satisfiability check on every rank, then the chains whose
- * bit is set in chain_mask (bit 0 U, 1 V, 2 W): coefficients to d_coeffs + c * n, evaluations on the coset to d_evals + c * n
- * (caller-owned device buffers of 3 n Fr elements each, n = the key's domain size).  The caller broadcasts coefficient vectors 0, 1
- * and evaluation vectors 0, 1, 2 from their owners on the library stream (zkb_stream; zksnake_b200/dist.py does it with NCCL).
- * finish: the quotient H from the three evaluation vectors and this rank's share of the five MSMs, as zkb_groth16_partial returns
- * them.  Every value is the same field element as in the one-call path, so the proof bytes do not change. */
+/* zkb_groth16_partial cut where the ranks exchange data, so that the three independent interpolation -> coset-evaluation chains of
+ * QAP.evaluate_witness (/root/reference/python/zksnake/groth16/qap.py:57-63: the A, B and C transforms) run on DIFFERENT GPUs and
+ * the quotient's last step (qap.py:64-69) on ONE of them, instead of everything on every GPU.
+ *   begin:    witness -> A.w, B.w, C.w and the satisfiability check on every rank (the SpMVs are cheap and the check needs all
+ *             three), then the chains whose bit is set in chain_mask (bit 0 U, 1 V, 2 W): coefficients to d_coeffs + c * n,
+ *             evaluations on the coset to d_evals + c * n (caller-owned device buffers of 3 n Fr elements each, n = the key's domain
+ *             size).  A rank with chain_mask == 0 starts its [K w] MSM instead (it needs the witness only).
+ *   exchange: (caller; zksnake_b200/dist.py:exchange_chains does it with NCCL) coefficient vectors 0 and 1 broadcast from their owners
+ *             on the library stream (zkb_stream); evaluation vectors sent to the quotient rank.
+ *   quotient: on the quotient rank only, on the library stream: H = coset-iNTT((eU eV - eW) / Z) from d_evals into d_h (n elements).
+ *   exchange: d_h broadcast from the quotient rank -- on any stream; h_ready_event (a cudaEvent_t recorded behind that broadcast, or
+ *             NULL if it ran on the library stream) tells finish when d_h is complete.
+ *   finish:   this rank's share of the MSMs over U, V and the witness, then -- behind h_ready_event -- of [H Z]; msm_xy / msm_inf as
+ *             zkb_groth16_partial returns them.
+ * Every value is the same field element as in the one-call path, so the proof bytes do not change. */
 int zkb_groth16_spread_begin(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const void* witness, int witness_on_device, size_t n_public,
                              unsigned chain_mask, void* d_coeffs, void* d_evals);
-int zkb_groth16_spread_finish(zkb_groth16_pk* pk, zkb_r1cs* r1cs, size_t n_public, const void* d_coeffs, void* d_evals,
-                              uint64_t* msm_xy, int* msm_inf);
+int zkb_groth16_spread_quotient(zkb_groth16_pk* pk, void* d_evals, void* d_h);
+int zkb_groth16_spread_finish(zkb_groth16_pk* pk, zkb_r1cs* r1cs, size_t n_public, const void* d_coeffs, const void* d_h,
+                              void* h_ready_event, uint64_t* msm_xy, int* msm_inf);
+/* msm_inf[3] may carry bit 1 (value 2): the rank was given (r, s) beforehand (zkb_groth16_precompute on a sharded key) and its HZ
+ * slot is [H Z]_i + s [U]_i + r [V]_i -- C is linear in the partial sums, so the two scalar multiplications of protocol.py:157-160
+ * are done per rank under its GPU work and only point additions follow the exchange.  Either every rank's slot carries the bit or
+ * none does. */
 int zkb_groth16_assemble(zkb_groth16_pk* pk, const uint64_t* msm_xy, const int* msm_inf, const uint64_t r[4],
                          const uint64_t s[4], uint64_t* out_a, uint64_t* out_b, uint64_t* out_c, int out_inf[3]);
 /* The last two steps in one call: all_xy = world x 5 x 24 uint64 (every rank's msm_xy, rank-major), all_inf = world x 5 flags; the

@@ -209,3 +209,14 @@ def test_chain_spreading_assignment():
             assert masks[owners[c]] >> c & 1
         if ws >= 3:
             assert all(bin(m).count("1") <= 1 for m in masks)
+        if ws >= 2:
+            # the rank that forms H: a valid rank, without a chain where one exists, never the rank with the most chains; and the
+            # point-to-point schedule of dist.exchange_chains pairs every send with one receive in the same order on both sides
+            h = dist.quotient_owner(ws)
+            assert 0 <= h < ws
+            assert masks[h] == 0 if ws >= 4 else bin(masks[h]).count("1") == min(bin(m).count("1") for m in masks)
+            senders = [(c, owners[c]) for c in range(3) if owners[c] != h]
+            assert len(senders) == 3 - bin(masks[h]).count("1")
+            for r in range(ws):
+                if r != h:
+                    assert [c for c, o in senders if o == r] == [c for c in range(3) if masks[r] >> c & 1]

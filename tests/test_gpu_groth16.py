@@ -229,3 +229,34 @@ def test_sharded_partials_assemble_to_the_same_proof(gpu, mode, world):
     ec = g.ec
     got = gm.Proof(ec.PointG1._from_flat(oa, inf[0]), ec.PointG2._from_flat(ob, inf[1]), ec.PointG1._from_flat(oc, inf[2]))
     assert got.to_bytes() == want
+    # the same with (r, s) handed to every rank beforehand (what the multi-GPU prover does): each rank multiplies ITS partial sums
+    # of [U] and [V] by s and r and folds them into its HZ slot (bit 1 of that slot's flag), the assembly is additions only --
+    # through both assembly routes (one C call over all ranks' slots; Python slot sums + zkb_groth16_assemble)
+    lr, ls = nat.ints_to_limbs([rr]), nat.ints_to_limbs([ss])
+    for route in ("partials", "python"):
+        parts_xy, parts_inf = [], []
+        for g in provers:
+            nat.check(nat.lib.zkb_groth16_precompute(g._pk_handle, nat.ptr(lr), nat.ptr(ls)))
+            xy = np.zeros((dist.MSM_SLOTS, dist.SLOT_LIMBS), dtype=np.uint64)
+            flags = np.zeros(dist.MSM_SLOTS, dtype=np.int32)
+            nat.check(nat.lib.zkb_groth16_partial(g._pk_handle, g._r1cs_handle, nat.ptr(w), 0, g.n_public, nat.ptr(xy), nat.ptr(flags)))
+            assert flags[3] & 2 and not any(int(f) & 2 for k, f in enumerate(flags) if k != 3)
+            parts_xy.append(xy)
+            parts_inf.append(flags)
+        oa[:], ob[:], oc[:] = 0, 0, 0
+        if route == "partials":
+            axy, ainf = np.ascontiguousarray(np.stack(parts_xy)), np.ascontiguousarray(np.stack(parts_inf), dtype=np.int32)
+            nat.check(nat.lib.zkb_groth16_assemble_partials(provers[0]._pk_handle, world, nat.ptr(axy), nat.ptr(ainf), nat.ptr(lr),
+                                                            nat.ptr(ls), nat.ptr(oa), nat.ptr(ob), nat.ptr(oc), inf))
+        else:
+            sxy, sinf = dist.add_partials(cid, np.stack(parts_xy), np.stack(parts_inf))
+            assert sinf[3] & 2
+            nat.check(nat.lib.zkb_groth16_assemble(provers[0]._pk_handle, nat.ptr(sxy), nat.ptr(sinf), nat.ptr(lr), nat.ptr(ls),
+                                                   nat.ptr(oa), nat.ptr(ob), nat.ptr(oc), inf))
+        got = gm.Proof(ec.PointG1._from_flat(oa, inf[0]), ec.PointG2._from_flat(ob, inf[1]), ec.PointG1._from_flat(oc, inf[2]))
+        assert got.to_bytes() == want, route
+    # a mix of folded and plain slots is refused
+    ainf[0, 3] &= 1
+    rc = nat.lib.zkb_groth16_assemble_partials(provers[0]._pk_handle, world, nat.ptr(axy), nat.ptr(ainf), nat.ptr(lr), nat.ptr(ls),
+                                               nat.ptr(oa), nat.ptr(ob), nat.ptr(oc), inf)
+    assert rc != 0

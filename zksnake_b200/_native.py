@@ -108,7 +108,8 @@ def _load():
         "zkb_groth16_prove_witness_dev": (c_int, [c_vp, c_vp, c_vp, c_sz, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "zkb_groth16_partial": (c_int, [c_vp, c_vp, c_vp, c_int, c_sz, c_vp, c_vp]),
         "zkb_groth16_spread_begin": (c_int, [c_vp, c_vp, c_vp, c_int, c_sz, ctypes.c_uint, c_vp, c_vp]),
-        "zkb_groth16_spread_finish": (c_int, [c_vp, c_vp, c_sz, c_vp, c_vp, c_vp, c_vp]),
+        "zkb_groth16_spread_quotient": (c_int, [c_vp, c_vp, c_vp]),
+        "zkb_groth16_spread_finish": (c_int, [c_vp, c_vp, c_sz, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "zkb_groth16_assemble": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "zkb_groth16_assemble_partials": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "zkb_groth16_last_poly": (c_int, [c_vp, c_int, c_vp]),

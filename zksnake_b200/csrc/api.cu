@@ -385,7 +385,17 @@ struct Groth16Pre {
   bool early = false;
   uint64_t A[12], sA[12], B1[12], rB1[12];
   int infA = 1, inf_sA = 1, infB1 = 1, inf_rB1 = 1;
+  // sharded provers (several GPUs): C is linear in the MSM results,
+  //   C = [H Z] + [K w] + s [U] + r [V]_1 + P0,   P0 = s alpha + r beta_1 + (r s) delta_1,
+  // so every rank multiplies ITS partial sums of [U] and [V]_1 by s and r on the host threads that finish those two MSMs -- under
+  // its remaining GPU work -- and hands out  [H Z]_i + s [U]_i + r [V]_i  in the HZ slot (flag bit 1 of that slot says so: `folded`).
+  // After the exchange only point additions are left; round 1 did both scalar multiplications after it (~0.25 ms exposed).
+  std::thread th3;
+  bool has_p0 = false, folded = false;
+  uint64_t p0[12], sU[12], rV[12];
+  int inf_p0 = 1, inf_sU = 1, inf_rV = 1;
 };
+#define ZKB_SLOT_FOLDED 2   // msm_inf[3] & 2: the HZ slot carries s [U]_i + r [V]_i as well
 static void pre_join(Groth16Pre* p);
 
 int zkb_groth16_pk_create_sharded(int curve, uint32_t log_n, const void* d_tau1, const void* d_tau2, const void* d_target1,
@@ -458,7 +468,8 @@ int zkb_groth16_pk_build_tables(zkb_groth16_pk* pk, uint32_t world) {
   const int grp[4] = {1, 2, 1, 1};
   for (int i = 0; i < 4; i++) {
     if (pk->tab[i] || cnt[i] == 0) continue;
-    int rc = zkb_msm_table_create(pk->curve, grp[i], vec[i], cnt[i], 0, world ? world : 1, &pk->tab[i]);
+    static const uint32_t force_c = [] { const char* e = getenv("ZKB_TABLE_C"); return e ? (uint32_t)atoi(e) : 0u; }();   // experiments
+    int rc = zkb_msm_table_create(pk->curve, grp[i], vec[i], cnt[i], force_c, world ? world : 1, &pk->tab[i]);
     if (rc) return rc;
   }
   ZKB_CUDA(cudaStreamSynchronize(S()));
@@ -502,8 +513,26 @@ static bool is_zero_pt(const uint64_t* p, size_t bytes) {
 // The five MSMs of protocol.py:133-155 as one batch: sort + accumulate back to back on the library stream, every reduction
 // (latency-bound) on a side stream as soon as its accumulation is done.  The G2 MSM goes first: its reduction chain is the
 // longest (an Fp2 addition is ~40 dependent Fq products) and so hides behind the four G1 accumulations.
-// Scalars: the full-length U, V, H in pk->work and d_priv.  Batch positions: B2 (G2, V), A (U), B1 (V), HZ (H), KW (priv).
+// Scalars: the full-length U, V, H in pk->work and d_priv.  The MSMs are named by their index in msm_xy (A, B1, B2, HZ, KW); the
+// batch ORDER depends on the prover:
+//  * one GPU: B2, A, B1, HZ, KW -- the G2 MSM first (its reduction chain, ~40 dependent Fq products per Fp2 addition, hides behind
+//    the four G1 accumulations) and [K w] last: nothing runs under the LAST reduction, and the witness MSM has the cheapest one
+//    (measured with H last instead: +0.4 ms of exposed reduction at 2^20);
+//  * a window shard of a multi-GPU proof: KW, B2, A, B1, HZ -- the order in which the scalars come into existence there: the private
+//    witness is there from the start (a rank that runs none of the transform chains accumulates [K w] while it waits for U and V), H
+//    arrives last, from the rank that formed it, while the other four MSMs run (zkb_groth16_spread_*).
 static MsmTicket g16_tk[5];
+enum { MSM_A = 0, MSM_B1 = 1, MSM_B2 = 2, MSM_HZ = 3, MSM_KW = 4 };
+static const int* groth16_order(const zkb_groth16_pk* pk) {   // batch position -> MSM
+  static const int single[5] = {MSM_B2, MSM_A, MSM_B1, MSM_HZ, MSM_KW}, shard[5] = {MSM_KW, MSM_B2, MSM_A, MSM_B1, MSM_HZ};
+  return pk->wworld > 1 ? shard : single;
+}
+static int groth16_pos(const zkb_groth16_pk* pk, int msm) {   // MSM -> batch position
+  const int* order = groth16_order(pk);
+  for (int i = 0; i < 5; i++)
+    if (order[i] == msm) return i;
+  return 0;
+}
 static void groth16_jobs(const zkb_groth16_pk* pk, const void* d_priv, MsmJob job[5]) {
   const size_t bytes = pk->n * 32;
   const char* w = pk->work;
@@ -513,33 +542,48 @@ static void groth16_jobs(const zkb_groth16_pk* pk, const void* d_priv, MsmJob jo
     if (t) return MsmJob{group, t->d_table, sc, n, t->c, t->n};
     return MsmJob{group, pts, sc, n, 0, 0};
   };
-  job[0] = mk(2, 1, pk->tau2, d_v, pk->len);
-  job[1] = mk(1, 0, pk->tau1, d_u, pk->len);
-  job[2] = mk(1, 0, pk->tau1, d_v, pk->len);
-  job[3] = mk(1, 2, pk->target1, d_h, pk->len);
-  job[4] = mk(1, 3, pk->kdelta1, (const char*)d_priv + pk->koff * 32, pk->klen);
+  job[groth16_pos(pk, MSM_KW)] = mk(1, 3, pk->kdelta1, (const char*)d_priv + pk->koff * 32, pk->klen);
+  job[groth16_pos(pk, MSM_B2)] = mk(2, 1, pk->tau2, d_v, pk->len);
+  job[groth16_pos(pk, MSM_A)] = mk(1, 0, pk->tau1, d_u, pk->len);
+  job[groth16_pos(pk, MSM_B1)] = mk(1, 0, pk->tau1, d_v, pk->len);
+  job[groth16_pos(pk, MSM_HZ)] = mk(1, 2, pk->target1, d_h, pk->len);
 }
 
-static int groth16_msms(zkb_groth16_pk* pk, const void* d_priv) {
-  const int curve = pk->curve;
-  MsmTicket* tk = g16_tk;
-  static const int slot[5] = {2, 0, 1, 3, 4};   // batch position -> index in msm_xy (A, B1, B2, HZ, KW)
+// jobs [first, first + count) of the batch on the library stream; `join`: order the stream behind their reductions
+static int groth16_enqueue(zkb_groth16_pk* pk, const void* d_priv, int first, int count, bool join) {
   MsmJob job[5];
   groth16_jobs(pk, d_priv, job);
-  int rc;
-  if ((rc = msm_enqueue_batch(curve, job, 5, pk->wrank, pk->wworld, tk))) return rc;
+  return msm_enqueue_batch(pk->curve, job + first, count, pk->wrank, pk->wworld, g16_tk + first, join, first);
+}
+// The host half of the five MSMs, after every job has been enqueued.
+static int groth16_collect(zkb_groth16_pk* pk) {
+  const int curve = pk->curve;
+  MsmTicket* tk = g16_tk;
+  const int* slot = groth16_order(pk);   // batch position -> index in msm_xy (A, B1, B2, HZ, KW)
   // the five host recombinations (~0.1-0.2 ms of 64-bit Montgomery arithmetic each) run on five host threads; each waits
   // for its own ticket's event, so they also overlap the reductions still running on the GPU
   int rcs[5] = {0, 0, 0, 0, 0};
   // whole-key single-GPU proofs: the MSM results are final, so the threads that finish [U] (-> A) and [V] in G1 (-> B1) go on
   // to s*A and r*B1, the two scalar multiplications of the assembly that depend on MSM results (~0.2 ms each), while the
-  // GPU still runs the later MSMs
+  // GPU still runs the later MSMs.  Sharded proofs: the same threads multiply this rank's PARTIAL sums (Groth16Pre::folded).
   Groth16Pre* pre = pk->pre;
-  const bool early = pre && pre->valid && pk->wworld == 1 && pk->len == pk->n && pk->klen == pk->n_kdelta;
-  if (pre) pre->early = false;
+  const bool whole = pk->wworld == 1 && pk->len == pk->n && pk->klen == pk->n_kdelta;
+  const bool early = pre && pre->valid && whole;
+  const bool fold = pre && pre->valid && !whole;
+  if (pre) pre->early = pre->folded = false;
   if (early) pre_join(pre);   // r*delta_1, s*delta_1 (started when r, s arrived; long done by now)
   auto after = [&](int i) {
-    if (!early || rcs[i]) return;
+    if (rcs[i]) return;
+    if (fold) {
+      if (slot[i] == 0 || slot[i] == 1) {
+        const uint64_t* p1[1] = {pk->msm_xy[slot[i]]};
+        int i1[1] = {pk->msm_inf[slot[i]]};
+        const uint64_t* s1[1] = {slot[i] == 0 ? pre->s : pre->r};
+        host_lincomb(curve, 1, 1, p1, i1, s1, slot[i] == 0 ? pre->sU : pre->rV, slot[i] == 0 ? &pre->inf_sU : &pre->inf_rV);
+      }
+      return;
+    }
+    if (!early) return;
     const size_t g1 = affine_bytes(curve, 1);
     if (slot[i] == 0) {
       const uint64_t* pts[3] = {pk->msm_xy[0], pk->alpha1, pre->rd1};
@@ -573,13 +617,43 @@ static int groth16_msms(zkb_groth16_pk* pk, const void* d_priv) {
   for (int i = 0; i < 5; i++)
     if (rcs[i]) return set_error(rcs[i], "msm_finish failed in the Groth16 MSM batch");
   if (early) pre->early = true;
+  if (fold) pre->folded = true;
   return ZKB_OK;
+}
+static int groth16_msms(zkb_groth16_pk* pk, const void* d_priv) {
+  int rc = groth16_enqueue(pk, d_priv, 0, 5, true);
+  if (rc) return rc;
+  return groth16_collect(pk);
+}
+// the deferred satisfiability answer (groth16_h_dev with check == 2 / the spread path's own copy); call after groth16_collect
+static int groth16_flag_result() {
+  const int* hf = groth16_flag_host();
+  if (hf && *hf) return set_error(ZKB_ERR_NOT_DIVISIBLE, "(U * V - W) did not divided by Z to zero");
+  return ZKB_OK;
+}
+// what a rank hands to the exchange: its five partial sums, the HZ slot carrying s [U]_i + r [V]_i when the fold ran
+static void groth16_export_partials(zkb_groth16_pk* pk, uint64_t* msm_xy, int* msm_inf) {
+  memcpy(msm_xy, pk->msm_xy, sizeof(pk->msm_xy));
+  memcpy(msm_inf, pk->msm_inf, sizeof(pk->msm_inf));
+  Groth16Pre* pre = pk->pre;
+  if (!pre || !pre->folded) return;
+  const uint64_t* pts[3] = {pk->msm_xy[3], pre->sU, pre->rV};
+  int infs[3] = {pk->msm_inf[3], pre->inf_sU, pre->inf_rV};
+  const uint64_t* sc[3] = {nullptr, nullptr, nullptr};
+  uint64_t out[24];
+  int inf = 1;
+  memset(out, 0, sizeof(out));
+  host_lincomb(pk->curve, 1, 3, pts, infs, sc, out, &inf);
+  memcpy(msm_xy + 3 * 24, out, sizeof(out));
+  msm_inf[3] = (inf ? 1 : 0) | ZKB_SLOT_FOLDED;
+  pre->folded = false;
 }
 
 static void pre_join(Groth16Pre* p) {
   if (p && p->running) {
     p->th1.join();
     p->th2.join();
+    if (p->th3.joinable()) p->th3.join();
     p->running = false;
   }
 }
@@ -588,7 +662,7 @@ static void pre_start(zkb_groth16_pk* pk, const uint64_t r[4], const uint64_t s[
   if (!pk->pre) pk->pre = new Groth16Pre();
   Groth16Pre* p = pk->pre;
   pre_join(p);
-  p->early = false;   // whatever was derived from an earlier (r, s) is void
+  p->early = p->folded = p->has_p0 = false;   // whatever was derived from an earlier (r, s) is void
   memcpy(p->r, r, 32);
   memcpy(p->s, s, 32);
   const int curve = pk->curve;
@@ -624,6 +698,18 @@ static void pre_start(zkb_groth16_pk* pk, const uint64_t r[4], const uint64_t s[
     const uint64_t* sc[1] = {p->s};
     host_lincomb(curve, 2, 1, pt, infs, sc, p->sd2, &p->inf_sd2);
   });
+  if (pk->wworld != 1 || pk->len != pk->n || pk->klen != pk->n_kdelta) {
+    // a shard of a multi-GPU proof: P0 = s alpha + r beta_1 + (r s) delta_1 for the folded assembly (Groth16Pre)
+    p->th3 = std::thread([pk, p, curve, g1, inf_d1]() {
+      uint64_t rs[4];
+      host_fr_mul(curve, p->r, p->s, rs);
+      const uint64_t* pt[3] = {pk->alpha1, pk->beta1, pk->delta1};
+      int infs[3] = {is_zero_pt(pk->alpha1, g1), is_zero_pt(pk->beta1, g1), inf_d1};
+      const uint64_t* sc[3] = {p->s, p->r, rs};
+      host_lincomb(curve, 1, 3, pt, infs, sc, p->p0, &p->inf_p0);
+    });
+    p->has_p0 = true;
+  }
   p->running = true;
   p->valid = true;
 }
@@ -634,9 +720,41 @@ int zkb_groth16_precompute(zkb_groth16_pk* pk, const uint64_t r[4], const uint64
   return ZKB_OK;
 }
 
+// folded: slot 3 is sum_i ([H Z]_i + s [U]_i + r [V]_i) (Groth16Pre): A, B and C are point additions only
+static int assemble_folded(zkb_groth16_pk* pk, const uint64_t* msm_xy, const int* msm_inf, const uint64_t r[4], const uint64_t s[4],
+                           uint64_t* out_a, uint64_t* out_b, uint64_t* out_c, int out_inf[3]) {
+  const int curve = pk->curve;
+  if (!pk->pre || !pk->pre->valid || !pk->pre->has_p0 || memcmp(pk->pre->r, r, 32) || memcmp(pk->pre->s, s, 32))
+    return set_error(ZKB_ERR_ARG, "folded partial sums need zkb_groth16_precompute with the same (r, s) on a sharded key");
+  Groth16Pre* pre = pk->pre;
+  pre_join(pre);
+  pre->valid = false;   // r and s are one-time values
+  const size_t g1 = affine_bytes(curve, 1), g2 = affine_bytes(curve, 2);
+  const uint64_t* mx[5];
+  for (int i = 0; i < 5; i++) mx[i] = msm_xy + i * 24;
+  const uint64_t* none[3] = {nullptr, nullptr, nullptr};
+  {
+    const uint64_t* pts[3] = {mx[0], pk->alpha1, pre->rd1};
+    int infs[3] = {msm_inf[0] & 1, is_zero_pt(pk->alpha1, g1), pre->inf_rd1};
+    host_lincomb(curve, 1, 3, pts, infs, none, out_a, &out_inf[0]);
+  }
+  {
+    const uint64_t* pts[3] = {mx[2], pk->beta2, pre->sd2};
+    int infs[3] = {msm_inf[2] & 1, is_zero_pt(pk->beta2, g2), pre->inf_sd2};
+    host_lincomb(curve, 2, 3, pts, infs, none, out_b, &out_inf[1]);
+  }
+  {
+    const uint64_t* pts[3] = {mx[3], mx[4], pre->p0};
+    int infs[3] = {msm_inf[3] & 1, msm_inf[4] & 1, pre->inf_p0};
+    host_lincomb(curve, 1, 3, pts, infs, none, out_c, &out_inf[2]);
+  }
+  return ZKB_OK;
+}
+
 int zkb_groth16_assemble(zkb_groth16_pk* pk, const uint64_t* msm_xy, const int* msm_inf, const uint64_t r[4], const uint64_t s[4],
                          uint64_t* out_a, uint64_t* out_b, uint64_t* out_c, int out_inf[3]) {
   if (!pk) return set_error(ZKB_ERR_ARG, "null proving key");
+  if (msm_inf[3] & ZKB_SLOT_FOLDED) return assemble_folded(pk, msm_xy, msm_inf, r, s, out_a, out_b, out_c, out_inf);
   const int curve = pk->curve;
   // proof assembly, protocol.py:133-165:
   //   A = [U] + alpha + r delta,  B = [V] + beta + s delta  (in G1 and in G2),
@@ -720,13 +838,46 @@ int zkb_groth16_assemble_partials(zkb_groth16_pk* pk, int world, const uint64_t*
   int sum_inf[5];
   memset(sum_xy, 0, sizeof(sum_xy));
   const int curve = pk->curve;
+  int n_folded = 0;
+  for (int k = 0; k < world; k++) n_folded += (all_inf[k * 5 + 3] & ZKB_SLOT_FOLDED) ? 1 : 0;
+  if (n_folded != 0 && n_folded != world)
+    return set_error(ZKB_ERR_ARG, "partial sums of some ranks carry the folded s [U] + r [V] term and others do not");
+  Groth16Pre* pre = pk->pre;
+  if (n_folded && pre && pre->valid && pre->has_p0 && !memcmp(pre->r, r, 32) && !memcmp(pre->s, s, 32)) {
+    // folded partial sums: A, B and C are three independent sums of points -- one lincomb (one affine conversion) each, side by
+    // side:  A = sum_i [U]_i + alpha + r delta_1,  B = sum_i [V]_i + beta_2 + s delta_2,  C = sum_i (HZ'_i + KW_i) + P0
+    pre_join(pre);
+    pre->valid = false;   // r and s are one-time values
+    const int curve = pk->curve;
+    const size_t g1 = affine_bytes(curve, 1), g2 = affine_bytes(curve, 2);
+    auto sum = [&](int grp, std::initializer_list<int> slots, std::initializer_list<const uint64_t*> extra,
+                   std::initializer_list<int> extra_inf, uint64_t* out, int* out_i) {
+      std::vector<const uint64_t*> pts;
+      std::vector<int> infs;
+      for (int slot : slots)
+        for (int k = 0; k < world; k++) {
+          pts.push_back(all_xy + ((size_t)k * 5 + slot) * 24);
+          infs.push_back(all_inf[k * 5 + slot] & 1);
+        }
+      pts.insert(pts.end(), extra.begin(), extra.end());
+      infs.insert(infs.end(), extra_inf.begin(), extra_inf.end());
+      std::vector<const uint64_t*> sc(pts.size(), nullptr);
+      host_lincomb(curve, grp, (int)pts.size(), pts.data(), infs.data(), sc.data(), out, out_i);
+    };
+    std::thread tb([&]() { sum(2, {2}, {pk->beta2, pre->sd2}, {is_zero_pt(pk->beta2, g2), pre->inf_sd2}, out_b, &out_inf[1]); });
+    std::thread tc([&]() { sum(1, {3, 4}, {pre->p0}, {pre->inf_p0}, out_c, &out_inf[2]); });
+    sum(1, {0}, {pk->alpha1, pre->rd1}, {is_zero_pt(pk->alpha1, g1), pre->inf_rd1}, out_a, &out_inf[0]);
+    tb.join();
+    tc.join();
+    return ZKB_OK;
+  }
   auto add_slot = [&](int slot) {
     const int grp = slot == 2 ? 2 : 1;
     std::vector<const uint64_t*> pts(world), sc(world, nullptr);
     std::vector<int> infs(world);
     for (int k = 0; k < world; k++) {
       pts[k] = all_xy + ((size_t)k * 5 + slot) * 24;
-      infs[k] = all_inf[k * 5 + slot];
+      infs[k] = all_inf[k * 5 + slot] & 1;
     }
     host_lincomb(curve, grp, world, pts.data(), infs.data(), sc.data(), sum_xy[slot], &sum_inf[slot]);
   };
@@ -734,6 +885,7 @@ int zkb_groth16_assemble_partials(zkb_groth16_pk* pk, int world, const uint64_t*
   for (int slot = 1; slot < 5; slot++) th[slot - 1] = std::thread(add_slot, slot);
   add_slot(0);
   for (int i = 0; i < 4; i++) th[i].join();
+  if (n_folded) sum_inf[3] |= ZKB_SLOT_FOLDED;
   return zkb_groth16_assemble(pk, &sum_xy[0][0], sum_inf, r, s, out_a, out_b, out_c, out_inf);
 }
 
@@ -749,8 +901,9 @@ int zkb_groth16_prove_dev(zkb_groth16_pk* pk, const void* d_a, const void* d_b, 
   char* w = pk->work;
   void *d_u = w + 3 * bytes, *d_v = w + 4 * bytes, *d_w = w + 5 * bytes, *d_h = w + 6 * bytes;
   int rc;
-  if ((rc = groth16_h_dev(pk->curve, pk->log_n, d_a, d_b, d_c, d_u, d_v, d_w, d_h, 1))) return rc;
+  if ((rc = groth16_h_dev(pk->curve, pk->log_n, d_a, d_b, d_c, d_u, d_v, d_w, d_h, 2))) return rc;
   if ((rc = groth16_msms(pk, d_priv))) return rc;
+  if ((rc = groth16_flag_result())) return rc;
   return zkb_groth16_assemble(pk, &pk->msm_xy[0][0], pk->msm_inf, r, s, out_a, out_b, out_c, out_inf);
 }
 
@@ -939,21 +1092,24 @@ static void presort_uv(void* arg) {   // called by groth16_h_dev when U and V ar
     c->rc = set_error(ZKB_ERR_CUDA, "presort fork failed");
     return;
   }
-  c->rc = msm_presort(c->pk->curve, c->job[0], c->pk->wrank, c->pk->wworld, &g16_tk[0], c->sort_st);        // V (shared by B1, B2)
-  if (!c->rc) c->rc = msm_presort(c->pk->curve, c->job[1], c->pk->wrank, c->pk->wworld, &g16_tk[1], c->sort_st);   // U
+  const int b2 = groth16_pos(c->pk, MSM_B2), a = groth16_pos(c->pk, MSM_A);
+  c->rc = msm_presort(c->pk->curve, c->job[b2], c->pk->wrank, c->pk->wworld, &g16_tk[b2], c->sort_st);   // V (B1 shares it)
+  if (!c->rc) c->rc = msm_presort(c->pk->curve, c->job[a], c->pk->wrank, c->pk->wworld, &g16_tk[a], c->sort_st);   // U
 }
 static int partial_from_resident_witness(zkb_groth16_pk* pk, zkb_r1cs* r1cs, size_t n_public) {
   const size_t bytes = pk->n * 32;
   char* w = pk->work;
   const void* d_priv = (char*)r1cs->w + n_public * 32;
   int rc;
+  // the satisfiability answer is read AFTER the MSMs (check == 2): nothing stops the host between the transforms and the batch
   static const bool presort_on = [] { const char* e = getenv("ZKB_PRESORT"); return !e || atoi(e) != 0; }();
   if (!presort_on || pk->log_n < 12) {
     if ((rc = r1cs_spmv3(r1cs, pk->n, w, w + bytes, w + 2 * bytes))) return rc;
     if ((rc = groth16_h_dev(pk->curve, pk->log_n, w, w + bytes, w + 2 * bytes, w + 3 * bytes, w + 4 * bytes, w + 5 * bytes,
-                            w + 6 * bytes, 1)))
+                            w + 6 * bytes, 2)))
       return rc;
-    return groth16_msms(pk, d_priv);
+    if ((rc = groth16_msms(pk, d_priv))) return rc;
+    return groth16_flag_result();
   }
   static cudaEvent_t ev = nullptr;
   if (!ev) ZKB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -975,24 +1131,24 @@ static int partial_from_resident_witness(zkb_groth16_pk* pk, zkb_r1cs* r1cs, siz
   // the witness is reduced and resident (r1cs_load_witness, library stream): its sort can start here
   if (cudaEventRecord(ev, S()) != cudaSuccess || cudaStreamWaitEvent(ctx.sort_st, ev, 0) != cudaSuccess)
     return done(set_error(ZKB_ERR_CUDA, "presort fork failed"));
-  if ((rc = msm_presort(pk->curve, ctx.job[4], pk->wrank, pk->wworld, &g16_tk[4], ctx.sort_st))) return done(rc);
+  const int kw = groth16_pos(pk, MSM_KW);
+  if ((rc = msm_presort(pk->curve, ctx.job[kw], pk->wrank, pk->wworld, &g16_tk[kw], ctx.sort_st))) return done(rc);
   if ((rc = r1cs_spmv3(r1cs, pk->n, w, w + bytes, w + 2 * bytes))) return done(rc);
   if ((rc = groth16_h_dev(pk->curve, pk->log_n, w, w + bytes, w + 2 * bytes, w + 3 * bytes, w + 4 * bytes, w + 5 * bytes,
-                          w + 6 * bytes, 1, presort_uv, &ctx)))
+                          w + 6 * bytes, 2, presort_uv, &ctx)))
     return done(rc);
   if (ctx.rc) return done(ctx.rc);
-  return done(groth16_msms(pk, d_priv));
+  if ((rc = groth16_msms(pk, d_priv))) return done(rc);
+  return done(groth16_flag_result());
 }
 
-// ---- chain spreading (several GPUs): zkb_groth16_spread_begin .. the caller's broadcasts .. zkb_groth16_spread_finish -------
-// What zkb_groth16_partial does in one call, cut where the ranks exchange data.  begin: witness -> A.w, B.w, C.w (every rank: the
-// SpMVs are cheap and the satisfiability check needs all three) -> the chains of `chain_mask` (bit c: 0 U, 1 V, 2 W): coefficients
-// into d_coeffs + c n, coset evaluations into d_evals + c n (caller-owned device buffers of 3 n elements each).  The caller then
-// broadcasts coefficient vectors 0, 1 and evaluation vectors 0, 1, 2 from their owners ON THE LIBRARY STREAM.  finish: U, V ->
-// the key's scalar slots, H from the three evaluation vectors, the five MSMs of this rank's window shard.
-// The scratch arena stays held between the two calls (the private-witness digit sort already runs on the sort stream).
+// ---- chain spreading (several GPUs): zkb_groth16_spread_begin .. exchange .. [_quotient] .. exchange .. zkb_groth16_spread_finish ----
+// What zkb_groth16_partial does in one call, cut where the ranks exchange data (the steps are spelled out in include/zkb200.h and
+// driven by zksnake_b200/dist.py:exchange_chains).  The scratch arena stays held from begin to finish: the private-witness digit
+// sort (and, on a rank without a chain, the whole [K w] MSM) is already running when begin returns.
 static struct SpreadState {
   bool active = false;
+  bool kw_enqueued = false;
   zkb_groth16_pk* pk = nullptr;
   int* flag = nullptr;
   void* tmp = nullptr;
@@ -1000,8 +1156,10 @@ static struct SpreadState {
 } g_spread;
 static void spread_drop() {
   for (int i = 0; i < 5; i++) msm_presort_cancel(&g16_tk[i]);
+  for (int i = 0; i < 5; i++)   // error paths: reductions of unjoined batches may still run on the arena (collected tickets are empty)
+    if (!g16_tk[i].empty && g16_tk[i].event) cudaStreamWaitEvent(S(), (cudaEvent_t)g16_tk[i].event, 0);
   scratch_hold_end();
-  g_spread.active = false;
+  g_spread.active = g_spread.kw_enqueued = false;
 }
 int zkb_groth16_spread_begin(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const void* witness, int witness_on_device, size_t n_public,
                              unsigned chain_mask, void* d_coeffs, void* d_evals) {
@@ -1010,6 +1168,8 @@ int zkb_groth16_spread_begin(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const void* wit
   if (g_spread.active) spread_drop();
   if ((rc = prove_witness_checks(pk, r1cs, n_public))) return rc;
   if (!d_coeffs || !d_evals || chain_mask > 7) return set_error(ZKB_ERR_ARG, "spread: bad argument");
+  if (pk->wworld < 2 || groth16_pos(pk, MSM_KW) != 0 || groth16_pos(pk, MSM_HZ) != 4)
+    return set_error(ZKB_ERR_ARG, "spread: the proving key must be a window shard of a multi-GPU proof");
   if ((rc = r1cs_load_witness(r1cs, witness, witness_on_device))) return rc;
   const size_t bytes = pk->n * 32;
   char* w = pk->work;
@@ -1017,12 +1177,15 @@ int zkb_groth16_spread_begin(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const void* wit
   if (!g_spread.ev) ZKB_CUDA(cudaEventCreateWithFlags(&g_spread.ev, cudaEventDisableTiming));
   cudaStream_t sort_st = (cudaStream_t)ctx_side_stream(7);
   if (!sort_st) return set_error(ZKB_ERR_CUDA, "cannot create the sort stream");
+  int* hflag = groth16_flag_host();
+  if (!hflag) return set_error(ZKB_ERR_CUDA, "cannot allocate the pinned flag");
   MsmJob job[5];
   groth16_jobs(pk, d_priv, job);
   size_t need_msm = 0;
   if ((rc = msm_batch_need(pk->curve, job, 5, pk->wrank, pk->wworld, &need_msm))) return rc;
   if ((rc = scratch_hold_begin(need_msm + bytes + (1 << 20)))) return rc;
   g_spread.active = true;
+  g_spread.kw_enqueued = false;
   g_spread.pk = pk;
   auto fail = [&](int code) {
     spread_drop();
@@ -1030,23 +1193,39 @@ int zkb_groth16_spread_begin(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const void* wit
   };
   if (cudaEventRecord(g_spread.ev, S()) != cudaSuccess || cudaStreamWaitEvent(sort_st, g_spread.ev, 0) != cudaSuccess)
     return fail(set_error(ZKB_ERR_CUDA, "presort fork failed"));
-  if ((rc = msm_presort(pk->curve, job[4], pk->wrank, pk->wworld, &g16_tk[4], sort_st))) return fail(rc);
+  if ((rc = msm_presort(pk->curve, job[0], pk->wrank, pk->wworld, &g16_tk[0], sort_st))) return fail(rc);   // [K w]: position 0
   g_spread.flag = (int*)scratch_take(256);
   g_spread.tmp = scratch_take(bytes);
   if (!g_spread.flag || !g_spread.tmp) return fail(set_error(ZKB_ERR_CUDA, "scratch exhausted"));
   if ((rc = r1cs_spmv3(r1cs, pk->n, w, w + bytes, w + 2 * bytes))) return fail(rc);
   if ((rc = groth16_check_dev(pk->curve, pk->log_n, w, w + bytes, w + 2 * bytes, g_spread.flag))) return fail(rc);
+  if (ZKB_D2H(hflag, g_spread.flag, sizeof(int)) != cudaSuccess) return fail(set_error(ZKB_ERR_CUDA, "spread: flag copy failed"));
   for (int c = 0; c < 3; c++)
     if (chain_mask >> c & 1)
       if ((rc = groth16_chain_dev(pk->curve, pk->log_n, c, w + c * bytes, (char*)d_coeffs + c * bytes, (char*)d_evals + c * bytes,
                                   g_spread.tmp)))
         return fail(rc);
+  if (!chain_mask) {
+    // nothing to transform on this rank: [K w] needs the witness only, so it runs while the chain owners work
+    if ((rc = groth16_enqueue(pk, d_priv, 0, 1, false))) return fail(rc);
+    g_spread.kw_enqueued = true;
+  }
   return ZKB_OK;
 }
-int zkb_groth16_spread_finish(zkb_groth16_pk* pk, zkb_r1cs* r1cs, size_t n_public, const void* d_coeffs, void* d_evals,
-                              uint64_t* msm_xy, int* msm_inf) {
+int zkb_groth16_spread_quotient(zkb_groth16_pk* pk, void* d_evals, void* d_h) {
   NEED_INIT();
-  if (!g_spread.active || g_spread.pk != pk || !r1cs) return set_error(ZKB_ERR_ARG, "spread: finish without begin");
+  if (!g_spread.active || g_spread.pk != pk || !d_evals || !d_h) return set_error(ZKB_ERR_ARG, "spread: quotient without begin");
+  const size_t bytes = pk->n * 32;
+  char* e = (char*)d_evals;
+  int rc = groth16_hfin_dev(pk->curve, pk->log_n, e, e + bytes, e + 2 * bytes, d_h, g_spread.tmp);
+  if (rc) spread_drop();
+  return rc;
+}
+int zkb_groth16_spread_finish(zkb_groth16_pk* pk, zkb_r1cs* r1cs, size_t n_public, const void* d_coeffs, const void* d_h,
+                              void* h_ready_event, uint64_t* msm_xy, int* msm_inf) {
+  NEED_INIT();
+  if (!g_spread.active || g_spread.pk != pk || !r1cs || !d_coeffs || !d_h)
+    return set_error(ZKB_ERR_ARG, "spread: finish without begin");
   int rc;
   const size_t bytes = pk->n * 32;
   char* w = pk->work;
@@ -1066,15 +1245,23 @@ int zkb_groth16_spread_finish(zkb_groth16_pk* pk, zkb_r1cs* r1cs, size_t n_publi
   groth16_jobs(pk, d_priv, ctx.job);
   presort_uv(&ctx);
   if (ctx.rc) return done(ctx.rc);
-  char* e = (char*)d_evals;
-  if ((rc = groth16_hfin_dev(pk->curve, pk->log_n, e, e + bytes, e + 2 * bytes, w + 6 * bytes, g_spread.tmp))) return done(rc);
-  int hflag = 0;
-  if (ZKB_D2H(&hflag, g_spread.flag, sizeof(int)) != cudaSuccess || cudaStreamSynchronize(S()) != cudaSuccess)
-    return done(set_error(ZKB_ERR_CUDA, "spread: flag readback failed"));
-  if (hflag) return done(set_error(ZKB_ERR_NOT_DIVISIBLE, "(U * V - W) did not divided by Z to zero"));
-  if ((rc = groth16_msms(pk, d_priv))) return done(rc);
-  memcpy(msm_xy, pk->msm_xy, sizeof(pk->msm_xy));
-  memcpy(msm_inf, pk->msm_inf, sizeof(pk->msm_inf));
+  // the MSMs that need U, V and the witness only; H is still on its way on most ranks
+  const int first = g_spread.kw_enqueued ? 1 : 0, last = 4;   // shard order: KW, B2, A, B1, HZ
+  if ((rc = groth16_enqueue(pk, d_priv, first, last - first, false))) return done(rc);
+  // H: complete in d_h once h_ready_event has fired (recorded by the caller on the stream its exchange ran on; null: d_h is already
+  // ordered on the library stream)
+  if (h_ready_event && cudaStreamWaitEvent(S(), (cudaEvent_t)h_ready_event, 0) != cudaSuccess)
+    return done(set_error(ZKB_ERR_CUDA, "spread: cannot wait for the quotient"));
+  if (cudaMemcpyAsync(w + 6 * bytes, d_h, bytes, cudaMemcpyDeviceToDevice, S()) != cudaSuccess)
+    return done(set_error(ZKB_ERR_CUDA, "spread: copy failed"));
+  if ((rc = groth16_enqueue(pk, d_priv, last, 1, true))) return done(rc);
+  for (int i = 0; i < last; i++)   // (the unjoined batches: order the library stream behind their reductions too)
+    if (!g16_tk[i].empty && g16_tk[i].event && cudaStreamWaitEvent(S(), (cudaEvent_t)g16_tk[i].event, 0) != cudaSuccess)
+      return done(set_error(ZKB_ERR_CUDA, "spread: join failed"));
+  g_spread.kw_enqueued = false;
+  if ((rc = groth16_collect(pk))) return done(rc);
+  if ((rc = groth16_flag_result())) return done(rc);
+  groth16_export_partials(pk, msm_xy, msm_inf);
   return done(ZKB_OK);
 }
 
@@ -1085,8 +1272,7 @@ int zkb_groth16_partial(zkb_groth16_pk* pk, zkb_r1cs* r1cs, const void* witness,
   if ((rc = prove_witness_checks(pk, r1cs, n_public))) return rc;
   if ((rc = r1cs_load_witness(r1cs, witness, witness_on_device))) return rc;
   if ((rc = partial_from_resident_witness(pk, r1cs, n_public))) return rc;
-  memcpy(msm_xy, pk->msm_xy, sizeof(pk->msm_xy));
-  memcpy(msm_inf, pk->msm_inf, sizeof(pk->msm_inf));
+  groth16_export_partials(pk, msm_xy, msm_inf);
   return ZKB_OK;
 }
 

@@ -50,6 +50,14 @@ EntryGuard::~EntryGuard() {
   g_entry_depth--;
 }
 void* ctx_stream() { return (void*)g_ctx.stream; }
+// Every launch helper of the library takes its stream from ctx_stream(); a stage that has to run beside the library stream (the
+// quotient's last step on the exchange stream of a multi-GPU proof, api.cu) swaps it for the duration of its enqueue calls and
+// swaps it back.  Single host thread by contract (EntryGuard), so a plain global is enough.
+void* ctx_stream_swap(void* s) {
+  void* old = (void*)g_ctx.stream;
+  g_ctx.stream = (cudaStream_t)s;
+  return old;
+}
 void* ctx_side_stream(int i) {
   if (i < 0 || i >= 8) return nullptr;
   if (!g_ctx.side[i] && cudaStreamCreateWithFlags(&g_ctx.side[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;

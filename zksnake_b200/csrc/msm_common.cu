@@ -129,8 +129,9 @@ void msm_presort_cancel(MsmTicket* tk) {
   if (tk->presorted && tk->sort_event) cudaStreamWaitEvent((cudaStream_t)ctx_stream(), (cudaEvent_t)tk->sort_event, 0);
   tk->presorted = false;
 }
-int msm_enqueue_batch(int curve, const MsmJob* jobs, int njobs, uint32_t wr, uint32_t ww, MsmTicket* tickets) {
-  if (njobs > 8) return set_error(ZKB_ERR_ARG, "msm batch: at most 8 jobs");
+int msm_enqueue_batch(int curve, const MsmJob* jobs, int njobs, uint32_t wr, uint32_t ww, MsmTicket* tickets, bool join,
+                      int side_base) {
+  if (njobs > 8 || side_base < 0) return set_error(ZKB_ERR_ARG, "msm batch: at most 8 jobs");
   size_t total = 0;
   int rc;
   // a ticket whose digit sort was enqueued ahead of this call (msm_presort) must be for exactly this job; it took its scratch then
@@ -221,7 +222,7 @@ int msm_enqueue_batch(int curve, const MsmJob* jobs, int njobs, uint32_t wr, uin
     if (tickets[i].empty) continue;
     cudaError_t ce = cudaSuccess;
     if (!fork_ev[i]) ce = cudaEventCreateWithFlags(&fork_ev[i], cudaEventDisableTiming);
-    cudaStream_t side = (cudaStream_t)ctx_side_stream(i);
+    cudaStream_t side = (cudaStream_t)ctx_side_stream((side_base + i) % 7);   // (side stream 7 is the sort stream)
     if (ce != cudaSuccess || !side) return fail(set_error(ZKB_ERR_CUDA, "msm batch: cannot create a side stream"));
     if ((ce = cudaEventRecord(fork_ev[i], main_st)) != cudaSuccess || (ce = cudaStreamWaitEvent(side, fork_ev[i], 0)) != cudaSuccess)
       return fail(cuda_fail((int)ce, "msm batch fork", __FILE__, __LINE__));
@@ -232,6 +233,7 @@ int msm_enqueue_batch(int curve, const MsmJob* jobs, int njobs, uint32_t wr, uin
       return fail(rc);
     }
   }
+  if (!join) return ZKB_OK;       // the caller enqueues more work first and joins the tickets' events itself
   prof_begin(PROF_MSM_REDUCE);   // what is left of the reductions after the last accumulation
   for (int i = 0; i < njobs; i++)
     if (!tickets[i].empty) ZKB_CUDA(cudaStreamWaitEvent(main_st, (cudaEvent_t)tickets[i].event, 0));

@@ -419,6 +419,14 @@ int fr_powers_dev(int curve, const uint64_t* base, const uint64_t* scale, size_t
 //   iNTT(2n), subtract, divide_by_vanishing_poly).  H is unique, so it is computed here on the coset g*<w> of the SAME size n:
 //   3 iNTT(n) + 3 coset-NTT(n) + pointwise + 1 coset-iNTT(n); Z is the constant g^n - 1 on that coset.
 // ------------------------------------------------------------------------------------------------------
+// One pinned int for the satisfiability flag of check_abc_kernel when the caller defers the test (check == 2): the copy is
+// enqueued behind the kernel and nobody waits for it -- a proof that is going to fail fails after its MSMs instead of before them,
+// and a proof that is not (every proof but a caller's mistake) never stops the host between the transforms and the MSM batch.
+int* groth16_flag_host() {
+  static int* p = nullptr;
+  if (!p && cudaHostAlloc((void**)&p, 64, cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+  return p;
+}
 template <class F>
 static int groth16_h_t(uint32_t log_n, const void* d_a, const void* d_b, const void* d_c, void* d_u, void* d_v, void* d_w,
                        void* d_h, int check, void (*after_interp)(void*), void* arg) {
@@ -445,6 +453,11 @@ static int groth16_h_t(uint32_t log_n, const void* d_a, const void* d_b, const v
     check_abc_kernel<F><<<blocks, 256, 0, S()>>>(n, (const F*)d_a, (const F*)d_b, (const F*)d_c, flag);
     prof_end(PROF_VEC);
     count_launch();
+    if (check == 2) {   // deferred: the caller reads groth16_flag_host() once later work of this stream is known to be complete
+      int* hf = groth16_flag_host();
+      if (!hf) return set_error(ZKB_ERR_CUDA, "cannot allocate the pinned flag");
+      ZKB_CUDA(ZKB_D2H(hf, flag, sizeof(int)));
+    }
   }
   PowTable<F> fwd = d->fwd.view(), inv_t = d->inv.view();
   PowTable<F> gpre = d->gen_pre.view(), gpre_r = d->gen_pre_r.view(), gpost = d->gen_post.view();
@@ -468,7 +481,7 @@ static int groth16_h_t(uint32_t log_n, const void* d_a, const void* d_b, const v
   }
   if ((rc = vec_op_t<F>(VEC_MULSUB_RAW, n, ea, n, eb, n, ec, ea))) return rc;                  // (U V - W)/R on the coset
   if ((rc = ntt_exec<F>(ea, n, H, log_n, inv_t, nullptr, &gpost, nullptr, tmp))) return rc;
-  if (check) {
+  if (check == 1) {
     int hflag = 0;
     ZKB_CUDA(ZKB_D2H(&hflag, flag, sizeof(int)));
     ZKB_CUDA(cudaStreamSynchronize(S()));

@@ -44,6 +44,7 @@ struct EntryGuard {
   if (!guard_.ok) return zkb::set_error(ZKB_ERR_ARG, "libzkb200 entry points are not re-entrant: another host thread is inside the library")
 
 void* ctx_stream();                 // cudaStream_t
+void* ctx_stream_swap(void* s);     // make `s` the stream every helper enqueues on; returns the previous one (core.cu)
 void* ctx_side_stream(int i);       // cudaStream_t, i < 8 (created on first use); nullptr on failure
 bool ctx_ready();
 // grow-only device scratch arena; `scratch_reset` starts a new allocation epoch (pointers from the previous epoch die)
@@ -77,8 +78,11 @@ int fr_powers_dev(int curve, const uint64_t* base, const uint64_t* scale, size_t
 // MSM scalars) and H (n coeffs, top one zero).  d_w is scratch for W.  Returns ZKB_ERR_NOT_DIVISIBLE when a.b != c.
 // after_interp(arg), when given, is called once the three interpolations are enqueued: U and V (the MSM scalars) are final on the
 // library stream from there on, while four more transforms follow -- the caller forks the digit sorts of the U / V MSMs there.
+// check: 0 none | 1 test a.b == c and wait for the answer | 2 test it, leave the answer in *groth16_flag_host() (pinned; non-zero =
+// not satisfied) and do not wait: valid once any later work of the library stream is known to have completed.
 int groth16_h_dev(int curve, uint32_t log_n, const void* d_a, const void* d_b, const void* d_c, void* d_u, void* d_v,
                   void* d_w, void* d_h, int check, void (*after_interp)(void*) = nullptr, void* arg = nullptr);
+int* groth16_flag_host();
 // the same pipeline step by step (multi-GPU chain spreading): witness check, one interpolation -> coset-evaluation chain
 // (which: 0 U, 1 V, 2 W), and H from the three coset evaluation vectors; d_tmp holds 2^log_n elements
 int groth16_check_dev(int curve, uint32_t log_n, const void* d_a, const void* d_b, const void* d_c, int* d_flag);
@@ -152,7 +156,11 @@ int msm_enqueue(int curve, const MsmJob& job, uint32_t wrank, uint32_t wworld, M
 int msm_table_build(int curve, int group, const void* d_pts, size_t n, uint32_t world, uint32_t* c, uint32_t* W, void* d_table);
 // A batch: phase 1 (sort + accumulate) of every job back to back on the library stream, then all phase 2s (the latency-bound
 // folds / bucket reductions) concurrently on side streams, joined back into the library stream.
-int msm_enqueue_batch(int curve, const MsmJob* jobs, int njobs, uint32_t wrank, uint32_t wworld, MsmTicket* tickets);
+// join = false: the library stream is NOT ordered behind the reductions (the caller goes on enqueueing -- another batch, an exchange
+// step -- and waits for the tickets' events later); side_base: first of the seven side streams the reductions use, so
+// that consecutive unjoined batches do not queue their reductions behind each other.
+int msm_enqueue_batch(int curve, const MsmJob* jobs, int njobs, uint32_t wrank, uint32_t wworld, MsmTicket* tickets,
+                      bool join = true, int side_base = 0);
 int msm_finish(MsmTicket* tk, uint64_t* out_xy, int* out_inf);
 int msm_dev(int curve, int group, const void* d_points, const void* d_scalars, size_t n, uint64_t* out_xy, int* out_inf);
 int points_to_mont_dev(int curve, int group, size_t n, void* d_points);

@@ -94,12 +94,16 @@ def upload_sharded(arr):
 
 
 # ---- the three interpolation -> coset-evaluation chains of the Groth16 quotient, one per rank ---------------------------------------
-# QAP.evaluate_witness (/root/reference/python/zksnake/groth16/qap.py:57-63) transforms A.w, B.w and C.w independently.  On one GPU
-# they are one batched launch per pass; on several, rank chain_owner(c) runs chain c alone (zkb_groth16_spread_begin) and the five
-# vectors the other ranks need -- U and V (the MSM scalars of every rank's window shard) and the three coset evaluation vectors (for
-# H) -- are broadcast over NVLink on the library stream; every rank then forms H itself (one fused kernel + one inverse transform,
-# zkb_groth16_spread_finish).  Per rank: 2 (or 4, two ranks) + 1 transforms instead of 7.
+# QAP.evaluate_witness (/root/reference/python/zksnake/groth16/qap.py:57-69) transforms A.w, B.w and C.w independently and then forms
+# H from the three results.  On one GPU the chains are one batched launch per pass; on several, rank chain_owner(c) runs chain c alone
+# (zkb_groth16_spread_begin), U and V -- the MSM scalars of every rank's window shard -- are broadcast over NVLink on the library
+# stream, the three coset evaluation vectors go point to point to ONE rank, quotient_owner(), which forms H (one fused kernel + one
+# inverse transform, zkb_groth16_spread_quotient) and broadcasts it.  On every other rank that last exchange runs on a second stream
+# beside the MSMs over U, V and the witness; only the [H Z] MSM, the last of the batch, waits for it (zkb_groth16_spread_finish).
+# Per rank: 2 transforms (chain owners), 1 (the quotient rank) or none, instead of 7; a rank without a chain runs its [K w] MSM while
+# the owners transform.  Two ranks: rank 0 takes the U and W chains, rank 1 the V chain and the quotient (4 + 3 transforms).
 _spread_bufs = {}
+_spread_state = {}
 
 
 def chain_owner(chain, world_size):
@@ -111,30 +115,63 @@ def chain_mask(rank, world_size):
     return sum(1 << c for c in range(3) if chain_owner(c, world_size) == rank)
 
 
+def quotient_owner(world_size):
+    """Rank that forms H from the three coset evaluation vectors: the first rank without a chain (four ranks or more), else the
+    rank with the least transform work (the W owner of three ranks, the V owner of two)."""
+    return 3 if world_size >= 4 else world_size - 1
+
+
 def spread_buffers(n_elems):
-    """Two persistent device buffers of 3 * n_elems Fr elements (coefficients U|V|W, coset evaluations) as torch uint8 tensors."""
+    """Persistent device buffers as torch uint8 tensors: coefficients U|V|W (3 n Fr elements), coset evaluations (3 n), H (n)."""
     import torch
     bufs = _spread_bufs.get(n_elems)
     if bufs is None:
         with torch.cuda.stream(library_stream()):
             bufs = (torch.empty(3 * n_elems * 32, dtype=torch.uint8, device="cuda"),
-                    torch.empty(3 * n_elems * 32, dtype=torch.uint8, device="cuda"))
+                    torch.empty(3 * n_elems * 32, dtype=torch.uint8, device="cuda"),
+                    torch.empty(n_elems * 32, dtype=torch.uint8, device="cuda"))
         _spread_bufs[n_elems] = bufs
     return bufs
 
 
-def broadcast_chains(coeffs, evals, n_elems):
-    """The exchange step between zkb_groth16_spread_begin and _finish: U, V and the three evaluation vectors from their owners to
-    everybody, enqueued on the library stream (no host synchronisation)."""
+def exchange_chains(coeffs, evals, hbuf, n_elems, run_quotient):
+    """The exchange between zkb_groth16_spread_begin and _finish (see the comment above).  run_quotient() is called on the quotient
+    rank once its evaluation vectors are ordered on the library stream.  Returns the raw cudaEvent_t (int) behind which `hbuf` holds
+    H, or None where H is ordered on the library stream itself.  No host synchronisation anywhere."""
     import torch
     import torch.distributed as td
-    _, ws = world()
+    rank, ws = world()
     nb = n_elems * 32
-    with torch.cuda.stream(library_stream()):
+    lib = library_stream()
+    h = quotient_owner(ws)
+    st = _spread_state
+    if not st:
+        st["comm"] = torch.cuda.Stream()
+        st["chains"] = torch.cuda.Event()
+        st["h"] = torch.cuda.Event()
+    st["chains"].record(lib)                       # this rank's chains are complete here (before the broadcasts queue up)
+    with torch.cuda.stream(lib):
         for c in (0, 1):
             td.broadcast(coeffs[c * nb:(c + 1) * nb], src=chain_owner(c, ws))
-        for c in (0, 1, 2):
-            td.broadcast(evals[c * nb:(c + 1) * nb], src=chain_owner(c, ws))
+    senders = [(c, chain_owner(c, ws)) for c in range(3) if chain_owner(c, ws) != h]
+    if rank == h:
+        with torch.cuda.stream(lib):
+            for c, o in senders:
+                td.recv(evals[c * nb:(c + 1) * nb], src=o)
+            try:
+                run_quotient()
+            finally:
+                td.broadcast(hbuf, src=h)          # (issued even if the quotient failed: the other ranks are already waiting in it)
+        return None
+    comm = st["comm"]
+    with torch.cuda.stream(comm):
+        comm.wait_event(st["chains"])
+        for c, o in senders:
+            if o == rank:
+                td.send(evals[c * nb:(c + 1) * nb], dst=h)
+        td.broadcast(hbuf, src=h)
+        st["h"].record(comm)
+    return st["h"].cuda_event
 
 
 # ---- host-side exchange of small payloads between the ranks of ONE node -----------------------------------------------------
@@ -266,7 +303,7 @@ def add_partials(curve, all_xy, all_inf):
     for slot, grp in enumerate(SLOT_GROUP):
         limbs = nat.lib.zkb_affine_bytes(curve, grp) // 8
         pts = np.ascontiguousarray(all_xy[:, slot, :limbs])
-        infs = np.ascontiguousarray(all_inf[:, slot].astype(np.int32))
+        infs = np.ascontiguousarray((all_inf[:, slot] & 1).astype(np.int32))      # (bit 1 of the HZ slot: zkb200.h, "folded")
         scal = np.zeros((ws, 4), dtype=np.uint64)
         has = np.zeros(ws, dtype=np.int32)
         res = np.zeros(limbs, dtype=np.uint64)
@@ -275,6 +312,11 @@ def add_partials(curve, all_xy, all_inf):
                                             nat.ptr(res), ctypes.byref(inf)))
         out_xy[slot, :limbs] = res
         out_inf[slot] = inf.value
+    folded = int(np.count_nonzero(all_inf[:, 3] & 2))
+    if folded not in (0, ws):
+        raise ValueError("partial sums of some ranks carry the folded s [U] + r [V] term and others do not")
+    if folded:
+        out_inf[3] |= 2
     return out_xy, out_inf
 
 

@@ -9,6 +9,7 @@ randomness hook is the module-level `get_random_int`, the name the reference's h
 import ctypes
 import os
 import random
+import time
 
 import numpy as np
 
@@ -165,6 +166,7 @@ class Groth16:
         self._r1cs_handle = None
         self._bound_key = None
         self._staging = None
+        self.phase_ms = {}
         self._staging_ptr = None
 
     # ------------------------------------------------------------------------------------------------ setup
@@ -334,6 +336,7 @@ class Groth16:
                          nat.ptr(ob), nat.ptr(oc), inf))
         else:
             keep = None
+            t_ph = [time.perf_counter()]
             if not on_dev and dist.nccl_ready() and os.environ.get("ZKB_WITNESS_SHARDED", "1") != "0":
                 # each rank uploads 1/world of the witness; NVLink all-gather instead of world x the same PCIe transfer
                 keep = dist.upload_sharded(witness_limbs)
@@ -343,23 +346,32 @@ class Groth16:
             xy = np.zeros((dist.MSM_SLOTS, dist.SLOT_LIMBS), dtype=np.uint64)
             flags = np.zeros(dist.MSM_SLOTS, dtype=np.int32)
             if self._spread_chains():
-                # the three transform chains on three ranks (two: 2 + 1), results broadcast over NVLink on the library stream
-                coeffs, evals = dist.spread_buffers(self.n)
+                # the three transform chains on three ranks (two: 2 + 1), the quotient's last step on one; dist.exchange_chains
+                coeffs, evals, hbuf = dist.spread_buffers(self.n)
+                pc, pe, ph = (ctypes.c_void_p(t.data_ptr()) for t in (coeffs, evals, hbuf))
                 nat.check(nat.lib.zkb_groth16_spread_begin(self._pk_handle, self._r1cs_handle, wptr, int(on_dev), self.n_public,
-                                                           dist.chain_mask(self.rank, self.world),
-                                                           ctypes.c_void_p(coeffs.data_ptr()), ctypes.c_void_p(evals.data_ptr())))
-                dist.broadcast_chains(coeffs, evals, self.n)
-                nat.check(nat.lib.zkb_groth16_spread_finish(self._pk_handle, self._r1cs_handle, self.n_public,
-                                                            ctypes.c_void_p(coeffs.data_ptr()), ctypes.c_void_p(evals.data_ptr()),
-                                                            nat.ptr(xy), nat.ptr(flags)))
+                                                           dist.chain_mask(self.rank, self.world), pc, pe))
+                h_ready = dist.exchange_chains(
+                    coeffs, evals, hbuf, self.n,
+                    lambda: nat.check(nat.lib.zkb_groth16_spread_quotient(self._pk_handle, pe, ph)))
+                nat.check(nat.lib.zkb_groth16_spread_finish(self._pk_handle, self._r1cs_handle, self.n_public, pc, ph,
+                                                            ctypes.c_void_p(h_ready), nat.ptr(xy), nat.ptr(flags)))
             else:
                 nat.check(nat.lib.zkb_groth16_partial(self._pk_handle, self._r1cs_handle, wptr, int(on_dev), self.n_public,
                                                       nat.ptr(xy), nat.ptr(flags)))
+            t_ph.append(time.perf_counter())
             all_xy, all_inf = dist.all_gather_partials(xy, flags)
+            t_ph.append(time.perf_counter())
             all_xy = np.ascontiguousarray(all_xy)
             all_inf = np.ascontiguousarray(all_inf, dtype=np.int32)
             nat.check(nat.lib.zkb_groth16_assemble_partials(self._pk_handle, self.world, nat.ptr(all_xy), nat.ptr(all_inf), nat.ptr(rr),
                                                             nat.ptr(ss), nat.ptr(oa), nat.ptr(ob), nat.ptr(oc), inf))
+            t_ph.append(time.perf_counter())
+            # host-side phases of the sharded proof (ms): this rank's work up to its partial sums | waiting for the slowest rank in
+            # the exchange | the assembly after it; bench.py reports their means as `host_phases_ms`
+            for k, name in enumerate(("partial", "exchange", "assemble")):
+                self.phase_ms[name] = self.phase_ms.get(name, 0.0) + (t_ph[k + 1] - t_ph[k]) * 1e3
+            self.phase_ms["proofs"] = self.phase_ms.get("proofs", 0) + 1
         ec = self.ec
         return Proof(ec.PointG1._from_flat(oa, inf[0]), ec.PointG2._from_flat(ob, inf[1]), ec.PointG1._from_flat(oc, inf[2]))
 
@@ -368,7 +380,9 @@ class Groth16:
         vectors on every rank (window sharding) and a domain large enough for a broadcast to be cheaper than a transform."""
         if os.environ.get("ZKB_NTT_SPREAD", "1") == "0" or self._emulate or self.shard_mode != "windows":
             return False
-        return self.world > 1 and dist.nccl_ready() and self.n >= (1 << 16)
+        # (two ranks: measured both ways -- rank 0 runs two chains either way and the rank that forms H joins the MSMs late; 14.5 ms
+        # replicated, 14.5 ms with five broadcasts, 15.8 ms with the quotient on rank 1 -- so the chains stay replicated there)
+        return self.world > 2 and dist.nccl_ready() and self.n >= (1 << 16)
 
     def last_polys(self):
         """U, V, H coefficient lists of the last prove (n entries each, unstripped) for parity tests."""

@@ -468,7 +468,11 @@ int zkb_groth16_pk_build_tables(zkb_groth16_pk* pk, uint32_t world) {
   const int grp[4] = {1, 2, 1, 1};
   for (int i = 0; i < 4; i++) {
     if (pk->tab[i] || cnt[i] == 0) continue;
-    static const uint32_t force_c = [] { const char* e = getenv("ZKB_TABLE_C"); return e ? (uint32_t)atoi(e) : 0u; }();   // experiments
+    // ZKB_TABLE_C: window size of every table (experiments).  The cost model's choice was checked on the B200 at 2^20 BN254
+    // (profiles/R2z_n2_c*.json, R2z_n1_c20.json, R3a_n1_kw*.json): 1 GPU c = 19 / 14 windows 23.3 ms, c = 20 23.9; 2 GPUs c = 16 /
+    // 2 x 8 windows 14.5 ms, c = 18 15.0, c = 19 (2 x 7 windows over 2^18 buckets) 14.8, c = 20 17.0; a smaller window for the
+    // LAST MSM of the batch only (shorter exposed reduction, more additions) 23.23-23.68 against 23.26 ms: nothing to gain.
+    static const uint32_t force_c = [] { const char* e = getenv("ZKB_TABLE_C"); return e ? (uint32_t)atoi(e) : 0u; }();
     int rc = zkb_msm_table_create(pk->curve, grp[i], vec[i], cnt[i], force_c, world ? world : 1, &pk->tab[i]);
     if (rc) return rc;
   }
@@ -1250,6 +1254,8 @@ int zkb_groth16_spread_finish(zkb_groth16_pk* pk, zkb_r1cs* r1cs, size_t n_publi
   if ((rc = groth16_enqueue(pk, d_priv, first, last - first, false))) return done(rc);
   // H: complete in d_h once h_ready_event has fired (recorded by the caller on the stream its exchange ran on; null: d_h is already
   // ordered on the library stream)
+  // (sorting H on the sort stream as soon as it arrives, under the accumulations, was measured at 8 GPUs: 6.64 against 6.57 ms --
+  // the sort only gets the SM slots the persistent accumulation grid leaves, profiles/R2z_n8_hsort.json; it stays in line)
   if (h_ready_event && cudaStreamWaitEvent(S(), (cudaEvent_t)h_ready_event, 0) != cudaSuccess)
     return done(set_error(ZKB_ERR_CUDA, "spread: cannot wait for the quotient"));
   if (cudaMemcpyAsync(w + 6 * bytes, d_h, bytes, cudaMemcpyDeviceToDevice, S()) != cudaSuccess)

@@ -479,6 +479,20 @@ def main_own(args):
         allph = allph.cpu().reshape(world, 3).tolist()
         host_phases = {"partial": [round(r[0], 3) for r in allph], "exchange": [round(r[1], 3) for r in allph],
                        "assemble": [round(r[2], 3) for r in allph], "note": "per rank, mean ms per proof, device-resident leg"}
+        if zdist.SPREAD_TRACE is not None:      # ZKB_SPREAD_TRACE=1: device timestamps of the exchange steps, per rank
+            tk = ("chains", "uv", "recv", "quot", "h", "end")
+            cnt = max(zdist.SPREAD_TRACE.get("proofs", 0), 1)
+            tv = torch.tensor([zdist.SPREAD_TRACE.get(k, 0.0) / cnt for k in tk], dtype=torch.float64, device="cuda")
+            allt = torch.empty(world * len(tk), dtype=torch.float64, device="cuda")
+            td.all_gather_into_tensor(allt, tv)
+            allt = allt.cpu().reshape(world, len(tk)).tolist()
+            host_phases["device_trace_ms"] = {k: [round(r[i], 3) for r in allt] for i, k in enumerate(tk)}
+            pk_ = sorted(prof)
+            pv = torch.tensor([prof[k][0] / args.steps for k in pk_], dtype=torch.float64, device="cuda")
+            allp = torch.empty(world * len(pk_), dtype=torch.float64, device="cuda")
+            td.all_gather_into_tensor(allp, pv)
+            allp = allp.cpu().reshape(world, len(pk_)).tolist()
+            host_phases["breakdown_ms_per_rank"] = {k: [round(r[i], 3) for r in allp] for i, k in enumerate(pk_)}
 
     if rank != 0:
         if td is not None:
@@ -518,8 +532,14 @@ def main_own(args):
         per_launch_ms = acc_ms / acc_cnt
         # `achieved` counts what the kernel EXECUTES: W (this key's window count, not the canonical 16) XYZZ mixed additions of
         # 10 Fq products per point ("W = the implementation's window, report it")
-        executed = pts_per_launch * win_w * 10 * mul_ops / (per_launch_ms * 1e-3) / 1e12
-        canonical = pts_per_launch * ops_per_pt / (per_launch_ms * 1e-3) / 1e12
+        # (per proof there are four G1 MSMs of win_w / world windows each; with the chains spread over the ranks this rank's [K w]
+        # MSM covers prover._kw_windows[1] windows instead -- possibly none, then there are three launches: count the work per proof)
+        g1_msms = 4.0
+        if getattr(prover, "_kw_windows", None) is not None and args.shard_mode == "windows":
+            g1_msms = 3.0 + prover._kw_windows[1] / (win_w / world)
+        step_s = acc_ms / args.steps * 1e-3
+        executed = g1_msms * pts_per_launch * win_w * 10 * mul_ops / step_s / 1e12
+        canonical = g1_msms * pts_per_launch * ops_per_pt / step_s / 1e12
         roofline = {"kernel": "msm_accumulate_kernel<G1>", "bound": "int32-pipe", "achieved": executed,
                     "peak": peak_t, "unit": "T 32x32->64 multiply-add lane-ops/s (IMAD.WIDE)",
                     "frac": executed / peak_t,
@@ -536,7 +556,7 @@ def main_own(args):
         msm_all_ms = sum(prof[k][0] for k in ("msm_sort", "msm_accum_g1", "msm_accum_g2", "msm_reduce")) / args.steps
         # executed additions of ALL FIVE MSMs (the G2 mixed addition is 8 Fq2 products + 2 Fq2 squarings = 28 Fq products)
         # over all MSM kernels of the proof, sorts and reductions included
-        ops_step = pts_per_launch * win_w * mul_ops * (4 * 10 + 28)   # (28: the one-thread Karatsuba count, kept as the work unit)
+        ops_step = pts_per_launch * win_w * mul_ops * (g1_msms * 10 + 28)   # (28: the one-thread Karatsuba count, kept as the work unit)
         roofline["whole_msm_frac"] = ops_step / (msm_all_ms * 1e-3) / imad_wide.value if msm_all_ms else None
     roofline_g2 = None
     g2_ms, g2_cnt = prof["msm_accum_g2"]
@@ -750,6 +770,20 @@ def main_plonk(args):
         allph = allph.cpu().reshape(world, 3).tolist()
         host_phases = {"partial": [round(r[0], 3) for r in allph], "exchange": [round(r[1], 3) for r in allph],
                        "assemble": [round(r[2], 3) for r in allph], "note": "per rank, mean ms per proof, device-resident leg"}
+        if zdist.SPREAD_TRACE is not None:      # ZKB_SPREAD_TRACE=1: device timestamps of the exchange steps, per rank
+            tk = ("chains", "uv", "recv", "quot", "h", "end")
+            cnt = max(zdist.SPREAD_TRACE.get("proofs", 0), 1)
+            tv = torch.tensor([zdist.SPREAD_TRACE.get(k, 0.0) / cnt for k in tk], dtype=torch.float64, device="cuda")
+            allt = torch.empty(world * len(tk), dtype=torch.float64, device="cuda")
+            td.all_gather_into_tensor(allt, tv)
+            allt = allt.cpu().reshape(world, len(tk)).tolist()
+            host_phases["device_trace_ms"] = {k: [round(r[i], 3) for r in allt] for i, k in enumerate(tk)}
+            pk_ = sorted(prof)
+            pv = torch.tensor([prof[k][0] / args.steps for k in pk_], dtype=torch.float64, device="cuda")
+            allp = torch.empty(world * len(pk_), dtype=torch.float64, device="cuda")
+            td.all_gather_into_tensor(allp, pv)
+            allp = allp.cpu().reshape(world, len(pk_)).tolist()
+            host_phases["breakdown_ms_per_rank"] = {k: [round(r[i], 3) for r in allp] for i, k in enumerate(pk_)}
     if rank != 0:
         if td is not None:
             td.destroy_process_group()

@@ -221,6 +221,11 @@ void zkb_groth16_pk_free(zkb_groth16_pk* pk);
  * zkb_groth16_partial covers only window shard `rank` of `world`.  Scales better than point slices (the digit sort and the
  * bucket reduction shrink too); costs the whole key per GPU (320 MiB at 2^20 BN254). */
 int zkb_groth16_pk_set_window_shard(zkb_groth16_pk* pk, uint32_t rank, uint32_t world);
+/* ... except, when enabled, for the MSM over the private witness ([K w], protocol.py:151-155), which then covers the windows
+ * [first, first + count) of its scalars (zkb_groth16_pk_msm_info(pk, 3, ...) says how many there are; count may be 0).  That MSM
+ * needs the witness only, so the ranks of a multi-GPU proof that run none of the quotient's transforms take the windows of the
+ * ranks that do (zksnake_b200/dist.py:kw_windows); over all ranks every window must be covered exactly once. */
+int zkb_groth16_pk_set_kw_windows(zkb_groth16_pk* pk, uint32_t first, uint32_t count, int enable);
 /* Optional, host only: start computing the multiples of delta_1 / delta_2 that depend on (r, s) alone on host threads, so that
  * they overlap the GPU work of zkb_groth16_partial; zkb_groth16_assemble picks them up when called with the same r, s (and
  * computes them itself otherwise).  The single-call provers do this internally. */

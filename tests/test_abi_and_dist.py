@@ -214,9 +214,23 @@ def test_chain_spreading_assignment():
             # point-to-point schedule of dist.exchange_chains pairs every send with one receive in the same order on both sides
             h = dist.quotient_owner(ws)
             assert 0 <= h < ws
-            assert masks[h] == 0 if ws >= 4 else bin(masks[h]).count("1") == min(bin(m).count("1") for m in masks)
+            assert masks[h] == 0 if ws >= 4 else masks[h] != 0         # (two ranks: rank 1 transforms everything, rank 0 nothing)
             senders = [(c, owners[c]) for c in range(3) if owners[c] != h]
             assert len(senders) == 3 - bin(masks[h]).count("1")
             for r in range(ws):
                 if r != h:
                     assert [c for c, o in senders if o == r] == [c for c in range(3) if masks[r] >> c & 1]
+        # the [K w] windows: contiguous ranges in rank order that partition [0, W), and a rank that transforms never gets more
+        # windows than one that does not
+        for n_windows in (1, 7, 13, 14, 16, 17):
+            ranges = [dist.kw_windows(r, ws, n_windows) for r in range(ws)]
+            at = 0
+            for first, count in ranges:
+                assert first == at and count >= 0
+                at += count
+            assert at == n_windows
+            if ws >= 2:
+                idle = [ranges[r][1] for r in range(ws) if masks[r] == 0 and r != dist.quotient_owner(ws)]
+                busy = [ranges[r][1] for r in range(ws) if masks[r] != 0]
+                if idle and busy:
+                    assert min(idle) >= max(busy)

@@ -255,6 +255,29 @@ def test_sharded_partials_assemble_to_the_same_proof(gpu, mode, world):
                                                    nat.ptr(oa), nat.ptr(ob), nat.ptr(oc), inf))
         got = gm.Proof(ec.PointG1._from_flat(oa, inf[0]), ec.PointG2._from_flat(ob, inf[1]), ec.PointG1._from_flat(oc, inf[2]))
         assert got.to_bytes() == want, route
+    # uneven shares of the [K w] MSM (what the chain-spreading prover does: ranks that transform nothing take more of its windows,
+    # dist.kw_windows); explicit window ranges per rank, including empty ones, must add up to the same proof
+    if mode == "windows":
+        wins = ctypes.c_uint32()
+        nat.check(nat.lib.zkb_groth16_pk_msm_info(provers[0]._pk_handle, 3, None, ctypes.byref(wins)))
+        for table in ([dist.kw_windows(k, world, wins.value) for k in range(world)],
+                      [(0, 0)] * (world - 1) + [(0, wins.value)],                       # one rank runs it all
+                      [(0, 1)] + [(1, 0)] * (world - 2) + [(1, wins.value + 5)]):       # (counts past the last window are clipped)
+            parts_xy, parts_inf = [], []
+            for g, (first, count) in zip(provers, table):
+                nat.check(nat.lib.zkb_groth16_pk_set_kw_windows(g._pk_handle, first, count, 1))
+                nat.check(nat.lib.zkb_groth16_precompute(g._pk_handle, nat.ptr(lr), nat.ptr(ls)))
+                xy = np.zeros((dist.MSM_SLOTS, dist.SLOT_LIMBS), dtype=np.uint64)
+                flags = np.zeros(dist.MSM_SLOTS, dtype=np.int32)
+                nat.check(nat.lib.zkb_groth16_partial(g._pk_handle, g._r1cs_handle, nat.ptr(w), 0, g.n_public, nat.ptr(xy), nat.ptr(flags)))
+                nat.check(nat.lib.zkb_groth16_pk_set_kw_windows(g._pk_handle, 0, 0, 0))
+                parts_xy.append(xy)
+                parts_inf.append(flags)
+            axy, ainf = np.ascontiguousarray(np.stack(parts_xy)), np.ascontiguousarray(np.stack(parts_inf), dtype=np.int32)
+            nat.check(nat.lib.zkb_groth16_assemble_partials(provers[0]._pk_handle, world, nat.ptr(axy), nat.ptr(ainf), nat.ptr(lr),
+                                                            nat.ptr(ls), nat.ptr(oa), nat.ptr(ob), nat.ptr(oc), inf))
+            got = gm.Proof(ec.PointG1._from_flat(oa, inf[0]), ec.PointG2._from_flat(ob, inf[1]), ec.PointG1._from_flat(oc, inf[2]))
+            assert got.to_bytes() == want, table
     # a mix of folded and plain slots is refused
     ainf[0, 3] &= 1
     rc = nat.lib.zkb_groth16_assemble_partials(provers[0]._pk_handle, world, nat.ptr(axy), nat.ptr(ainf), nat.ptr(lr), nat.ptr(ls),

@@ -87,6 +87,7 @@ def _load():
         "zkb_groth16_pk_build_tables": (c_int, [c_vp, c_u32]),
         "zkb_msm_dev_windows": (c_int, [c_int, c_int, c_vp, c_vp, c_sz, c_u32, c_u32, c_vp, ctypes.POINTER(c_int)]),
         "zkb_groth16_pk_set_window_shard": (c_int, [c_vp, c_u32, c_u32]),
+        "zkb_groth16_pk_set_kw_windows": (c_int, [c_vp, c_u32, c_u32, c_int]),
         "zkb_groth16_pk_msm_info": (c_int, [c_vp, c_int, c_vp, c_vp]),
         "zkb_groth16_precompute": (c_int, [c_vp, c_vp, c_vp]),
         "zkb_batch_mul_dev": (c_int, [c_int, c_int, c_vp, c_int, c_vp, c_sz, c_vp]),

@@ -362,6 +362,8 @@ struct zkb_groth16_pk {
   size_t n, n_kdelta;
   size_t off, len, koff, klen;  // this rank's slice of the n-point vectors / of the n_kdelta-point vector
   uint32_t wrank, wworld;       // window shard of every MSM (0/1 = all windows)
+  bool kw_custom;               // the [K w] MSM runs the windows [kw_first, kw_first + kw_count) instead (zkb_groth16_pk_set_kw_windows)
+  uint32_t kw_first, kw_count;
   zkb_msm_table* tab[4];        // optional fixed-base tables of tau1, tau2, target1, kdelta1 (over this key's slices)
   const void *tau1, *tau2, *target1, *kdelta1;
   uint64_t alpha1[12], beta1[12], beta2[24], delta1[12], delta2[24];
@@ -501,6 +503,14 @@ int zkb_msm_kernel_info(int curve, int group, int* lanes_per_point, int* ctas_pe
   return ZKB_OK;
 }
 
+int zkb_groth16_pk_set_kw_windows(zkb_groth16_pk* pk, uint32_t first, uint32_t count, int enable) {
+  if (!pk || count > 0xffff) return set_error(ZKB_ERR_ARG, "bad [K w] window range");
+  pk->kw_custom = enable != 0;
+  pk->kw_first = first;
+  pk->kw_count = count;
+  return ZKB_OK;
+}
+
 int zkb_groth16_pk_set_window_shard(zkb_groth16_pk* pk, uint32_t rank, uint32_t world) {
   if (!pk || world == 0 || rank >= world) return set_error(ZKB_ERR_ARG, "bad window shard");
   pk->wrank = rank;
@@ -546,7 +556,12 @@ static void groth16_jobs(const zkb_groth16_pk* pk, const void* d_priv, MsmJob jo
     if (t) return MsmJob{group, t->d_table, sc, n, t->c, t->n};
     return MsmJob{group, pts, sc, n, 0, 0};
   };
-  job[groth16_pos(pk, MSM_KW)] = mk(1, 3, pk->kdelta1, (const char*)d_priv + pk->koff * 32, pk->klen);
+  MsmJob& kw = job[groth16_pos(pk, MSM_KW)];
+  kw = mk(1, 3, pk->kdelta1, (const char*)d_priv + pk->koff * 32, pk->klen);
+  if (pk->kw_custom) {
+    kw.own_wrank = pk->kw_first;
+    kw.own_wworld = ZKB_WINDOW_RANGE | pk->kw_count;
+  }
   job[groth16_pos(pk, MSM_B2)] = mk(2, 1, pk->tau2, d_v, pk->len);
   job[groth16_pos(pk, MSM_A)] = mk(1, 0, pk->tau1, d_u, pk->len);
   job[groth16_pos(pk, MSM_B1)] = mk(1, 0, pk->tau1, d_v, pk->len);

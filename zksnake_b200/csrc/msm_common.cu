@@ -32,11 +32,21 @@ DECL(g1bn) DECL(g2bn) DECL(g1bls) DECL(g2bls)
   if (curve == ZKB_BLS12_381 && group == 2) return CALL_BL2;              \
   return set_error(ZKB_ERR_ARG, "unknown (curve, group)");
 
+// Ranks of a multi-GPU proof share one host: with five finishing threads per rank spinning in cudaEventSynchronize (the default
+// for events) eight ranks keep forty cores' worth of threads busy-waiting while other ranks' main threads are still enqueueing
+// kernels.  Once any MSM of the process is a window shard, ticket events are created with cudaEventBlockingSync: the waiters sleep
+// (a few tens of microseconds later to wake, once per MSM) and the cores go to the threads that have work.
+static bool g_blocking_events = false;
 int ticket_reserve(MsmTicket* tk, size_t bytes) {
+  if (tk->event && tk->event_blocking != g_blocking_events) {
+    cudaEventDestroy((cudaEvent_t)tk->event);
+    tk->event = nullptr;
+  }
   if (!tk->event) {
     cudaEvent_t e;
-    ZKB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ZKB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | (g_blocking_events ? cudaEventBlockingSync : 0)));
     tk->event = (void*)e;
+    tk->event_blocking = g_blocking_events;
   }
   if (bytes > tk->host_cap) {
     if (tk->host) ZKB_CUDA(cudaFreeHost(tk->host));
@@ -60,11 +70,14 @@ void ticket_release(MsmTicket* tk) {
 }
 static int msm_need(int curve, const MsmJob& j, uint32_t wr, uint32_t ww, size_t* need) {
   const int group = j.group;
+  wr = job_wrank(j, wr), ww = job_wworld(j, ww);
   DISPATCH(msm_need_g1bn(j.n, wr, ww, j.table_c, j.table_n, need), msm_need_g2bn(j.n, wr, ww, j.table_c, j.table_n, need),
            msm_need_g1bls(j.n, wr, ww, j.table_c, j.table_n, need), msm_need_g2bls(j.n, wr, ww, j.table_c, j.table_n, need))
 }
 static int msm_phase1(int curve, const MsmJob& j, uint32_t wr, uint32_t ww, const MsmTicket* share, MsmTicket* tk) {
   const int group = j.group;
+  wr = job_wrank(j, wr), ww = job_wworld(j, ww);
+  if (ww != 1) g_blocking_events = true;   // a window shard: this process is one of several on the host (ticket_reserve)
   DISPATCH(msm_phase1_g1bn(j.points, j.scalars, j.n, wr, ww, j.table_c, j.table_n, share, tk),
            msm_phase1_g2bn(j.points, j.scalars, j.n, wr, ww, j.table_c, j.table_n, share, tk),
            msm_phase1_g1bls(j.points, j.scalars, j.n, wr, ww, j.table_c, j.table_n, share, tk),
@@ -72,6 +85,8 @@ static int msm_phase1(int curve, const MsmJob& j, uint32_t wr, uint32_t ww, cons
 }
 static int msm_sort(int curve, const MsmJob& j, uint32_t wr, uint32_t ww, const MsmTicket* share, MsmTicket* tk, void* stream) {
   const int group = j.group;
+  wr = job_wrank(j, wr), ww = job_wworld(j, ww);
+  if (ww != 1) g_blocking_events = true;   // a window shard: this process is one of several on the host (ticket_reserve)
   DISPATCH(msm_sort_g1bn(j.scalars, j.n, wr, ww, j.table_c, j.table_n, share, tk, stream),
            msm_sort_g2bn(j.scalars, j.n, wr, ww, j.table_c, j.table_n, share, tk, stream),
            msm_sort_g1bls(j.scalars, j.n, wr, ww, j.table_c, j.table_n, share, tk, stream),

@@ -66,6 +66,7 @@ template <class F> constexpr uint32_t accum_run_threads() { return 148u * AccumF
 // sharding); 0/1 = all windows.
 // table_c / table_n: non-zero when the points come from a fixed-base table built for window size table_c over table_n points.
 inline int msm_choose_window(size_t n, uint32_t scalar_bits, uint32_t wworld, bool table) {
+  if (wworld & ZKB_WINDOW_RANGE) wworld = 1;   // an explicit window range: plan as for the whole MSM
   uint32_t logn = 0;
   while (((size_t)1 << logn) < n) logn++;
   // cost model in units of one mixed addition: every window costs n additions; every bucket ~5 (the bucket reduction is ~2.3
@@ -103,8 +104,14 @@ inline MsmPlan msm_make_plan(size_t n, uint32_t scalar_bits, uint32_t wrank, uin
   if (c > 22) c = 22;
   pl.c = (uint32_t)c;
   pl.nwin_total = (scalar_bits + 1 + pl.c - 1) / pl.c;
-  pl.win0 = pl.nwin_total * wrank / wworld;
-  pl.nwin = pl.nwin_total * (wrank + 1) / wworld - pl.win0;
+  if (wworld & ZKB_WINDOW_RANGE) {   // explicit range [wrank, wrank + count), clipped to the windows there are
+    const uint32_t count = wworld & ~ZKB_WINDOW_RANGE;
+    pl.win0 = wrank < pl.nwin_total ? wrank : pl.nwin_total;
+    pl.nwin = pl.win0 + count <= pl.nwin_total ? count : pl.nwin_total - pl.win0;
+  } else {
+    pl.win0 = pl.nwin_total * wrank / wworld;
+    pl.nwin = pl.nwin_total * (wrank + 1) / wworld - pl.win0;
+  }
   pl.table_n = (uint32_t)table_n;
   pl.bwin = table_n ? (pl.nwin ? 1u : 0u) : pl.nwin;
   pl.nbuck = 1u << (pl.c - 1);
@@ -193,7 +200,7 @@ template <class X>
 inline int msm_geometry(size_t n, uint32_t scalar_bits, uint32_t wrank, uint32_t wworld, uint32_t table_c, size_t table_n,
                         uint32_t run_threads, MsmGeom<X>* g) {
   memset(g, 0, sizeof(*g));
-  if (wworld == 0 || wrank >= wworld) return set_error(ZKB_ERR_ARG, "msm: bad window shard");
+  if (wworld == 0 || (!(wworld & ZKB_WINDOW_RANGE) && wrank >= wworld)) return set_error(ZKB_ERR_ARG, "msm: bad window shard");
   if (n >= ((size_t)1 << 31)) return set_error(ZKB_ERR_ARG, "msm: more than 2^31-1 points");
   if (n == 0) {
     g->skip = true;

@@ -128,13 +128,17 @@ struct MsmTicket {
   unsigned char* host = nullptr;   // pinned
   size_t host_cap = 0;
   void* event = nullptr;           // cudaEvent_t
+  bool event_blocking = false;     // created with cudaEventBlockingSync (msm_common.cu:ticket_reserve)
   bool presorted = false;          // msm_presort ran this ticket's digit sort on a side stream; sort_event marks its end
   void* sort_event = nullptr;      // cudaEvent_t
   alignas(16) unsigned char dev[512];   // MsmDev<X>: plan + device pointers between phase 1 and phase 2
 };
 int ticket_reserve(MsmTicket* tk, size_t bytes);
 void ticket_release(MsmTicket* tk);
-// wrank/wworld: window shard handled by this call (0/1 = the whole MSM); the result is then the partial sum over those windows
+// wrank/wworld: window shard handled by this call (0/1 = the whole MSM); the result is then the partial sum over those windows.
+// wworld = ZKB_WINDOW_RANGE | count selects the explicit window range [wrank, wrank + count) instead of an even share (count may be
+// 0: the job is empty): ranks of a multi-GPU proof that have idle time take more windows of an MSM than the busy ones.
+#define ZKB_WINDOW_RANGE 0x80000000u
 struct MsmJob {
   int group;
   const void* points;     // n affine points, or a fixed-base table (table_n != 0)
@@ -142,7 +146,10 @@ struct MsmJob {
   size_t n;
   uint32_t table_c;       // window size the table was built for (0 = plain points)
   size_t table_n;         // points per window of the table
+  uint32_t own_wrank, own_wworld;   // own_wworld != 0: this job's window shard, overriding the batch's
 };
+inline uint32_t job_wrank(const MsmJob& j, uint32_t batch_wrank) { return j.own_wworld ? j.own_wrank : batch_wrank; }
+inline uint32_t job_wworld(const MsmJob& j, uint32_t batch_wworld) { return j.own_wworld ? j.own_wworld : batch_wworld; }
 // Scratch bytes a batch of these jobs takes from the arena (what msm_enqueue_batch reserves).
 int msm_batch_need(int curve, const MsmJob* jobs, int njobs, uint32_t wrank, uint32_t wworld, size_t* total);
 // The digit sort of one job of a LATER msm_enqueue_batch call, enqueued on `stream` now (its scalars must be complete there); the

@@ -104,11 +104,38 @@ def upload_sharded(arr):
 # the owners transform.  Two ranks: rank 0 takes the U and W chains, rank 1 the V chain and the quotient (4 + 3 transforms).
 _spread_bufs = {}
 _spread_state = {}
+# ZKB_SPREAD_TRACE=1: device timestamps of the exchange steps (ms after the proof's first kernel: own chains done | U, V received |
+# evaluation vectors received | quotient formed | H received | last kernel), kept in SPREAD_TRACE and reported by bench.py
+SPREAD_TRACE = {} if __import__("os").environ.get("ZKB_SPREAD_TRACE", "0") != "0" else None
+
+
+def spread_trace_mark(key):
+    """Record trace event `key` ("start" / "end") on the library stream (no-op unless tracing)."""
+    if SPREAD_TRACE is not None and _spread_state:
+        _spread_state[key].record(library_stream())
+
+
+def spread_trace_collect():
+    """After a proof has completed: add its event times to SPREAD_TRACE (sums; "proofs" counts them)."""
+    st = _spread_state
+    if SPREAD_TRACE is None or "start" not in st:
+        return
+    rank, ws = world()
+    keys = ["chains", "uv", "h", "end"] + (["recv", "quot"] if rank == quotient_owner(ws) else [])
+    try:
+        st["end"].synchronize()
+        st["h"].synchronize()
+        for k in keys:
+            SPREAD_TRACE[k] = SPREAD_TRACE.get(k, 0.0) + st["start"].elapsed_time(st[k])
+        SPREAD_TRACE["proofs"] = SPREAD_TRACE.get("proofs", 0) + 1
+    except Exception:       # (the first proof creates the events after "start" would have been recorded)
+        pass
 
 
 def chain_owner(chain, world_size):
-    """Rank that runs chain 0 (U), 1 (V) or 2 (W).  Three or more ranks: one chain each; two ranks: rank 0 takes U and W."""
-    return chain % world_size if world_size >= 3 else (0, 1 % world_size, 0)[chain]
+    """Rank that runs chain 0 (U), 1 (V) or 2 (W).  Three or more ranks: one chain each; two ranks: rank 1 runs all three (and the
+    quotient) while rank 0 runs most of the [K w] MSM, which needs the witness only (kw_windows)."""
+    return chain % world_size if world_size >= 3 else world_size - 1
 
 
 def chain_mask(rank, world_size):
@@ -117,8 +144,35 @@ def chain_mask(rank, world_size):
 
 def quotient_owner(world_size):
     """Rank that forms H from the three coset evaluation vectors: the first rank without a chain (four ranks or more), else the
-    rank with the least transform work (the W owner of three ranks, the V owner of two)."""
+    last chain owner (nothing to send on two ranks)."""
     return 3 if world_size >= 4 else world_size - 1
+
+
+# Rough device times of one proof's stages in units of ONE window of the [K w] MSM (2^20 BN254: ~0.2 ms; all of them scale with the
+# domain size together, so only the ratios matter): one interpolation -> coset-evaluation chain, the wait for U and V behind it, the
+# quotient's last step, one evaluation vector received for it.
+# Fitted on the B200 boxes: 2 GPUs -- 14 / 2 windows left rank 1 0.4 ms early (profiles/R3b_n2_spread1.json); 4 GPUs -- the even
+# 4 / 4 / 4 / 4 is balanced to 0.1 ms and a fifth window on the quotient rank makes it the slowest (R2z_n4_spread1, R3c_n4).
+_CHAIN_COST, _UV_WAIT_COST, _QUOTIENT_COST, _RECV_COST = 2.6, 1.0, 1.6, 0.5
+
+
+def kw_windows(rank, world_size, n_windows):
+    """(first, count): the windows of the [K w] MSM that `rank` runs when the transform chains are spread over the ranks.  That MSM
+    needs the witness only, so it is what a rank does while it has nothing else: the windows are dealt one by one to the rank
+    whose modelled busy time (chains, the wait for U and V, the quotient) is lowest, and laid out as contiguous ranges in rank
+    order.  Every rank computes the same table; the ranges partition [0, n_windows)."""
+    busy = []
+    for r in range(world_size):
+        chains = bin(chain_mask(r, world_size)).count("1")
+        b = chains * _CHAIN_COST + (_UV_WAIT_COST if chains else 0.0)
+        if r == quotient_owner(world_size) and world_size > 1:
+            b += _QUOTIENT_COST + _RECV_COST * (3 - chains)
+        busy.append(b)
+    count = [0] * world_size
+    for _ in range(n_windows):
+        r = min(range(world_size), key=lambda k: (busy[k] + count[k], k))
+        count[r] += 1
+    return sum(count[:rank]), count[rank]
 
 
 def spread_buffers(n_elems):
@@ -146,29 +200,42 @@ def exchange_chains(coeffs, evals, hbuf, n_elems, run_quotient):
     h = quotient_owner(ws)
     st = _spread_state
     if not st:
+        trace = SPREAD_TRACE is not None
         st["comm"] = torch.cuda.Stream()
-        st["chains"] = torch.cuda.Event()
-        st["h"] = torch.cuda.Event()
+        st["chains"] = torch.cuda.Event(enable_timing=trace)
+        st["h"] = torch.cuda.Event(enable_timing=trace)
+        if trace:
+            for k in ("start", "uv", "recv", "quot", "end"):
+                st[k] = torch.cuda.Event(enable_timing=True)
+    mark = (lambda k: st[k].record(lib)) if SPREAD_TRACE is not None else (lambda k: None)
     st["chains"].record(lib)                       # this rank's chains are complete here (before the broadcasts queue up)
     with torch.cuda.stream(lib):
         for c in (0, 1):
             td.broadcast(coeffs[c * nb:(c + 1) * nb], src=chain_owner(c, ws))
+    mark("uv")
     senders = [(c, chain_owner(c, ws)) for c in range(3) if chain_owner(c, ws) != h]
+    # the evaluation vectors travel as ONE batch of point-to-point operations per rank (unbatched send / recv calls are serialised
+    # with everything else on the communicator: three receives took 0.86 ms on 8 x B200, profiles/R3d_n8_trace.json)
     if rank == h:
         with torch.cuda.stream(lib):
-            for c, o in senders:
-                td.recv(evals[c * nb:(c + 1) * nb], src=o)
+            if senders:
+                for work in td.batch_isend_irecv([td.P2POp(td.irecv, evals[c * nb:(c + 1) * nb], o) for c, o in senders]):
+                    work.wait()
+            mark("recv")
             try:
                 run_quotient()
             finally:
+                mark("quot")
                 td.broadcast(hbuf, src=h)          # (issued even if the quotient failed: the other ranks are already waiting in it)
+        st["h"].record(lib)
         return None
     comm = st["comm"]
     with torch.cuda.stream(comm):
         comm.wait_event(st["chains"])
-        for c, o in senders:
-            if o == rank:
-                td.send(evals[c * nb:(c + 1) * nb], dst=h)
+        mine = [td.P2POp(td.isend, evals[c * nb:(c + 1) * nb], h) for c, o in senders if o == rank]
+        if mine:
+            for work in td.batch_isend_irecv(mine):
+                work.wait()
         td.broadcast(hbuf, src=h)
         st["h"].record(comm)
     return st["h"].cuda_event
@@ -226,6 +293,7 @@ class HostExchange:
 
     def all_gather(self, payload):
         """payload: uint8 array of at most SLOT bytes, same length on every rank -> (world, len) uint8 array"""
+        import os
         import time
         n = payload.size
         assert n <= self.SLOT
@@ -240,6 +308,7 @@ class HostExchange:
             spins = 0
             while seq[0] != self.round:
                 spins += 1
+                os.sched_yield()       # (the ranks share the host's cores: let a rank that still enqueues kernels have this one)
                 if spins & 0xFFFF == 0 and time.monotonic() > deadline:
                     raise RuntimeError(f"rank {self.rank}: no partial sums from rank {r} after 120 s")
             out[r] = self._data[r][b][:n]

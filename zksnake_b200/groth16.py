@@ -167,6 +167,7 @@ class Groth16:
         self._bound_key = None
         self._staging = None
         self.phase_ms = {}
+        self._kw_windows = None
         self._staging_ptr = None
 
     # ------------------------------------------------------------------------------------------------ setup
@@ -271,6 +272,7 @@ class Groth16:
                                                         hi - lo, pk.kdelta_1.ptr, self.m - self.n_public, klo, khi - klo,
                                                         *[nat.ptr(s) for s in singles], ctypes.byref(h)))
         self._pk_handle = h
+        self._kw_windows = None
         self._singles = singles
         if self.shard_mode == "windows" and self.world > 1:
             nat.check(nat.lib.zkb_groth16_pk_set_window_shard(h, self.rank, self.world))
@@ -345,10 +347,13 @@ class Groth16:
             nat.check(nat.lib.zkb_groth16_precompute(self._pk_handle, nat.ptr(rr), nat.ptr(ss)))   # host threads, under the GPU work
             xy = np.zeros((dist.MSM_SLOTS, dist.SLOT_LIMBS), dtype=np.uint64)
             flags = np.zeros(dist.MSM_SLOTS, dtype=np.int32)
-            if self._spread_chains():
+            spread = self._spread_chains()
+            self._set_kw_windows(spread)
+            if spread:
                 # the three transform chains on three ranks (two: 2 + 1), the quotient's last step on one; dist.exchange_chains
                 coeffs, evals, hbuf = dist.spread_buffers(self.n)
                 pc, pe, ph = (ctypes.c_void_p(t.data_ptr()) for t in (coeffs, evals, hbuf))
+                dist.spread_trace_mark("start")
                 nat.check(nat.lib.zkb_groth16_spread_begin(self._pk_handle, self._r1cs_handle, wptr, int(on_dev), self.n_public,
                                                            dist.chain_mask(self.rank, self.world), pc, pe))
                 h_ready = dist.exchange_chains(
@@ -356,6 +361,8 @@ class Groth16:
                     lambda: nat.check(nat.lib.zkb_groth16_spread_quotient(self._pk_handle, pe, ph)))
                 nat.check(nat.lib.zkb_groth16_spread_finish(self._pk_handle, self._r1cs_handle, self.n_public, pc, ph,
                                                             ctypes.c_void_p(h_ready), nat.ptr(xy), nat.ptr(flags)))
+                dist.spread_trace_mark("end")
+                dist.spread_trace_collect()
             else:
                 nat.check(nat.lib.zkb_groth16_partial(self._pk_handle, self._r1cs_handle, wptr, int(on_dev), self.n_public,
                                                       nat.ptr(xy), nat.ptr(flags)))
@@ -375,14 +382,29 @@ class Groth16:
         ec = self.ec
         return Proof(ec.PointG1._from_flat(oa, inf[0]), ec.PointG2._from_flat(ob, inf[1]), ec.PointG1._from_flat(oc, inf[2]))
 
+    def _set_kw_windows(self, spread):
+        """With the chains spread, the ranks that transform nothing run more windows of the [K w] MSM than the ones that do
+        (dist.kw_windows); otherwise every MSM is cut evenly.  Needs the fixed-base tables (they fix the window count)."""
+        # Measured on the B200 boxes (profiles/R3b_*, R3c_*): 2 GPUs 14.45 -> 14.08 ms; 4 GPUs 8.51 -> 8.92 and 8 GPUs 6.57 -> 6.71 --
+        # there the ranks without a chain are not idle for as long as the model says, so only two ranks use it (ZKB_KW_UNEVEN=1 / 0
+        # forces it on / off).
+        mode = os.environ.get("ZKB_KW_UNEVEN", "auto")
+        uneven = spread and (mode == "1" or (mode == "auto" and self.world == 2))
+        want = None
+        if uneven and self.tables and self.m - self.n_public > 0:
+            wins = ctypes.c_uint32()
+            nat.check(nat.lib.zkb_groth16_pk_msm_info(self._pk_handle, 3, None, ctypes.byref(wins)))
+            want = dist.kw_windows(self.rank, self.world, wins.value)
+        if want != self._kw_windows:
+            nat.check(nat.lib.zkb_groth16_pk_set_kw_windows(self._pk_handle, *(want or (0, 0)), int(want is not None)))
+            self._kw_windows = want
+
     def _spread_chains(self):
         """Run the quotient's three transform chains on different ranks?  Needs the NCCL world this prover shards over, whole key
         vectors on every rank (window sharding) and a domain large enough for a broadcast to be cheaper than a transform."""
         if os.environ.get("ZKB_NTT_SPREAD", "1") == "0" or self._emulate or self.shard_mode != "windows":
             return False
-        # (two ranks: measured both ways -- rank 0 runs two chains either way and the rank that forms H joins the MSMs late; 14.5 ms
-        # replicated, 14.5 ms with five broadcasts, 15.8 ms with the quotient on rank 1 -- so the chains stay replicated there)
-        return self.world > 2 and dist.nccl_ready() and self.n >= (1 << 16)
+        return self.world > 1 and dist.nccl_ready() and self.n >= (1 << 16)
 
     def last_polys(self):
         """U, V, H coefficient lists of the last prove (n entries each, unstripped) for parity tests."""

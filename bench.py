@@ -576,6 +576,8 @@ def main_own(args):
                        "window_bits": int(c2_c.value), "windows": int(c2_w.value), "lanes_per_point": lanes.value,
                        "ctas_per_sm": ctas.value, "executed_ops_per_addition": add_ops,
                        "executed_ops_per_point": int(c2_w.value) * add_ops, "launch_ms": per2, "launches": g2_cnt,
+                       "traffic": (traffic.get("msm_accumulate_pair_kernel") or {}).get("dram_bytes") if lanes.value == 2 else None,
+                       "traffic_detail": traffic.get("msm_accumulate_pair_kernel") if lanes.value == 2 else None,
                        "share_of_step": g2_ms / args.steps / dev_ms}
     ntt_ms, ntt_cnt = prof["ntt"]
     roofline_ntt = None

@@ -62,7 +62,11 @@ def main(tag):
         f.write("kernel,launches,total_us,share\n")
         for k, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"\"{k[:110]}\",{c},{v / 1e3:.1f},{v / total:.4f}\n")
-    traffic = {}
+    try:        # entries of other kernels / earlier captures stay (bench.py reads all of them)
+        with open(os.path.join(PROF, "traffic.json")) as f:
+            traffic = json.load(f)
+    except (OSError, ValueError):
+        traffic = {}
     for fn in sorted(os.listdir(OUT)):
         if not (fn.startswith(f"full_{tag}_") and fn.endswith(".csv")):
             continue

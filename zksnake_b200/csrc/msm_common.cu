@@ -1,5 +1,6 @@
 // msm_common.cu -- (curve, group) dispatch for the MSM and point-vector entry points.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 #include "zkb_internal.h"
 
@@ -32,10 +33,11 @@ DECL(g1bn) DECL(g2bn) DECL(g1bls) DECL(g2bls)
   if (curve == ZKB_BLS12_381 && group == 2) return CALL_BL2;              \
   return set_error(ZKB_ERR_ARG, "unknown (curve, group)");
 
-// Ranks of a multi-GPU proof share one host: with five finishing threads per rank spinning in cudaEventSynchronize (the default
-// for events) eight ranks keep forty cores' worth of threads busy-waiting while other ranks' main threads are still enqueueing
-// kernels.  Once any MSM of the process is a window shard, ticket events are created with cudaEventBlockingSync: the waiters sleep
-// (a few tens of microseconds later to wake, once per MSM) and the cores go to the threads that have work.
+// Ranks of a multi-GPU proof share one host: five finishing threads per rank spin in cudaEventSynchronize (the default for events)
+// while other ranks' main threads may still be enqueueing kernels.  ZKB_BLOCKING_EVENTS=1 creates the ticket events of window
+// shards with cudaEventBlockingSync, so that the waiters sleep.  OFF by default -- measured on the B200 boxes (32 host cores): 8
+// ranks 6.58 ms either way, 2 ranks 13.87 ms spinning against 14.27 ms sleeping (the wake-up latency lands on the proof's tail,
+// profiles/R3g_n2_*.json); for hosts with fewer cores than 6 x ranks.
 static bool g_blocking_events = false;
 int ticket_reserve(MsmTicket* tk, size_t bytes) {
   if (tk->event && tk->event_blocking != g_blocking_events) {
@@ -77,7 +79,8 @@ static int msm_need(int curve, const MsmJob& j, uint32_t wr, uint32_t ww, size_t
 static int msm_phase1(int curve, const MsmJob& j, uint32_t wr, uint32_t ww, const MsmTicket* share, MsmTicket* tk) {
   const int group = j.group;
   wr = job_wrank(j, wr), ww = job_wworld(j, ww);
-  if (ww != 1) g_blocking_events = true;   // a window shard: this process is one of several on the host (ticket_reserve)
+  static const bool blocking_ok = [] { const char* e = getenv("ZKB_BLOCKING_EVENTS"); return e && atoi(e) != 0; }();
+  if (ww != 1 && blocking_ok) g_blocking_events = true;   // a window shard: this process is one of several on the host (ticket_reserve)
   DISPATCH(msm_phase1_g1bn(j.points, j.scalars, j.n, wr, ww, j.table_c, j.table_n, share, tk),
            msm_phase1_g2bn(j.points, j.scalars, j.n, wr, ww, j.table_c, j.table_n, share, tk),
            msm_phase1_g1bls(j.points, j.scalars, j.n, wr, ww, j.table_c, j.table_n, share, tk),
@@ -86,7 +89,8 @@ static int msm_phase1(int curve, const MsmJob& j, uint32_t wr, uint32_t ww, cons
 static int msm_sort(int curve, const MsmJob& j, uint32_t wr, uint32_t ww, const MsmTicket* share, MsmTicket* tk, void* stream) {
   const int group = j.group;
   wr = job_wrank(j, wr), ww = job_wworld(j, ww);
-  if (ww != 1) g_blocking_events = true;   // a window shard: this process is one of several on the host (ticket_reserve)
+  static const bool blocking_ok = [] { const char* e = getenv("ZKB_BLOCKING_EVENTS"); return e && atoi(e) != 0; }();
+  if (ww != 1 && blocking_ok) g_blocking_events = true;   // a window shard: this process is one of several on the host (ticket_reserve)
   DISPATCH(msm_sort_g1bn(j.scalars, j.n, wr, ww, j.table_c, j.table_n, share, tk, stream),
            msm_sort_g2bn(j.scalars, j.n, wr, ww, j.table_c, j.table_n, share, tk, stream),
            msm_sort_g1bls(j.scalars, j.n, wr, ww, j.table_c, j.table_n, share, tk, stream),

@@ -14,5 +14,10 @@ built here (no Rust toolchain).  What *is* pinned (tests/test_oracle_pins.py):
   * the published constants (roots of unity, Montgomery constants, curve generators and the
     standard Zcash/IETF compressed encodings of the BLS12-381 generators),
   * algebraic identities (NTT by definition, H*Z == U*V-W, MSM == discrete-log closed form,
-    Groth16 verification equation through an independent pairing implementation).
+    Groth16 verification equation through an independent pairing implementation),
+  * ONE outside anchor the reference's own tests do hold: the five Poseidon hashes over BN254's
+    Fr of /root/reference/tests/test_gadgets.py:19-50 (Hades reference code, circomlib) --
+    oracle/poseidon.py, tests/test_poseidon_kat.py.  They pin Fr addition and multiplication
+    (ints, the host build of csrc/ff.cuh, the device) to implementations independent of this
+    repository; NTT, MSM and encodings stay unpinned in the contract's sense.
 """

@@ -328,7 +328,7 @@ int zkb_groth16_h_dev(int curve, uint32_t log_n, const void* d_a, const void* d_
                       void* d_w, void* d_h, int check) {
   NEED_INIT();
   CHECK_CURVE(curve);
-  return groth16_h_dev(curve, log_n, d_a, d_b, d_c, d_u, d_v, d_w, d_h, check);
+  return groth16_h_dev(curve, log_n, d_a, d_b, d_c, d_u, d_v, d_w, d_h, check ? 1 : 0);   // (the deferred mode is internal)
 }
 
 int zkb_groth16_h(int curve, uint32_t log_n, const uint64_t* a, const uint64_t* b, const uint64_t* c, uint64_t* u,

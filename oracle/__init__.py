@@ -19,5 +19,7 @@ built here (no Rust toolchain).  What *is* pinned (tests/test_oracle_pins.py):
     Fr of /root/reference/tests/test_gadgets.py:19-50 (Hades reference code, circomlib) --
     oracle/poseidon.py, tests/test_poseidon_kat.py.  They pin Fr addition and multiplication
     (ints, the host build of csrc/ff.cuh, the device) to implementations independent of this
-    repository; NTT, MSM and encodings stay unpinned in the contract's sense.
+    repository; NTT, MSM and encodings stay unpinned in the contract's sense.  The reference's
+    fixture tests/stub/test_poseidon.r1cs (circom-compiled Poseidon(3)) carries the same anchor to
+    the .r1cs reader and the row semantics (oracle/circom.py).
 """

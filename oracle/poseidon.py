@@ -22,7 +22,7 @@ schedule runs on Python ints, on the host build of csrc/ff.cuh and on the GPU (t
 from .fields import BN254, PARAMS
 
 # (t, R_F, R_P) of the instances the vectors use (the paper's table for alpha = 5, 254-bit fields; circomlib's N_ROUNDS_P)
-INSTANCES = {3: (8, 57), 5: (8, 60), 6: (8, 60)}
+INSTANCES = {3: (8, 57), 4: (8, 56), 5: (8, 60), 6: (8, 60)}
 
 # /root/reference/tests/test_gadgets.py:19-50: (inputs, expected hash)
 REFERENCE_VECTORS = [

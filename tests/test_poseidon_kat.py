@@ -9,11 +9,17 @@ limb anywhere changes the result -- goes through
   * on the B200: the same text compiled for the device (zkb_test_field_op_dev) and the product's element-wise kernel
     (zkb_vec_op -> vec_op_kernel, the F4 row of SURVEY.md section 8: mul / add_over_evaluation_domain).
 """
+import os
+import random
+
 import numpy as np
 import pytest
 
-from oracle import poseidon
+from oracle import circom, poseidon
 from oracle.fields import BN254, PARAMS
+
+# byte copy of /root/reference/tests/stub/test_poseidon.r1cs (circomlib Poseidon(3), compiled by circom 2.1.6); see oracle/circom.py
+CIRCOM_POSEIDON3 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "circom_poseidon3.r1cs")
 
 R = PARAMS[BN254].r
 FR_BN254 = 0          # field id of the self-test hooks (include/zkb200.h: 0 FrBN254)
@@ -105,3 +111,64 @@ def test_reference_vectors_host_build_of_the_gpu_multiplier(native, inputs, expe
 def test_reference_vectors_on_the_device(gpu, inputs, expected):
     assert poseidon.poseidon_hash(inputs, HookBackend(gpu, gpu.lib.zkb_test_field_op_dev)) == expected
     assert poseidon.poseidon_hash(inputs, VecOpBackend(gpu)) == expected
+
+
+# ---- the circom-compiled Poseidon(3) circuit of the reference's test fixtures -------------------------------------------------
+def _circom_circuit_and_witness(inputs):
+    from zksnake_b200 import r1cs as rm
+    circuit, header = rm.read_r1cs_file(CIRCOM_POSEIDON3)
+    first_input = 1 + header["n_pub_out"] + header["n_pub_in"]
+    witness = circom.forward_witness(circuit.A.triplets, circuit.B.triplets, circuit.C.triplets, header["m_constraints"],
+                                     header["n_wires"], {first_input + k: v for k, v in enumerate(inputs)}, R)
+    return circuit, header, witness
+
+
+def test_reader_on_a_real_circom_file_and_poseidon_through_its_constraints():
+    """zksnake_b200.r1cs.read_r1cs_file on a file circom wrote (every other reader test uses files this repository wrote itself):
+    header fields, wire order [1, h, a, b, c, intermediates], and -- solving the 261 rows forward from (a, b, c) -- wire h equals
+    the Poseidon hash computed from the Grain-generated parameters (t = 4), i.e. the coefficients in the file are circomlib's
+    constants and the rows mean <A,w> * <B,w> = <C,w>.  The product's own SparseArray.dot agrees row by row."""
+    rnd = random.Random(7)
+    for inputs in ([1, 2, 3], [0, 0, 0], [R - 1, 5, R - 2], [rnd.randrange(R) for _ in range(3)]):
+        circuit, header, w = _circom_circuit_and_witness(inputs)
+        assert (header["n_wires"], header["m_constraints"], header["n_pub_out"], header["n_pub_in"], header["n_priv_in"]) == (265, 261, 1, 0, 3)
+        assert circuit.n_public == 2 and circuit.A.n_col == 265
+        assert w[0] == 1 and w[2:5] == [v % R for v in inputs]
+        assert w[1] == poseidon.poseidon_hash(inputs, poseidon.IntBackend())
+        az, bz, cz = circuit.A.dot(w), circuit.B.dot(w), circuit.C.dot(w)
+        assert all(x * y % R == z for x, y, z in zip(az, bz, cz))
+    # (a, b, c) = (1, 2, 3): the value both routes agree on, for the record
+    _, _, w = _circom_circuit_and_witness([1, 2, 3])
+    assert w[1] == 6542985608222806190361240322586112750744169038454362455181422643027100751666
+    # a wrong witness is caught by the same row check
+    w[7] = (w[7] + 1) % R
+    circuit, _, _ = _circom_circuit_and_witness([1, 2, 3])
+    assert any(x * y % R != z for x, y, z in zip(circuit.A.dot(w), circuit.B.dot(w), circuit.C.dot(w)))
+
+
+@pytest.mark.gpu
+def test_groth16_over_the_circom_poseidon_circuit(gpu):
+    """Groth16 setup / prove / verify on the B200 over the circom-compiled circuit with the forward-solved witness: device SpMV over
+    a real circom constraint system, proof bytes == the oracle's closed form, verify() passes and rejects a wrong public output."""
+    from oracle import groth16 as og
+    from zksnake_b200 import groth16 as gm
+    circuit, header, w = _circom_circuit_and_witness([1, 2, 3])
+    pub, priv = w[:circuit.n_public], w[circuit.n_public:]
+    rnd = random.Random(11)
+    toxic = [rnd.randint(1, R - 1) for _ in range(5)]
+    rr, ss = rnd.randint(1, R - 1), rnd.randint(1, R - 1)
+    st = og.Setup(BN254, list(circuit.A.triplets), list(circuit.B.triplets), list(circuit.C.triplets), header["m_constraints"],
+                  circuit.A.n_col, circuit.n_public, tuple(toxic))
+    prover = gm.Groth16(circuit, "BN254")
+    seq = iter(toxic + [rr, ss])
+    old = gm.get_random_int
+    gm.get_random_int = lambda n_max: next(seq)
+    try:
+        prover.setup()
+        proof = prover.prove(pub, priv)
+    finally:
+        gm.get_random_int = old
+    A, B, C = og.prove_closed_form(st, w, rr, ss)
+    assert proof.to_bytes() == og.proof_bytes(BN254, A, B, C)
+    assert prover.verify(proof, pub)
+    assert not prover.verify(proof, [pub[0], (pub[1] + 1) % R])

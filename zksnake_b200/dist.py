@@ -8,6 +8,7 @@ the slice sums add up to the same group element and the proof bytes do not depen
 rank (< 1 KiB).
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -106,7 +107,7 @@ _spread_bufs = {}
 _spread_state = {}
 # ZKB_SPREAD_TRACE=1: device timestamps of the exchange steps (ms after the proof's first kernel: own chains done | U, V received |
 # evaluation vectors received | quotient formed | H received | last kernel), kept in SPREAD_TRACE and reported by bench.py
-SPREAD_TRACE = {} if __import__("os").environ.get("ZKB_SPREAD_TRACE", "0") != "0" else None
+SPREAD_TRACE = {} if os.environ.get("ZKB_SPREAD_TRACE", "0") != "0" else None
 
 
 def spread_trace_mark(key):
@@ -262,7 +263,6 @@ class HostExchange:
         self.rank, self.ws = world()
         name = [None]
         if self.rank == 0:
-            import os
             name[0] = f"zkb200_{os.getpid()}_{int.from_bytes(os.urandom(4), 'little')}"
             self.shm = shared_memory.SharedMemory(name=name[0], create=True, size=self.ws * 2 * (self.SLOT + 64))
             self.shm.buf[:] = bytes(len(self.shm.buf))
@@ -293,7 +293,6 @@ class HostExchange:
 
     def all_gather(self, payload):
         """payload: uint8 array of at most SLOT bytes, same length on every rank -> (world, len) uint8 array"""
-        import os
         import time
         n = payload.size
         assert n <= self.SLOT
@@ -321,7 +320,6 @@ _host_exchange = None
 def host_exchange():
     """The node-local mailbox, created on first use (None when the job spans several nodes or shared memory is unavailable)."""
     global _host_exchange
-    import os
     if _host_exchange is None:
         local = int(os.environ.get("LOCAL_WORLD_SIZE", "0") or 0)
         rank, ws = world()

@@ -13,6 +13,8 @@
  *   zkb_batch_mul_dev                src/bn254/curve.rs:326-354 batch_multi_scalar_g1/g2 (setup side)
  *   zkb_groth16_h / _h_dev           python/zksnake/groth16/qap.py:42-71 QAP.evaluate_witness (after the A.w/B.w/C.w dots)
  *   zkb_groth16_pk_* / _prove        python/zksnake/groth16/protocol.py:115-165 Groth16.prove
+ *   zkb_groth16_partial / _spread_* / _assemble(_partials)   the same two calls (qap.py:42-71, protocol.py:133-165) cut where the
+ *                                    ranks of a multi-GPU proof exchange data (the reference has no multi-device path)
  *   zkb_r1cs_create / _eval(_dev)    python/zksnake/array.py:36-43 SparseArray.dot (x3: groth16/qap.py:53-55); over the transposed
  *                                    matrices: the L/R/O loop of Groth16.setup (groth16/protocol.py:64-77)
  *   zkb_fr_*_dev, zkb_plonk_*        the Polynomial / list glue of python/zksnake/plonk/protocol.py:270-466

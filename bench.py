@@ -615,7 +615,8 @@ def main_own(args):
         "metric": metric_name(args), "value": dev_ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": wall_ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32 limbs (int32 pipe)", "data": "synthetic",
-        "config": workload_config(args), "parallelism": f"msm-{args.shard_mode}-shard{world}",
+        "config": workload_config(args),
+        "parallelism": f"msm-{args.shard_mode}-shard{world}" + ("+quotient-chains-spread" if world > 1 and prover._spread_chains() else ""),
         "timing": "CUDA events on the library stream around the K steps (value); wall clock between barriers (ms_per_step, e2e)",
         "clocks": clocks,
         "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),

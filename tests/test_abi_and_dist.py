@@ -234,3 +234,41 @@ def test_chain_spreading_assignment():
                 busy = [ranges[r][1] for r in range(ws) if masks[r] != 0]
                 if idle and busy:
                     assert min(idle) >= max(busy)
+
+
+def test_add_partials_masks_and_carries_the_folded_marker(native):
+    """Bit 1 of the HZ slot's flag says that a rank folded s [U]_i + r [V]_i into that slot (include/zkb200.h).  The Python slot
+    sums (host group law, no GPU) must treat it as a marker, not as "infinity", hand it on when EVERY rank set it and refuse a mix."""
+    import random
+
+    import numpy as np
+
+    from oracle import cport
+    from zksnake_b200 import dist
+    curve, ws = 0, 3
+    rnd = random.Random(9)
+    n = 8
+    xy = np.zeros((ws, dist.MSM_SLOTS, dist.SLOT_LIMBS), dtype=np.uint64)
+    inf = np.zeros((ws, dist.MSM_SLOTS), dtype=np.int32)
+    want = []
+    for slot, grp in enumerate(dist.SLOT_GROUP):
+        pts = cport.chain_points(curve, grp, 5 + slot, n * ws)
+        scal = cport.pack([rnd.randrange(1, 1 << 64) for _ in range(n * ws)])
+        for k in range(ws):
+            part, pinf = cport.msm(curve, grp, pts[k * n:(k + 1) * n], scal[k * n:(k + 1) * n])
+            xy[k, slot, :len(part)] = part
+            inf[k, slot] = int(pinf)
+        want.append(cport.msm(curve, grp, pts, scal))
+    plain_xy, plain_inf = dist.add_partials(curve, xy, inf)
+    for slot, grp in enumerate(dist.SLOT_GROUP):
+        limbs = cport.affine_limbs(curve, grp)
+        assert (plain_xy[slot, :limbs] == want[slot][0]).all() and int(plain_inf[slot]) == int(want[slot][1])
+    folded = inf.copy()
+    folded[:, 3] |= 2
+    f_xy, f_inf = dist.add_partials(curve, xy, folded)
+    assert (f_xy == plain_xy).all() and int(f_inf[3]) == (int(plain_inf[3]) | 2)
+    assert [int(v) for k, v in enumerate(f_inf) if k != 3] == [int(v) for k, v in enumerate(plain_inf) if k != 3]
+    mixed = folded.copy()
+    mixed[1, 3] &= 1
+    with pytest.raises(ValueError, match="folded"):
+        dist.add_partials(curve, xy, mixed)
